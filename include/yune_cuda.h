@@ -1,0 +1,127 @@
+/* yune_cuda.h -- the drop-in boundary: a C ABI that replaces the reference's CLManager + kernel launch.
+ *
+ * The reference has no FFI; its seam is (1) the public methods of yune::CLManager as called by
+ * RendererCore/RendererGUI (include/CLManager.h:50-88) and (2) the OpenCL kernel-argument contract
+ * (template/kernel.cl:66-68, set at src/RendererCore.cpp:202-236, 284, 516-577).  Every entry point below
+ * names the reference interface it stands in for.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions (the C rendering of the reference's "bool + GUI message" protocol, src/CLManager.cpp:261-265):
+ *   - every call returns 0 on success or a negative YUNE_ERR_* code; the text is at yune_last_error();
+ *   - no exception crosses the boundary; a context is NOT thread-safe (the reference is single-threaded,
+ *     include/CLManager.h:40-42);
+ *   - host buffers passed in are copied before the call returns (CL_MEM_COPY_HOST_PTR semantics,
+ *     src/CLManager.cpp:428, 451, 475); the caller keeps ownership;
+ *   - images are RGBA float32, row 0 = bottom row (GL renderbuffer convention, udpt.cl:220);
+ *   - there is no CPU fallback: with no usable sm_100 device yune_setup fails.
+ */
+#ifndef YUNE_CUDA_H
+#define YUNE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "yune_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YUNE_OK            0
+#define YUNE_ERR_INVALID  -1   /* bad argument / null pointer / size mismatch            */
+#define YUNE_ERR_CUDA     -2   /* a CUDA runtime call failed (text has file:line + name) */
+#define YUNE_ERR_STATE    -3   /* call made before the buffers it needs were set up      */
+#define YUNE_ERR_LIMIT    -4   /* scene exceeds a documented limit (BVH depth, lights)   */
+#define YUNE_ERR_NODEVICE -5   /* no CUDA device / not a Blackwell (sm_100) GPU          */
+
+typedef struct yune_ctx yune_ctx;
+
+/* ---- CLManager::setup() (src/CLManager.cpp:118-156): pick the device, create the context/queue ---- */
+int  yune_setup(int device, yune_ctx** out_ctx);
+void yune_destroy(yune_ctx* ctx);                      /* ~CLManager (src/CLManager.cpp:83-111) */
+/* CLManager::checkError text (src/CLManager.cpp:755-855); ctx may be NULL for a failed yune_setup. */
+const char* yune_last_error(const yune_ctx* ctx);
+
+/* ---- CLManager::createRenderProgram(fn, path, reload) (src/CLManager.cpp:158-268) ----
+ * There is no run-time compilation.  `kernel` selects a built-in integrator by the reference's file
+ * name: "udpt.cl" | "udpt" (kernels/legacy/udpt.cl) or "bdpt.cl" | "bdpt" (kernels/legacy/bdpt.cl).
+ * `compiler_opts` is the one-token '#yune-preproc compiler-opts' string (src/CLManager.cpp:182-204):
+ * "-DMIS" enables udpt.cl's #ifdef MIS branch (udpt.cl:9, 566-608); NULL or "" = none.
+ * Selecting a program also installs that kernel's built-in __constant light_sources[] (udpt.cl:97-106 /
+ * bdpt.cl:106-115) unless yune_set_light_sources was called. */
+int yune_create_render_program(yune_ctx* ctx, const char* kernel, const char* compiler_opts);
+/* CLManager::createPostProcProgram (src/CLManager.cpp:270-379): only "tonemap.cl" | "tonemap" exists. */
+int yune_create_postproc_program(yune_ctx* ctx, const char* kernel, const char* compiler_opts);
+
+/* ---- buffer set-up: CLManager::setup*Buffer (src/CLManager.cpp:381-484) = kernel args 2-7 ---- */
+int yune_setup_vertex_buffer(yune_ctx* ctx, const yune_triangle* tris, int n_triangles);   /* args 3,4 */
+int yune_setup_mat_buffer(yune_ctx* ctx, const yune_material* mats, int n_materials);      /* arg 5    */
+int yune_setup_bvh_buffer(yune_ctx* ctx, const yune_bvh_node* nodes, int n_nodes);         /* args 6,7; n = 0: no BVH is NOT supported (udpt.cl:280-284 brute force) */
+int yune_setup_camera_buffer(yune_ctx* ctx, const yune_cam* cam);                          /* arg 2    */
+int yune_setup_image_buffers(yune_ctx* ctx, int width, int height);                        /* args 0,1 */
+/* Replaces the kernels' __constant Quad light_sources[LIGHT_SIZE]; n in [1, 8].  n = 0 restores the
+ * built-in light of the selected program. */
+int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_lights);
+
+/* Tunables that the reference exposes as '#define's at the top of its kernels or as GUI widgets:
+ *   "rr_threshold" (udpt.cl:6 / bdpt.cl:4), "bdpt_bounces" (bdpt.cl:7), "oren_nayar" (0/1: use
+ *   udpt-primitives.cl:681-725 for pure-diffuse lobes with sigma^2 = alpha_x),
+ *   and engine knobs: "pool_slots", "smem_nodes", "isect" (0 = reference Moller-Trumbore, 1 = watertight),
+ *   "max_iterations".  Unknown key -> YUNE_ERR_INVALID. */
+int yune_set_option(yune_ctx* ctx, const char* key, double value);
+int yune_get_option(yune_ctx* ctx, const char* key, double* value);
+
+/* ---- one call = RendererCore::enqueueKernels frames (src/RendererCore.cpp:248-469) ----
+ * Renders samples [spp_begin, spp_begin + spp_count) of every pixel and adds them to the fp32 SUM buffer
+ * (rgb = sum of sample radiance, a = number of samples; the reference's running mean is sum/a,
+ * udpt.cl:196-209).  reset != 0 clears the sum first (kernel arg 9).  gi_check = kernel arg 8.
+ * `seed` keys the counter-based RNG (it replaces the per-frame `rand`, kernel arg 10): sample s of pixel p
+ * always sees the same random numbers, whatever the spp split or GPU count. */
+int yune_render(yune_ctx* ctx, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset);
+/* Post-processing launch (src/RendererCore.cpp:340-371): mean = sum/a, Reinhard + gamma of tonemap.cl:14-47. */
+int yune_tonemap(yune_ctx* ctx);
+
+/* Read-backs (the reference reads the GL renderbuffer, src/RendererCore.cpp:608-646).
+ * hdr: running mean in rgb, sample count in a -- exactly the reference's image contents.
+ * sum: the raw accumulation buffer.  ldr: output of yune_tonemap. */
+int yune_read_hdr(yune_ctx* ctx, float* rgba);
+int yune_read_sum(yune_ctx* ctx, float* rgba);
+int yune_read_ldr(yune_ctx* ctx, float* rgba);
+/* Load a (e.g. all-reduced) sum buffer back from the host. */
+int yune_write_sum(yune_ctx* ctx, const float* rgba);
+
+/* Device pointer of the fp32 RGBA sum buffer (width*height*4 floats) so a collective library can reduce it
+ * in place across GPUs; and the CUDA stream the context launches on. */
+int yune_sum_device_ptr(yune_ctx* ctx, void** dptr, size_t* n_bytes);
+int yune_stream(yune_ctx* ctx, void** cuda_stream);
+int yune_synchronize(yune_ctx* ctx);
+
+/* ---- parity hooks (test surface; they run the same raygen/extend kernels as yune_render) ---- */
+/* Primary rays only.  jitter_mode 0: pixel centres; 1: the reference's jitter for `rand`
+ * (wang_hash/xor_shift, udpt.cl:175-187).  Outputs per pixel: triangle id (-1 none), light id (-1 none), t. */
+int yune_trace_primary(yune_ctx* ctx, int jitter_mode, uint32_t rand, int32_t* tri_id, int32_t* light_id, float* t_hit);
+/* Arbitrary rays: od6 = n x (origin xyz, dir xyz), tmax may be NULL (= infinity). any_hit != 0 runs the
+ * shadow-ray query (udpt.cl:306-308): tri_id is then 0 (occluded) or -1. */
+int yune_trace_rays(yune_ctx* ctx, int n, const float* od6, const float* tmax, int any_hit,
+                    int32_t* tri_id, int32_t* light_id, float* t_hit);
+
+/* ---- metrics (the reference's benchmark window, src/RendererCore.cpp:483-505) ---- */
+typedef struct yune_stats {
+    double   render_ms;        /* device time of the last yune_render (CUDA events on the context's stream) */
+    double   trace_ms;         /* ... of which: trace kernels (extend + shadow)                         */
+    double   shade_ms;         /* ... of which: logic/shade kernels                                      */
+    double   tonemap_ms;       /* device time of the last yune_tonemap                                   */
+    uint64_t samples;          /* samples completed by the last yune_render                               */
+    uint64_t extend_rays;      /* closest-hit rays traced                                                 */
+    uint64_t shadow_rays;      /* any-hit rays traced (NEE + MIS + BDPT connections)                      */
+    uint64_t box_tests;        /* only counted when option "count_work" = 1                               */
+    uint64_t tri_tests;
+    uint32_t iterations;       /* wavefront iterations                                                    */
+    uint32_t kernel_launches;  /* kernels launched by the last yune_render                                */
+    uint32_t trace_launches;   /* ... of which trace kernels                                              */
+    uint32_t reserved;
+} yune_stats;
+int yune_get_stats(yune_ctx* ctx, yune_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YUNE_CUDA_H */

@@ -1,0 +1,559 @@
+// context.cu -- the C ABI of include/yune_cuda.h: device/buffer management (what CLManager did with OpenCL,
+// src/CLManager.cpp) and the headless frame loop (what RendererCore::enqueueKernels did, src/RendererCore.cpp:248-469).
+//
+// There is no CPU execution path in this file or behind it: every entry point either drives the CUDA kernels
+// of kernels.cu or fails with an error code.
+#include "yune_cuda.h"
+#include "kernels.h"
+#include "trav_layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace yune;
+
+namespace {
+thread_local std::string g_setup_err;
+
+const yune_quad_light kBuiltinLightUdpt = {      // udpt.cl:97-106
+    {{-0.1979f, 0.92f, -3.1972f, 1.f}}, {{0.f, -1.f, 0.f, 0.f}}, {{16.f, 16.f, 16.f, 0.f}}, {{0.f, 0.f, 0.f, 0.f}},
+    {{0.f, 0.f, 0.f, 0.f}}, {{0.4f, 0.f, 0.f, 0.f}}, {{0.f, 0.f, 0.4f, 0.f}}, 0.f, {0.f, 0.f, 0.f}};
+const yune_quad_light kBuiltinLightBdpt = {      // bdpt.cl:106-115
+    {{-0.1979f, 0.703f, -3.1972f, 1.f}}, {{0.f, 1.f, 0.f, 0.f}}, {{18.3f, 16.2f, 14.5f, 0.f}}, {{0.f, 0.f, 0.f, 0.f}},
+    {{0.f, 0.f, 0.f, 0.f}}, {{0.4f, 0.f, 0.f, 0.f}}, {{0.f, 0.f, 0.4f, 0.f}}, 0.f, {0.f, 0.f, 0.f}};
+
+LightDev unpack_light(const yune_quad_light& q)
+{
+    LightDev L;
+    L.pos = v3(q.pos.s[0], q.pos.s[1], q.pos.s[2]);
+    L.normal = v3(q.normal.s[0], q.normal.s[1], q.normal.s[2]);
+    L.ke = v3(q.ke.s[0], q.ke.s[1], q.ke.s[2]);
+    L.edge_l = v3(q.edge_l.s[0], q.edge_l.s[1], q.edge_l.s[2]);
+    L.edge_w = v3(q.edge_w.s[0], q.edge_w.s[1], q.edge_w.s[2]);
+    L.la = vlength(L.edge_l);        // length(float4) with w = 0 (udpt.cl:259-260)
+    L.lb = vlength(L.edge_w);
+    return L;
+}
+}
+
+enum { INTEGRATOR_NONE = 0, INTEGRATOR_UDPT = 1, INTEGRATOR_BDPT = 2 };
+
+struct yune_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    std::string err;
+
+    // host copies of the reference-layout buffers (re-laid-out lazily when both are present)
+    std::vector<yune_triangle> h_tris; std::vector<yune_bvh_node> h_nodes; std::vector<yune_material> h_mats;
+    bool layout_dirty = true, have_tris = false, have_nodes = false, have_mats = false, have_cam = false;
+    TravLayoutHost lay;
+    float4 *d_pairs = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_mats = nullptr;
+    DevScene sc{};
+    yune_cam cam{};
+
+    int integrator = INTEGRATOR_NONE; int mis = 0; bool postproc = false;
+    LightSet lights{}; bool user_lights = false;
+
+    int W = 0, H = 0;
+    float4 *d_sum = nullptr, *d_hdr = nullptr, *d_ldr = nullptr;
+
+    PathPool pool{}; int pool_alloc = 0;
+    IterCounters* d_ctr = nullptr; Totals* d_tot = nullptr; Totals* h_tot = nullptr;
+
+    // hook scratch
+    float4 *hk_o = nullptr, *hk_d = nullptr, *hk_hit = nullptr; int *hk_tri = nullptr, *hk_light = nullptr; float *hk_t = nullptr, *hk_od = nullptr, *hk_tmax = nullptr;
+    unsigned char* hk_vis = nullptr; int* hk_cnt = nullptr; int hk_cap = 0;
+
+    // options
+    int opt_pool_slots = 1 << 20, opt_smem_nodes = 1024, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
+
+    yune_stats stats{};
+};
+
+// ------------------------------------------------------------------------------------------------------------
+#define Y_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->err = _b; return (code); } while (0)
+#define Y_CUDA(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { \
+        char _b[512]; snprintf(_b, sizeof(_b), "%s in File: %s at Line number: %d (%s)", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+        (ctx)->err = _b; return YUNE_ERR_CUDA; } } while (0)
+
+template <class T> static void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+static void free_pool(yune_ctx* c)
+{
+    PathPool& P = c->pool;
+    dfree(P.ray_o); dfree(P.ray_d); dfree(P.hit); dfree(P.thr); dfree(P.thr_next); dfree(P.col); dfree(P.pend_l);
+    dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
+    P.n_slots = 0; c->pool_alloc = 0;
+}
+
+static int ensure_pool(yune_ctx* c)
+{
+    const int n = c->opt_pool_slots;
+    if (c->pool_alloc == n) return YUNE_OK;
+    free_pool(c);
+    PathPool& P = c->pool;
+    const size_t N = (size_t)n;
+    Y_CUDA(c, cudaMalloc(&P.ray_o, N * 16)); Y_CUDA(c, cudaMalloc(&P.ray_d, N * 16)); Y_CUDA(c, cudaMalloc(&P.hit, N * 16));
+    Y_CUDA(c, cudaMalloc(&P.thr, N * 16)); Y_CUDA(c, cudaMalloc(&P.thr_next, N * 16)); Y_CUDA(c, cudaMalloc(&P.col, N * 16));
+    Y_CUDA(c, cudaMalloc(&P.pend_l, N * 16)); Y_CUDA(c, cudaMalloc(&P.meta, N * 16));
+    Y_CUDA(c, cudaMalloc(&P.evt_idx, N * 4)); Y_CUDA(c, cudaMalloc(&P.vis_l, N)); Y_CUDA(c, cudaMalloc(&P.eq, N * 4));
+    Y_CUDA(c, cudaMalloc(&P.sq_o, 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.sq_d, 3 * N * 16));
+    Y_CUDA(c, cudaMalloc(&P.evt, 2 * 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.evt_vis, 2 * 4 * N));
+    P.n_slots = n; c->pool_alloc = n;
+    return YUNE_OK;
+}
+
+static void set_builtin_lights(yune_ctx* c)
+{
+    if (c->user_lights) return;
+    c->lights.n = 1;
+    c->lights.l[0] = unpack_light(c->integrator == INTEGRATOR_BDPT ? kBuiltinLightBdpt : kBuiltinLightUdpt);
+}
+
+// (re)build the traversal layout and upload it
+static int ensure_scene(yune_ctx* c)
+{
+    if (!c->have_tris || !c->have_nodes || !c->have_mats)
+        Y_FAIL(c, YUNE_ERR_STATE, "scene incomplete: vertex, material and BVH buffers must all be set up before rendering");
+    if (!c->layout_dirty) return YUNE_OK;
+    std::string err;
+    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err))
+        Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
+    for (const yune_triangle& t : c->h_tris)
+        if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade);
+    const TravLayoutHost& L = c->lay;
+    Y_CUDA(c, cudaMalloc(&c->d_pairs, std::max<size_t>(L.pairs.size(), 4) * 16));
+    Y_CUDA(c, cudaMalloc(&c->d_tris, std::max<size_t>(L.tris.size(), 3) * 16));
+    Y_CUDA(c, cudaMalloc(&c->d_shade, std::max<size_t>(L.shade.size(), 4) * 16));
+    if (!L.pairs.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_pairs, L.pairs.data(), L.pairs.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    if (!L.tris.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_tris, L.tris.data(), L.tris.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    if (!L.shade.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_shade, L.shade.data(), L.shade.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    DevScene& s = c->sc;
+    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats;
+    s.n_inner = L.n_inner; s.n_tris = L.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = L.root_ref;
+    for (int k = 0; k < 3; k++) { s.root_lo[k] = L.root_lo[k]; s.root_hi[k] = L.root_hi[k]; }
+    c->layout_dirty = false;
+    return YUNE_OK;
+}
+
+struct TraceLaunch { int grid; size_t smem; };
+static int trace_config(yune_ctx* c, TraceLaunch& tl)
+{
+    int n_smem = c->opt_smem_nodes < c->sc.n_inner ? c->opt_smem_nodes : c->sc.n_inner;
+    if (n_smem < 0) n_smem = 0;
+    if (n_smem > 3400) n_smem = 3400;                         // 3400 * 64 B = 212.5 KB < 227 KB
+    c->sc.n_smem_pairs = n_smem;
+    tl.smem = (size_t)n_smem * 64;
+    Y_CUDA(c, trace_set_smem(tl.smem > 0 ? tl.smem : 16));
+    int per_sm = trace_blocks_per_sm(tl.smem);
+    if (per_sm < 1) Y_FAIL(c, YUNE_ERR_CUDA, "trace kernel does not fit on an SM with %zu bytes of shared memory", tl.smem);
+    tl.grid = c->sm_count * per_sm;
+    return YUNE_OK;
+}
+
+static RenderArgs make_args(yune_ctx* c)
+{
+    RenderArgs a{};
+    a.sc = c->sc; a.lights = c->lights; a.pool = c->pool; a.sum = c->d_sum; a.ctr = c->d_ctr; a.tot = c->d_tot;
+    std::memcpy(a.cam, &c->cam, 80);
+    a.width = c->W; a.height = c->H;
+    a.rr_threshold = c->opt_rr_threshold >= 0 ? c->opt_rr_threshold : (c->integrator == INTEGRATOR_BDPT ? 4 : 6);
+    a.mis = c->mis; a.oren_nayar = c->opt_oren_nayar; a.count_work = c->opt_count_work;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* yune_last_error(const yune_ctx* ctx) { return ctx ? ctx->err.c_str() : g_setup_err.c_str(); }
+
+int yune_setup(int device, yune_ctx** out)
+{
+    if (!out) { g_setup_err = "yune_setup: out_ctx is NULL"; return YUNE_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_setup_err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return YUNE_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= n) { g_setup_err = "yune_setup: device index out of range"; return YUNE_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_setup_err = cudaGetErrorString(e); return YUNE_ERR_CUDA; }
+    if (prop.major != 10) {
+        char b[256]; snprintf(b, sizeof(b), "device %d (%s) is sm_%d%d; this build contains sm_100a code only", device, prop.name, prop.major, prop.minor);
+        g_setup_err = b; return YUNE_ERR_NODEVICE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_setup_err = cudaGetErrorString(e); return YUNE_ERR_CUDA; }
+    yune_ctx* c = new yune_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess && cudaEventCreate(&c->ev2) == cudaSuccess
+           && cudaMalloc(&c->d_ctr, 2 * sizeof(IterCounters)) == cudaSuccess && cudaMalloc(&c->d_tot, sizeof(Totals)) == cudaSuccess
+           && cudaMallocHost(&c->h_tot, sizeof(Totals)) == cudaSuccess;
+    if (!ok) { g_setup_err = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError()); yune_destroy(c); return YUNE_ERR_CUDA; }
+    c->integrator = INTEGRATOR_UDPT; set_builtin_lights(c);
+    *out = c;
+    return YUNE_OK;
+}
+
+void yune_destroy(yune_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_pool(c);
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats);
+    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_ctr); dfree(c->d_tot);
+    dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
+    if (c->h_tot) cudaFreeHost(c->h_tot);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static bool name_is(const char* s, const char* base)
+{
+    if (!s) return false;
+    std::string a(s);
+    size_t slash = a.find_last_of('/'); if (slash != std::string::npos) a = a.substr(slash + 1);
+    return a == base || a == std::string(base) + ".cl";
+}
+
+int yune_create_render_program(yune_ctx* c, const char* kernel, const char* opts)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    int integ = name_is(kernel, "udpt") ? INTEGRATOR_UDPT : name_is(kernel, "bdpt") ? INTEGRATOR_BDPT : INTEGRATOR_NONE;
+    if (integ == INTEGRATOR_NONE) Y_FAIL(c, YUNE_ERR_INVALID, "unknown render kernel '%s' (built-in: udpt.cl, bdpt.cl)", kernel ? kernel : "(null)");
+    int mis = 0;
+    if (opts && *opts) {
+        if (std::strcmp(opts, "-DMIS") == 0 || std::strcmp(opts, "-D MIS") == 0) mis = 1;
+        else Y_FAIL(c, YUNE_ERR_INVALID, "unsupported compiler-opts '%s' (supported: -DMIS)", opts);
+    }
+    if (integ == INTEGRATOR_BDPT) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt.cl: the bidirectional integrator is not built into this revision");
+    c->integrator = integ; c->mis = mis;
+    set_builtin_lights(c);
+    return YUNE_OK;
+}
+
+int yune_create_postproc_program(yune_ctx* c, const char* kernel, const char* opts)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!name_is(kernel, "tonemap")) Y_FAIL(c, YUNE_ERR_INVALID, "unknown post-processing kernel '%s' (built-in: tonemap.cl)", kernel ? kernel : "(null)");
+    if (opts && *opts) Y_FAIL(c, YUNE_ERR_INVALID, "unsupported compiler-opts '%s'", opts);
+    c->postproc = true;
+    return YUNE_OK;
+}
+
+int yune_setup_vertex_buffer(yune_ctx* c, const yune_triangle* tris, int n)
+{
+    if (!c || n < 0 || (n > 0 && !tris)) { if (c) c->err = "yune_setup_vertex_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->h_tris.assign(tris, tris + n);
+    c->have_tris = true; c->layout_dirty = true;
+    return YUNE_OK;
+}
+
+int yune_setup_mat_buffer(yune_ctx* c, const yune_material* mats, int n)
+{
+    if (!c || n <= 0 || !mats) { if (c) c->err = "yune_setup_mat_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    Y_CUDA(c, cudaSetDevice(c->device));
+    c->h_mats.assign(mats, mats + n);
+    dfree(c->d_mats);
+    Y_CUDA(c, cudaMalloc(&c->d_mats, (size_t)n * 80));
+    Y_CUDA(c, cudaMemcpyAsync(c->d_mats, mats, (size_t)n * 80, cudaMemcpyHostToDevice, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->sc.mats = c->d_mats; c->sc.n_mats = n;
+    c->have_mats = true;
+    return YUNE_OK;
+}
+
+int yune_setup_bvh_buffer(yune_ctx* c, const yune_bvh_node* nodes, int n)
+{
+    if (!c || n < 0 || (n > 0 && !nodes)) { if (c) c->err = "yune_setup_bvh_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    if (n == 0) Y_FAIL(c, YUNE_ERR_INVALID, "bvh_size == 0 (brute-force intersection, udpt.cl:280-284) is not supported; build a BVH");
+    c->h_nodes.assign(nodes, nodes + n);
+    c->have_nodes = true; c->layout_dirty = true;
+    return YUNE_OK;
+}
+
+int yune_setup_camera_buffer(yune_ctx* c, const yune_cam* cam)
+{
+    if (!c || !cam) { if (c) c->err = "yune_setup_camera_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->cam = *cam; c->have_cam = true;
+    return YUNE_OK;
+}
+
+int yune_setup_image_buffers(yune_ctx* c, int W, int H)
+{
+    if (!c || W <= 0 || H <= 0 || (long long)W * H > (1ll << 30)) { if (c) c->err = "yune_setup_image_buffers: bad size"; return YUNE_ERR_INVALID; }
+    Y_CUDA(c, cudaSetDevice(c->device));
+    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr);
+    const size_t n = (size_t)W * H;
+    Y_CUDA(c, cudaMalloc(&c->d_sum, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_hdr, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_ldr, n * 16));
+    Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n * 16, c->stream));
+    Y_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, n * 16, c->stream));
+    Y_CUDA(c, cudaMemsetAsync(c->d_ldr, 0, n * 16, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->W = W; c->H = H;
+    return YUNE_OK;
+}
+
+int yune_set_light_sources(yune_ctx* c, const yune_quad_light* lights, int n)
+{
+    if (!c || n < 0 || (n > 0 && !lights)) { if (c) c->err = "yune_set_light_sources: bad arguments"; return YUNE_ERR_INVALID; }
+    if (n > YUNE_MAX_LIGHTS) Y_FAIL(c, YUNE_ERR_LIMIT, "at most %d quad lights are supported", YUNE_MAX_LIGHTS);
+    if (n == 0) { c->user_lights = false; set_builtin_lights(c); return YUNE_OK; }
+    c->lights.n = n;
+    for (int i = 0; i < n; i++) c->lights.l[i] = unpack_light(lights[i]);
+    c->user_lights = true;
+    return YUNE_OK;
+}
+
+static int* option_slot(yune_ctx* c, const char* key)
+{
+    if (!key) return nullptr;
+    struct { const char* k; int* p; } tab[] = {
+        {"pool_slots", &c->opt_pool_slots}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
+        {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
+        {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
+        {"time_stages", &c->opt_time_stages},
+    };
+    for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
+    return nullptr;
+}
+int yune_set_option(yune_ctx* c, const char* key, double value)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    int* p = option_slot(c, key);
+    if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
+    const int v = (int)value;
+    if (p == &c->opt_pool_slots && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be in [1024, 2^26]");
+    if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
+    if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
+    *p = v;
+    return YUNE_OK;
+}
+int yune_get_option(yune_ctx* c, const char* key, double* value)
+{
+    if (!c || !value) return YUNE_ERR_INVALID;
+    int* p = option_slot(c, key);
+    if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
+    *value = *p;
+    return YUNE_OK;
+}
+
+int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (spp_begin < 0 || spp_count < 0) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: negative sample range");
+    if (c->integrator != INTEGRATOR_UDPT) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: no render program selected");
+    if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: image buffers not set up");
+    if (!c->have_cam) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: camera buffer not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
+    if ((rc = ensure_pool(c)) != YUNE_OK) return rc;
+    TraceLaunch tl;
+    if ((rc = trace_config(c, tl)) != YUNE_OK) return rc;
+
+    const size_t n_pix = (size_t)c->W * c->H;
+    if (reset) Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n_pix * 16, c->stream));
+    std::memset(c->h_tot, 0, sizeof(Totals));
+    c->h_tot->n_samples = (unsigned long long)n_pix * (unsigned long long)spp_count;
+    c->h_tot->live_last = 1;
+    Y_CUDA(c, cudaMemcpyAsync(c->d_tot, c->h_tot, sizeof(Totals), cudaMemcpyHostToDevice, c->stream));
+    Y_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(IterCounters), c->stream));
+    Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
+
+    RenderArgs a = make_args(c);
+    a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
+    TraceArgs t{};
+    t.sc = c->sc; t.eq = c->pool.eq; t.ray_o = c->pool.ray_o; t.ray_d = c->pool.ray_d; t.hit = c->pool.hit;
+    t.sq_o = c->pool.sq_o; t.sq_d = c->pool.sq_d; t.vis_a = c->pool.vis_l; t.vis_b = c->pool.evt_vis; t.tot = c->d_tot;
+
+    yune_stats st{};
+    float shade_ms = 0.f, trace_ms = 0.f;
+    Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    int it = 0;
+    bool done = spp_count == 0;
+    while (!done) {
+        for (int b = 0; b < c->opt_sync_every && it < c->opt_max_iterations; b++, it++) {
+            const int p = it & 1;
+            a.parity = p;
+            t.n_extend = &c->d_ctr[p].n_extend; t.fetch_extend = &c->d_ctr[p].fetch_extend;
+            t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
+            if (c->opt_time_stages) Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+            Y_CUDA(c, launch_shade_udpt(a, c->stream));
+            if (c->opt_time_stages) {
+                Y_CUDA(c, cudaEventRecord(c->ev2, c->stream)); Y_CUDA(c, cudaEventSynchronize(c->ev2));
+                float ms = 0; cudaEventElapsedTime(&ms, c->ev1, c->ev2); shade_ms += ms;
+                Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+            }
+            Y_CUDA(c, launch_trace(t, tl.grid, tl.smem, c->opt_count_work != 0, c->stream));
+            if (c->opt_time_stages) {
+                Y_CUDA(c, cudaEventRecord(c->ev2, c->stream)); Y_CUDA(c, cudaEventSynchronize(c->ev2));
+                float ms = 0; cudaEventElapsedTime(&ms, c->ev1, c->ev2); trace_ms += ms;
+            }
+            Y_CUDA(c, launch_iter_end(c->d_ctr, c->d_tot, p, c->stream));
+            st.kernel_launches += 3; st.trace_launches += 1;
+        }
+        Y_CUDA(c, cudaMemcpyAsync(c->h_tot, c->d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+        Y_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->h_tot->live_last == 0) done = true;
+        else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
+    }
+    Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    Y_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    st.render_ms = ms; st.shade_ms = shade_ms; st.trace_ms = trace_ms;
+    st.samples = c->h_tot->n_samples; st.extend_rays = c->h_tot->extend_rays; st.shadow_rays = c->h_tot->shadow_rays;
+    st.box_tests = c->h_tot->box_tests; st.tri_tests = c->h_tot->tri_tests; st.iterations = (uint32_t)it;
+    st.tonemap_ms = c->stats.tonemap_ms;
+    c->stats = st;
+    return YUNE_OK;
+}
+
+int yune_tonemap(yune_ctx* c)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_tonemap: image buffers not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    Y_CUDA(c, launch_tonemap(c->d_sum, c->d_hdr, c->d_ldr, c->W * c->H, c->stream));
+    Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    Y_CUDA(c, cudaEventSynchronize(c->ev1));
+    float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.tonemap_ms = ms;
+    return YUNE_OK;
+}
+
+static int read_image(yune_ctx* c, const float4* src, float* dst)
+{
+    if (!dst) Y_FAIL(c, YUNE_ERR_INVALID, "read: destination is NULL");
+    if (!src) Y_FAIL(c, YUNE_ERR_STATE, "read: image buffers not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)c->W * c->H * 16, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YUNE_OK;
+}
+int yune_read_hdr(yune_ctx* c, float* rgba)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "read: image buffers not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, launch_tonemap(c->d_sum, c->d_hdr, nullptr, c->W * c->H, c->stream));
+    return read_image(c, c->d_hdr, rgba);
+}
+int yune_read_sum(yune_ctx* c, float* rgba) { return c ? read_image(c, c->d_sum, rgba) : YUNE_ERR_INVALID; }
+int yune_read_ldr(yune_ctx* c, float* rgba) { return c ? read_image(c, c->d_ldr, rgba) : YUNE_ERR_INVALID; }
+int yune_write_sum(yune_ctx* c, const float* rgba)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!rgba) Y_FAIL(c, YUNE_ERR_INVALID, "yune_write_sum: source is NULL");
+    if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_write_sum: image buffers not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, cudaMemcpyAsync(c->d_sum, rgba, (size_t)c->W * c->H * 16, cudaMemcpyHostToDevice, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YUNE_OK;
+}
+int yune_sum_device_ptr(yune_ctx* c, void** dptr, size_t* n_bytes)
+{
+    if (!c || !dptr) return YUNE_ERR_INVALID;
+    if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "image buffers not set up");
+    *dptr = c->d_sum; if (n_bytes) *n_bytes = (size_t)c->W * c->H * 16;
+    return YUNE_OK;
+}
+int yune_stream(yune_ctx* c, void** s) { if (!c || !s) return YUNE_ERR_INVALID; *s = (void*)c->stream; return YUNE_OK; }
+int yune_synchronize(yune_ctx* c) { if (!c) return YUNE_ERR_INVALID; Y_CUDA(c, cudaSetDevice(c->device)); Y_CUDA(c, cudaStreamSynchronize(c->stream)); return YUNE_OK; }
+int yune_get_stats(yune_ctx* c, yune_stats* out) { if (!c || !out) return YUNE_ERR_INVALID; *out = c->stats; return YUNE_OK; }
+
+// ---- parity hooks ----
+static int ensure_hook(yune_ctx* c, int n)
+{
+    if (c->hk_cap >= n) return YUNE_OK;
+    dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
+    c->hk_cap = 0;
+    const size_t N = (size_t)n;
+    Y_CUDA(c, cudaMalloc(&c->hk_o, N * 16)); Y_CUDA(c, cudaMalloc(&c->hk_d, N * 16)); Y_CUDA(c, cudaMalloc(&c->hk_hit, N * 16));
+    Y_CUDA(c, cudaMalloc(&c->hk_tri, N * 4)); Y_CUDA(c, cudaMalloc(&c->hk_light, N * 4)); Y_CUDA(c, cudaMalloc(&c->hk_t, N * 4));
+    Y_CUDA(c, cudaMalloc(&c->hk_od, N * 24)); Y_CUDA(c, cudaMalloc(&c->hk_tmax, N * 4)); Y_CUDA(c, cudaMalloc(&c->hk_vis, N));
+    Y_CUDA(c, cudaMalloc(&c->hk_cnt, 4 * sizeof(int)));
+    c->hk_cap = n;
+    return YUNE_OK;
+}
+
+// run k_trace over hook rays [0, n): closest (any == 0) or any-hit
+static int hook_trace(yune_ctx* c, int n, int any)
+{
+    TraceLaunch tl; int rc;
+    if ((rc = trace_config(c, tl)) != YUNE_OK) return rc;
+    int h_cnt[4] = {any ? 0 : n, 0, any ? n : 0, 0};       // n_extend, fetch_extend, n_shadow, fetch_shadow
+    Y_CUDA(c, cudaMemcpyAsync(c->hk_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, c->stream));
+    TraceArgs t{};
+    t.sc = c->sc; t.eq = nullptr; t.ray_o = c->hk_o; t.ray_d = c->hk_d; t.hit = c->hk_hit;
+    t.n_extend = c->hk_cnt + 0; t.fetch_extend = c->hk_cnt + 1; t.n_shadow = c->hk_cnt + 2; t.fetch_shadow = c->hk_cnt + 3;
+    t.sq_o = c->hk_o; t.sq_d = c->hk_d; t.vis_a = c->hk_vis; t.vis_b = c->hk_vis; t.tot = nullptr;
+    Y_CUDA(c, launch_trace(t, tl.grid, tl.smem, false, c->stream));
+    return YUNE_OK;
+}
+
+int yune_trace_primary(yune_ctx* c, int jitter_mode, uint32_t rand, int32_t* tri_id, int32_t* light_id, float* t_hit)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!tri_id || !light_id) Y_FAIL(c, YUNE_ERR_INVALID, "yune_trace_primary: output pointers are NULL");
+    if (c->W <= 0) Y_FAIL(c, YUNE_ERR_STATE, "yune_trace_primary: image buffers not set up");
+    if (!c->have_cam) Y_FAIL(c, YUNE_ERR_STATE, "yune_trace_primary: camera buffer not set up");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    int rc; const int n = c->W * c->H;
+    if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
+    if ((rc = ensure_hook(c, n)) != YUNE_OK) return rc;
+    RenderArgs a = make_args(c);
+    Y_CUDA(c, launch_hook_primary(a, jitter_mode, rand, c->hk_o, c->hk_d, c->stream));
+    // light ids were stored in ray_d.w by the raygen; copy them out through the finish kernel's light_id input
+    Y_CUDA(c, cudaMemsetAsync(c->hk_light, 0xff, (size_t)n * 4, c->stream));
+    if ((rc = hook_trace(c, n, 0)) != YUNE_OK) return rc;
+    Y_CUDA(c, launch_hook_finish(n, 0, c->hk_o, c->hk_hit, c->hk_vis, c->hk_tri, c->hk_light, c->hk_t, c->stream));
+    std::vector<float> raydw((size_t)n * 4);
+    Y_CUDA(c, cudaMemcpyAsync(tri_id, c->hk_tri, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t_hit) Y_CUDA(c, cudaMemcpyAsync(t_hit, c->hk_t, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaMemcpyAsync(raydw.data(), c->hk_d, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) {
+        int lid; std::memcpy(&lid, &raydw[(size_t)i * 4 + 3], 4);
+        light_id[i] = tri_id[i] >= 0 ? -1 : lid;
+    }
+    return YUNE_OK;
+}
+
+int yune_trace_rays(yune_ctx* c, int n, const float* od6, const float* tmax, int any_hit, int32_t* tri_id, int32_t* light_id, float* t_hit)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (n < 0 || !od6 || !tri_id || !light_id) Y_FAIL(c, YUNE_ERR_INVALID, "yune_trace_rays: bad arguments");
+    if (n == 0) return YUNE_OK;
+    Y_CUDA(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
+    if ((rc = ensure_hook(c, n)) != YUNE_OK) return rc;
+    Y_CUDA(c, cudaMemcpyAsync(c->hk_od, od6, (size_t)n * 24, cudaMemcpyHostToDevice, c->stream));
+    if (tmax) Y_CUDA(c, cudaMemcpyAsync(c->hk_tmax, tmax, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    Y_CUDA(c, launch_hook_prepare(c->lights, n, c->hk_od, tmax ? c->hk_tmax : nullptr, any_hit, c->hk_o, c->hk_d, c->hk_light, c->hk_vis, c->stream));
+    if ((rc = hook_trace(c, n, any_hit)) != YUNE_OK) return rc;
+    Y_CUDA(c, launch_hook_finish(n, any_hit, c->hk_o, c->hk_hit, c->hk_vis, c->hk_tri, c->hk_light, c->hk_t, c->stream));
+    Y_CUDA(c, cudaMemcpyAsync(tri_id, c->hk_tri, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaMemcpyAsync(light_id, c->hk_light, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t_hit) Y_CUDA(c, cudaMemcpyAsync(t_hit, c->hk_t, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YUNE_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,601 @@
+// kernels.cu -- the sm_100a wavefront kernels of the path-tracing hot path.
+//
+//   k_trace        persistent-thread BVH walk: drains the shadow queue (any-hit) then the extension queue
+//                  (closest hit).  Replaces traceRay/traverseBVH/rayTriangleIntersection/rayAabbIntersection
+//                  (kernels/legacy/udpt.cl:240-431).
+//   k_shade_udpt   "logic + material" stage, one thread per path slot: collects last iteration's NEE answers,
+//                  processes the hit (udpt.cl:433-533 `shading`), creates the NEE / MIS shadow rays
+//                  (:535-609 `evaluateDirectLighting`), samples the next direction, regenerates finished
+//                  slots with fresh camera rays (:158-238 `pathtracer`/`createRay`) and accumulates finished
+//                  samples (:193-210).  Queues are compacted with warp ballot/popc.
+//   k_tonemap      kernels/post-proc/tonemap.cl:14-47 on the mean image.
+//   k_hook_*       parity hooks: primary rays / arbitrary rays through the same k_trace.
+//
+// Tensor cores are not used: no stage is a dense contraction (every ray gathers its own nodes/triangles).
+#include "kernels.h"
+#include "trace_core.h"
+#include "shade_core.h"
+#include "rng.h"
+
+namespace yune {
+
+// ------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 xyz(const float4& f) { return v3(f.x, f.y, f.z); }
+__device__ __forceinline__ float4 f4(V3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+__device__ __forceinline__ F4 toF4(const float4& f) { F4 r; r.x = f.x; r.y = f.y; r.z = f.z; r.w = f.w; return r; }
+
+// warp-aggregated slot allocation in a global counter: returns this lane's index, or -1 for lanes with want == false
+__device__ __forceinline__ int warp_alloc(int* counter, bool want)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return want ? base + __popc(m & ((1u << lane) - 1)) : -1;
+}
+__device__ __forceinline__ long long warp_alloc64(unsigned long long* counter, bool want)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// trace kernel
+// ------------------------------------------------------------------------------------------------------------
+struct DevPairFetch {
+    const float4* smem; const float4* gmem; int n_smem;
+    __device__ __forceinline__ void operator()(int i, F4& a, F4& b, F4& c, F4& d) const
+    {
+        float4 q0, q1, q2, q3;
+        if (i < n_smem) { const float4* p = smem + 4 * i; q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3]; }
+        else { const float4* p = gmem + 4 * (size_t)i; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3); }
+        a = toF4(q0); b = toF4(q1); c = toF4(q2); d = toF4(q3);
+    }
+};
+struct DevTriFetch {
+    const float4* gmem;
+    __device__ __forceinline__ void operator()(int i, F4& a, F4& b, F4& c) const
+    {
+        const float4* p = gmem + 3 * (size_t)i;
+        a = toF4(__ldg(p)); b = toF4(__ldg(p + 1)); c = toF4(__ldg(p + 2));
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(YUNE_TRACE_BLOCK, YUNE_TRACE_MIN_BLOCKS) k_trace(TraceArgs A)
+{
+    extern __shared__ float4 s_pairs[];
+    const DevScene& sc = A.sc;
+    for (int i = threadIdx.x; i < sc.n_smem_pairs * 4; i += blockDim.x) s_pairs[i] = __ldg(sc.pairs + i);
+    __syncthreads();
+
+    DevPairFetch pf; pf.smem = s_pairs; pf.gmem = sc.pairs; pf.n_smem = sc.n_smem_pairs;
+    DevTriFetch tf; tf.gmem = sc.tris;
+    const int lane = threadIdx.x & 31;
+    WorkCount wc; wc.box = 0; wc.tri = 0;
+
+    // ---- shadow queue: any-hit ----
+    {
+        const int n = *A.n_shadow;
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(A.fetch_shadow, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const int q = base + lane;
+            if (q < n) {
+                const float4 o = A.sq_o[q], d = A.sq_d[q];
+                const RayPre r = make_ray(xyz(o), xyz(d));
+                const bool occluded = any_hit<DevPairFetch, DevTriFetch, COUNT>(pf, tf, sc.root_ref, sc.root_lo, sc.root_hi, r, o.w, &wc);
+                const int target = __float_as_int(d.w);
+                if (target >= 0) A.vis_a[target] = occluded ? 0 : 1;
+                else A.vis_b[~target] = occluded ? 0 : 1;
+            }
+        }
+    }
+    // ---- extension queue: closest hit ----
+    {
+        const int n = *A.n_extend;
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(A.fetch_extend, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const int q = base + lane;
+            if (q < n) {
+                const int s = A.eq ? A.eq[q] : q;
+                const float4 o = A.ray_o[s], d = A.ray_d[s];
+                const RayPre r = make_ray(xyz(o), xyz(d));
+                HitRec h;
+                closest_hit<DevPairFetch, DevTriFetch, COUNT>(pf, tf, sc.root_ref, sc.root_lo, sc.root_hi, r, o.w, h, &wc);
+                A.hit[s] = make_float4(h.t, h.u, h.v, __int_as_float(h.tri));
+            }
+        }
+    }
+    if (COUNT) {
+        // warp-reduce then one atomic per warp
+        unsigned long long b = wc.box, t = wc.tri;
+        for (int o = 16; o > 0; o >>= 1) { b += __shfl_down_sync(0xffffffffu, b, o); t += __shfl_down_sync(0xffffffffu, t, o); }
+        if (lane == 0 && A.tot) { atomicAdd(&A.tot->box_tests, b); atomicAdd(&A.tot->tri_tests, t); }
+    }
+}
+
+// One thread: fold this iteration's queue sizes into the running totals and clear the OTHER parity's counters so
+// the next shade launch starts from zero.  Runs between k_trace and the next k_shade on the same stream.
+__global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
+{
+    IterCounters& c = ctr[parity];
+    tot->extend_rays += (unsigned long long)c.n_extend;
+    tot->shadow_rays += (unsigned long long)c.n_shadow;
+    tot->live_last = c.live;
+    tot->iterations += 1;
+    IterCounters z; z.n_extend = z.n_shadow = z.n_events = z.live = 0; z.fetch_extend = z.fetch_shadow = z.pad0 = z.pad1 = 0;
+    ctr[parity ^ 1] = z;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// camera ray (createRay, udpt.cl:213-238); fp64 where the kernel's literals make it fp64
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void create_ray(const float* cam, int W, int H, float pixel_x, float pixel_y, V3& o, V3& d)
+{
+    const float aspect_ratio = (float)(((double)W * 1.0) / (double)H);
+    V3 dir;
+    dir.x = (float)((double)aspect_ratio * ((2.0 * (double)pixel_x / (double)W) - 1.0));
+    dir.y = (float)((2.0 * (double)pixel_y / (double)H) - 1.0);
+    dir.z = -cam[16];
+    V3 w;
+    w.x = vdot(v3(cam[0], cam[1], cam[2]), dir);
+    w.y = vdot(v3(cam[4], cam[5], cam[6]), dir);
+    w.z = vdot(v3(cam[8], cam[9], cam[10]), dir);
+    d = vnormalize(w);
+    o = v3(cam[3], cam[7], cam[11]);
+}
+
+__device__ __forceinline__ MatDev load_material(const float4* mats, int id)
+{
+    const float4* p = mats + 5 * (size_t)id;
+    const float4 ke = __ldg(p), kd = __ldg(p + 1), ks = __ldg(p + 2), a = __ldg(p + 3), b = __ldg(p + 4);
+    MatDev m;
+    m.ke = xyz(ke); m.kd = xyz(kd); m.ks = xyz(ks);
+    m.n = a.x; m.px = a.z; m.py = a.w; m.alpha_x = b.x;
+    m.is_specular = __float_as_int(b.z); m.is_transmissive = __float_as_int(b.w);
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// shade kernel (unidirectional path tracing, with or without MIS)
+// ------------------------------------------------------------------------------------------------------------
+struct ShadowOut { bool has; V3 o, d; float tmax; };
+
+template <bool MIS>
+__global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < A.pool.n_slots;
+    const PathPool& P = A.pool;
+    IterCounters* C = A.ctr + A.parity;
+    const LightDev* lights = A.lights.l;
+    const int n_lights = A.lights.n;
+
+    uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
+    unsigned state = meta.w & YS_STATE_MASK;
+    V3 col = v3(0, 0, 0), T = v3(1, 1, 1), Tn = v3(1, 1, 1);
+    unsigned new_flags = 0;
+    bool has_ext = false; V3 ext_o = v3(0, 0, 0), ext_d = v3(0, 0, 1); float ext_t = INFINITY; int ext_lid = -1;
+    ShadowOut S, MV, MO; S.has = MV.has = MO.has = false;
+    bool mo_is_mv = false;
+    V3 Lv = v3(0, 0, 0), BV = v3(0, 0, 0), BO = v3(0, 0, 0);
+    bool nee_pending = false;       // the NEE of THIS visit left something to resolve next visit
+    bool need_new = false;
+
+    if (state == YS_TRACE || state == YS_DRAIN) {
+        col = xyz(P.col[s]);
+        T = xyz(P.thr[s]);
+        // ---- 1. resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
+        if (meta.w & YF_PEND_EVT) {
+            const int e = P.evt_idx[s];
+            const float4 e0 = P.evt[3 * (size_t)e], e1 = P.evt[3 * (size_t)e + 1], e2 = P.evt[3 * (size_t)e + 2];
+            const int ef = __float_as_int(e0.w);
+            const bool visS = (ef & YE_HAS_S) && P.evt_vis[4 * (size_t)e + 0];
+            const bool visMV = (ef & YE_HAS_MV) && P.evt_vis[4 * (size_t)e + 1];
+            const bool visMO = (ef & YE_MO_IS_MV) ? visMV : ((ef & YE_HAS_MO) && P.evt_vis[4 * (size_t)e + 2]);
+            V3 nee;
+            if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
+            else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
+            col = vadd(col, vmul(T, nee));
+        } else if (meta.w & YF_PEND_L) {
+            if (P.vis_l[s]) col = vadd(col, vmul(T, xyz(P.pend_l[s])));
+        }
+    }
+
+    bool finished = false;          // the sample's radiance is final
+    if (state == YS_DRAIN) finished = true;
+    else if (state == YS_TRACE) {
+        const float4 hit = P.hit[s], ro = P.ray_o[s], rd = P.ray_d[s];
+        const int tri = __float_as_int(hit.w);
+        const V3 o = xyz(ro), d = xyz(rd);
+        const unsigned vtx = meta.z;
+        bool terminate = false;
+        if (tri < 0) {
+            const int lid = __float_as_int(rd.w);
+            if (vtx == 0) {                                                     // udpt.cl:437-446
+                if (lid >= 0) col = (vdot(d, lights[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
+                else col = v3(0.4f, 0.4f, 0.4f);
+            } else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(T, lights[lid].ke));   // :490-493
+            terminate = true;
+        } else {
+            // ---- 2. the surface point (udpt.cl:375-385)
+            const float4 s0 = __ldg(A.sc.shade + 4 * (size_t)tri), s1 = __ldg(A.sc.shade + 4 * (size_t)tri + 1), s2 = __ldg(A.sc.shade + 4 * (size_t)tri + 2);
+            const MatDev mat = load_material(A.sc.mats, __float_as_int(s0.w));
+            const float bw = YF_SUB(YF_SUB(1.0f, hit.y), hit.z);
+            const V3 hp = vadd(o, vscale(d, hit.x));
+            const V3 n = vnormalize(vmadd3(xyz(s0), bw, xyz(s1), hit.y, xyz(s2), hit.z));
+            const V3 w_o = vneg(d);
+            const U4 u_nee = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_NEE);
+
+            if (vtx > 0) {                                                      // arrival of bounce i = vtx - 1
+                Tn = xyz(P.thr_next[s]);
+                col = vadd(col, vmul(T, mat.ke));                               // :498
+                T = Tn;                                                         // :504-507 (product was formed at sampling time)
+                if ((int)vtx - 1 > A.rr_threshold) {                            // :514-523
+                    const float p = cl_min(luminance(T), 0.95f);
+                    const float r = u01(u_nee.x);
+                    if (r >= p) terminate = true;
+                    else T = vscale(T, YF_DIV(1.0f, p));
+                }
+            }
+            if (!terminate) {
+                // ---- 3. next-event estimation at this vertex (evaluateDirectLighting, :535-609)
+                if (!mat.is_specular) {
+                    col = vadd(col, vmul(T, mat.ke));                           // the 'emission' term of every return path
+                    float u_l[2 * YUNE_MAX_LIGHTS]; float u_pick = 0.0f;
+                    for (int i = 0; i < n_lights; i++) {
+                        const U4 ul = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_LIGHT + i);
+                        u_l[2 * i] = u01(ul.x); u_l[2 * i + 1] = u01(ul.y);
+                        if (i == 0) u_pick = u01(ul.z);
+                    }
+                    float light_pdf = 0.0f; V3 w_i = v3(0, 0, 0);
+                    const int j = sample_lights(lights, n_lights, hp, n, u_l, u_pick, light_pdf, w_i);
+                    if (!(j == -1 || light_pdf <= 0.0f)) {
+                        float len = vlength(w_i);
+                        len = YF_SUB(len, YF_MUL(YUNE_EPS, 1.5f));
+                        w_i = vnormalize(w_i);
+                        S.o = vadd(hp, vscale(w_i, YUNE_EPS)); S.d = w_i; S.tmax = len;
+                        float tl = len;
+                        const bool s_blocked = light_loop(lights, n_lights, S.o, S.d, tl) >= 0;     // traceRay's light loop (:244-276)
+                        S.has = !s_blocked;
+                        // branch "light sample visible": lobe selection happens only then (:559-561)
+                        float prob = 0.0f;
+                        const bool glossy = select_lobe(mat, u01(u_nee.y), false, prob);
+                        const bool v_alive = prob != 0.0f;
+                        const V3 Lke = lights[j].ke;
+                        if (v_alive) {
+                            Lv = vscale(vmul(eval_brdf(mat, w_i, w_o, n, glossy, prob, true, A.oren_nayar != 0), Lke), fmaxf(vdot(w_i, n), 0.0f));
+                            Lv = vscale(Lv, YF_DIV(1.0f, light_pdf));
+                        }
+                        if (MIS) {
+                            const float r1 = u01(u_nee.z), r2 = u01(u_nee.w);
+                            const bool use_on = A.oren_nayar != 0;
+                            float pdfV = 0.0f, pdfO = 0.0f;
+                            V3 dv = v3(0, 0, 1), dq;
+                            if (v_alive) {
+                                const float brdf_pdf = glossy ? phong_pdf(mat, w_i, w_o, n) : cos_pdf(w_i, n);
+                                Lv = vscale(Lv, power_heuristic(light_pdf, light_pdf, brdf_pdf));                    // :570-577
+                                dv = glossy ? sample_phong(w_o, n, mat.px, mat.py, r1, r2, true, pdfV) : sample_cosine(n, r1, r2, pdfV);
+                                if (pdfV > 0.0f) {                                                                   // :587-588
+                                    MV.o = vadd(hp, vscale(dv, YUNE_EPS)); MV.d = dv; MV.tmax = INFINITY;
+                                    if (light_loop(lights, n_lights, MV.o, MV.d, MV.tmax) == j) {                    // closest light must be j (:594)
+                                        MV.has = true;
+                                        BV = vscale(vmul(eval_brdf(mat, dv, w_o, n, glossy, prob, true, use_on), Lke), fmaxf(vdot(dv, n), 0.0f));
+                                        BV = vscale(BV, YF_DIV(power_heuristic(pdfV, light_pdf, pdfV), pdfV));       // :597-600
+                                    }
+                                }
+                            }
+                            // Branch "light sample occluded": sample_glossy = false and brdf_prob = 0 keep their initial values
+                            // (:541-542), so the BRDF sample is cosine-distributed and evaluateBRDF divides by zero.  Reproduced
+                            // as is (it is why the reference's MIS images collect inf / pink pixels near shadow edges).
+                            const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
+                            if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
+                            if (pdfO > 0.0f) {
+                                bool reaches = false;
+                                if (same_dir) { reaches = MV.has; mo_is_mv = MV.has; }
+                                else {
+                                    MO.o = vadd(hp, vscale(dq, YUNE_EPS)); MO.d = dq; MO.tmax = INFINITY;
+                                    reaches = MO.has = (light_loop(lights, n_lights, MO.o, MO.d, MO.tmax) == j);
+                                }
+                                if (reaches) {
+                                    BO = vscale(vmul(eval_brdf(mat, dq, w_o, n, false, 0.0f, true, use_on), Lke), fmaxf(vdot(dq, n), 0.0f));
+                                    BO = vscale(BO, YF_DIV(power_heuristic(pdfO, light_pdf, pdfO), pdfO));
+                                }
+                            }
+                        }
+                        nee_pending = S.has || MV.has || MO.has;
+                    }
+                }
+                // ---- 4. continue the path (udpt.cl:463-530)
+                if (!A.gi_check) terminate = true;
+                else {
+                    const U4 u_b = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_BOUNCE);
+                    V3 dir;
+                    if (mat.is_specular) {
+                        float ior = 1.0f;
+                        dir = sample_specular(mat, w_o, n, u01(u_b.w), ior);
+                        Tn = vscale(T, ior);
+                    } else {
+                        float prob = 0.0f, pdf = 1.0f;
+                        const bool glossy = select_lobe(mat, u01(u_b.x), false, prob);
+                        if (prob == 0.0f) terminate = true;                     // absorbed (:475-476)
+                        else {
+                            dir = glossy ? sample_phong(w_o, n, mat.px, mat.py, u01(u_b.y), u01(u_b.z), true, pdf)
+                                         : sample_cosine(n, u01(u_b.y), u01(u_b.z), pdf);
+                            if (pdf <= 0.0f) terminate = true;                  // :488
+                            else Tn = vdivs(vscale(vmul(T, eval_brdf(mat, dir, w_o, n, glossy, prob, true, A.oren_nayar != 0)), fmaxf(vdot(dir, n), 0.0f)), pdf);
+                        }
+                    }
+                    if (!terminate) {
+                        has_ext = true;
+                        ext_d = dir; ext_o = vadd(hp, vscale(dir, YUNE_EPS)); ext_t = INFINITY;
+                        ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
+                        new_flags = YS_TRACE | (mat.is_specular ? YF_PREV_SPEC : 0u);
+                        meta.z = vtx + 1;
+                    }
+                }
+            }
+        }
+        if (terminate && !has_ext) {
+            if (nee_pending) new_flags = YS_DRAIN;
+            else finished = true;
+        }
+    }
+
+    // ---- 5. a finished sample goes to the accumulation buffer (udpt.cl:193-210; sum instead of running mean)
+    if (finished) {
+        if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (:193-194)
+        float* dst = reinterpret_cast<float*>(A.sum + meta.x);
+        atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
+        state = YS_FREE;
+    }
+    need_new = valid && (finished || state == YS_FREE) && !has_ext && new_flags == 0;
+
+    // ---- 6. regenerate: next (pixel, sample) in global order + camera ray (udpt.cl:164-189)
+    {
+        const long long g = warp_alloc64(&A.tot->next_sample, need_new);
+        if (need_new) {
+            if ((unsigned long long)g >= A.tot->n_samples) new_flags = YS_DONE;
+            else {
+                const unsigned long long n_pix = (unsigned long long)A.width * A.height;
+                const unsigned pixel = (unsigned)((unsigned long long)g % n_pix);
+                const unsigned sample = (unsigned)(A.spp_begin + (int)((unsigned long long)g / n_pix));
+                const int px = pixel % A.width, py = pixel / A.width;
+                const U4 uj = draw4(A.seed, pixel, sample, YUNE_VERTEX_CAMERA, 0u);
+                create_ray(A.cam, A.width, A.height, (float)px + u01(uj.x), (float)py + u01(uj.y), ext_o, ext_d);
+                ext_t = INFINITY;
+                ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
+                has_ext = true;
+                meta.x = pixel; meta.y = sample; meta.z = 0;
+                col = v3(0, 0, 0); T = v3(1, 1, 1); Tn = v3(1, 1, 1);
+                new_flags = YS_TRACE;
+            }
+        }
+    }
+
+    // ---- 7. queue pushes (ballot/popc compaction) and state write-back
+    const int qe = warp_alloc(&C->n_extend, has_ext);
+    if (has_ext) {
+        P.eq[qe] = s;
+        P.ray_o[s] = f4(ext_o, ext_t);
+        P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
+    }
+    const bool is_event = MV.has || MO.has;
+    // event records and their answers are double-buffered by iteration parity: this visit still READS last iteration's
+    const int ev = A.parity * P.n_slots + warp_alloc(&C->n_events, is_event);
+    if (is_event) {
+        int ef = (S.has ? YE_HAS_S : 0) | (MV.has ? YE_HAS_MV : 0) | (MO.has ? YE_HAS_MO : 0) | (mo_is_mv ? YE_MO_IS_MV : 0);
+        P.evt[3 * (size_t)ev] = f4(Lv, __int_as_float(ef));
+        P.evt[3 * (size_t)ev + 1] = f4(BV, 0.0f);
+        P.evt[3 * (size_t)ev + 2] = f4(BO, 0.0f);
+        P.evt_idx[s] = ev;
+        new_flags |= YF_PEND_EVT;
+    } else if (S.has) new_flags |= YF_PEND_L;
+    const int qs = warp_alloc(&C->n_shadow, S.has);
+    if (S.has) {
+        P.sq_o[qs] = f4(S.o, S.tmax);
+        P.sq_d[qs] = f4(S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
+        if (!is_event) P.pend_l[s] = f4(Lv, 0.0f);
+    }
+    if (MIS) {
+        const int qv = warp_alloc(&C->n_shadow, MV.has);
+        if (MV.has) { P.sq_o[qv] = f4(MV.o, MV.tmax); P.sq_d[qv] = f4(MV.d, __int_as_float(~(4 * ev + 1))); }
+        const int qo = warp_alloc(&C->n_shadow, MO.has);
+        if (MO.has) { P.sq_o[qo] = f4(MO.o, MO.tmax); P.sq_d[qo] = f4(MO.d, __int_as_float(~(4 * ev + 2))); }
+    }
+    if (valid && (meta.w & YS_STATE_MASK) != YS_DONE) {
+        meta.w = new_flags;
+        P.meta[s] = meta;
+        if ((new_flags & YS_STATE_MASK) != YS_DONE) {
+            P.col[s] = f4(col, 0.0f);
+            P.thr[s] = f4(T, 0.0f);
+            if (has_ext) P.thr_next[s] = f4(Tn, 0.0f);
+        }
+    }
+    const bool live = valid && (new_flags & YS_STATE_MASK) != YS_DONE && (meta.w & YS_STATE_MASK) != YS_DONE;
+    const unsigned lm = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && lm) atomicAdd(&C->live, __popc(lm));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pool / buffer initialisation, tonemap, hooks
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pool_reset(PathPool P)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n_slots) P.meta[s] = make_uint4(0, 0, 0, YS_FREE);
+}
+__global__ void k_fill_f4(float4* p, size_t n, float4 v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// tonemap.cl:14-47 on mean = sum / count.  Output keeps the reference's "gamma on all four channels".
+__global__ void k_tonemap(const float4* sum, float4* hdr, float4* ldr, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 sv = sum[i];
+    float4 c;
+    if (sv.w > 0.0f) { c.x = YF_DIV(sv.x, sv.w); c.y = YF_DIV(sv.y, sv.w); c.z = YF_DIV(sv.z, sv.w); c.w = sv.w; }
+    else c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hdr) hdr[i] = c;
+    if (!ldr) return;
+    const float lum_world = YF_ADD(YF_ADD(YF_ADD(YF_MUL(0.212671f, c.x), YF_MUL(0.715160f, c.y)), YF_MUL(0.072169f, c.z)), 0.001f);
+    const float lum_white = 1.0f;
+    const float lum_display = YF_DIV(YF_MUL(lum_world, YF_ADD(1.0f, YF_DIV(lum_world, YF_MUL(lum_white, lum_white)))), YF_ADD(1.0f, lum_world));
+    float4 l;
+    l.x = YF_MUL(lum_display, powf(YF_DIV(c.x, lum_world), 1.0f));
+    l.y = YF_MUL(lum_display, powf(YF_DIV(c.y, lum_world), 1.0f));
+    l.z = YF_MUL(lum_display, powf(YF_DIV(c.z, lum_world), 1.0f));
+    l.w = YF_MUL(lum_display, powf(YF_DIV(c.w, lum_world), 1.0f));
+    const float g = YF_DIV(1.0f, 2.2f);
+    ldr[i] = make_float4(powf(l.x, g), powf(l.y, g), powf(l.z, g), powf(l.w, g));
+}
+
+// Primary rays for the parity hook: same create_ray as the renderer; jitter from the REFERENCE generator
+// (udpt.cl:175-187) or pixel centres.
+__global__ void k_hook_primary(RenderArgs A, int jitter_mode, uint32_t rand, float4* ray_o, float4* ray_d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.width * A.height) return;
+    const int x = i % A.width, y = i / A.width;
+    float r1 = 0.5f, r2 = 0.5f;
+    if (jitter_mode == 1) {
+        uint32_t seed = (uint32_t)((y + 1) * A.width + (x + 1));
+        seed = rand * seed;
+        seed = wang_hash(seed);
+        if (seed == 0) seed = wang_hash(seed);
+        seed = xor_shift(seed); r1 = u01(seed);
+        seed = xor_shift(seed); r2 = u01(seed);
+    }
+    V3 o, d; create_ray(A.cam, A.width, A.height, (float)x + r1, (float)y + r2, o, d);
+    float t = INFINITY;
+    const int lid = light_loop(A.lights.l, A.lights.n, o, d, t);
+    ray_o[i] = f4(o, t); ray_d[i] = f4(d, __int_as_float(lid));
+}
+
+// Arbitrary rays for the parity hook: run traceRay's light loop, then hand the ray to k_trace.
+__global__ void k_hook_prepare(LightSet L, int n, const float* od6, const float* tmax, int any_hit,
+                               float4* ray_o, float4* ray_d, int* light_id, unsigned char* vis)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 o = v3(od6[6 * (size_t)i], od6[6 * (size_t)i + 1], od6[6 * (size_t)i + 2]);
+    const V3 d = v3(od6[6 * (size_t)i + 3], od6[6 * (size_t)i + 4], od6[6 * (size_t)i + 5]);
+    float t = tmax ? tmax[i] : INFINITY;
+    const int lid = light_loop(L.l, L.n, o, d, t);
+    light_id[i] = lid;
+    if (any_hit) {
+        // a light inside the segment already occludes (traceRay ORs the two answers, udpt.cl:278-279)
+        ray_o[i] = f4(o, lid >= 0 ? -1.0f : t);
+        ray_d[i] = f4(d, __int_as_float(i));
+        vis[i] = 0;
+    } else {
+        ray_o[i] = f4(o, t); ray_d[i] = f4(d, __int_as_float(lid));
+    }
+}
+__global__ void k_hook_finish(int n, int any_hit, const float4* ray_o, const float4* hit, const unsigned char* vis,
+                              int* tri_id, int* light_id, float* t_hit)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (any_hit) {
+        const bool occluded = light_id[i] >= 0 || vis[i] == 0;
+        tri_id[i] = occluded ? 0 : -1;
+        if (t_hit) t_hit[i] = ray_o[i].w;
+    } else {
+        const float4 h = hit[i];
+        const int tri = __float_as_int(h.w);
+        tri_id[i] = tri;
+        if (tri >= 0) light_id[i] = -1;
+        if (t_hit) t_hit[i] = h.x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------------------
+static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+cudaError_t launch_trace(const TraceArgs& a, int grid, size_t smem_bytes, bool count, cudaStream_t st)
+{
+    if (count) k_trace<true><<<grid, YUNE_TRACE_BLOCK, smem_bytes, st>>>(a);
+    else       k_trace<false><<<grid, YUNE_TRACE_BLOCK, smem_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t trace_set_smem(size_t smem_bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+int trace_blocks_per_sm(size_t smem_bytes)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, YUNE_TRACE_BLOCK, smem_bytes) != cudaSuccess) return 0;
+    return n;
+}
+cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st)
+{
+    k_iter_end<<<1, 1, 0, st>>>(ctr, tot, parity);
+    return cudaGetLastError();
+}
+cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st)
+{
+    const int grid = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
+    if (a.mis) k_shade_udpt<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
+    else       k_shade_udpt<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st)
+{
+    k_pool_reset<<<ceil_div(p.n_slots, 256), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    k_fill_f4<<<ceil_div((long long)n, 256), 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}
+cudaError_t launch_tonemap(const float4* sum, float4* hdr, float4* ldr, int n, cudaStream_t st)
+{
+    k_tonemap<<<ceil_div(n, 256), 256, 0, st>>>(sum, hdr, ldr, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_hook_primary(const RenderArgs& a, int jitter_mode, uint32_t rand, float4* ray_o, float4* ray_d, cudaStream_t st)
+{
+    k_hook_primary<<<ceil_div((long long)a.width * a.height, 256), 256, 0, st>>>(a, jitter_mode, rand, ray_o, ray_d);
+    return cudaGetLastError();
+}
+cudaError_t launch_hook_prepare(const LightSet& L, int n, const float* od6, const float* tmax, int any_hit,
+                                float4* ray_o, float4* ray_d, int* light_id, unsigned char* vis, cudaStream_t st)
+{
+    k_hook_prepare<<<ceil_div(n, 256), 256, 0, st>>>(L, n, od6, tmax, any_hit, ray_o, ray_d, light_id, vis);
+    return cudaGetLastError();
+}
+cudaError_t launch_hook_finish(int n, int any_hit, const float4* ray_o, const float4* hit, const unsigned char* vis,
+                               int* tri_id, int* light_id, float* t_hit, cudaStream_t st)
+{
+    k_hook_finish<<<ceil_div(n, 256), 256, 0, st>>>(n, any_hit, ray_o, hit, vis, tri_id, light_id, t_hit);
+    return cudaGetLastError();
+}
+
+} // namespace yune

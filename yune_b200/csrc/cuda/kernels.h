@@ -1,0 +1,41 @@
+// kernels.h -- host-callable launch wrappers of kernels.cu.
+#ifndef YUNE_KERNELS_H
+#define YUNE_KERNELS_H
+
+#include "wavefront_types.h"
+
+#define YUNE_TRACE_BLOCK      256
+#define YUNE_TRACE_MIN_BLOCKS 2
+#define YUNE_SHADE_BLOCK      256
+
+namespace yune {
+
+// Work description of one k_trace launch.  Counts are read from device memory so the launch shape never
+// depends on them (persistent grid; lets a whole batch of iterations be replayed as one CUDA graph).
+struct TraceArgs {
+    DevScene sc;
+    // extension rays (closest hit): ray = ray_o/ray_d[eq ? eq[q] : q], answer -> hit[same index]
+    const int* eq; const float4* ray_o; const float4* ray_d; float4* hit;
+    const int* n_extend; int* fetch_extend;
+    // shadow rays (any hit): answer -> vis_a[target] (target >= 0) or vis_b[~target]; 1 = unoccluded
+    const float4* sq_o; const float4* sq_d; unsigned char* vis_a; unsigned char* vis_b;
+    const int* n_shadow; int* fetch_shadow;
+    Totals* tot;
+};
+
+cudaError_t launch_trace(const TraceArgs& a, int grid, size_t smem_bytes, bool count, cudaStream_t st);
+cudaError_t trace_set_smem(size_t smem_bytes);
+int         trace_blocks_per_sm(size_t smem_bytes);
+cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
+cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st);
+cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
+cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);
+cudaError_t launch_tonemap(const float4* sum, float4* hdr, float4* ldr, int n, cudaStream_t st);
+cudaError_t launch_hook_primary(const RenderArgs& a, int jitter_mode, uint32_t rand, float4* ray_o, float4* ray_d, cudaStream_t st);
+cudaError_t launch_hook_prepare(const LightSet& L, int n, const float* od6, const float* tmax, int any_hit,
+                                float4* ray_o, float4* ray_d, int* light_id, unsigned char* vis, cudaStream_t st);
+cudaError_t launch_hook_finish(int n, int any_hit, const float4* ray_o, const float4* hit, const unsigned char* vis,
+                               int* tri_id, int* light_id, float* t_hit, cudaStream_t st);
+
+} // namespace yune
+#endif

@@ -1,0 +1,52 @@
+// trav_layout.h -- the traversal-side layout of the reference BVH and triangles in HBM.
+//
+// The drop-in boundary receives the reference's AoS records (BVHNodeGPU 80 B, TriangleGPU 112 B,
+// include/CL_headers.h:67-92).  Traversal never touches those: at upload they are re-laid-out ONCE into
+//
+//   pair records  (64 B, one per INNER node, breadth-first order so the hot top of the tree is a prefix):
+//       q0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)      c0/c1 = the two (adjacent) children
+//       q1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//       q2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//       q3 = (ref0, ref1, -, -) as int bits
+//     one fetch of four 16-byte vectors tests both children; the 40 dead bytes of vert_list are gone and no
+//     node is read twice (the reference reads each node as a child and again as a parent, udpt.cl:300-316).
+//   triangle records (48 B, LEAF ORDER: leaves sorted by node index, slots in vert_list order):
+//       t0 = (v1.xyz, original triangle index as int bits), t1 = (v2 - v1, 0), t2 = (v3 - v1, 0)
+//     The position in this array equals the reference's breadth-first visiting rank, which is what breaks exact
+//     ties in t the way the reference's first-come-first-kept rule does (udpt.cl:373).
+//   shading records (64 B, by ORIGINAL triangle index): normalised vertex normals + matID
+//       s0 = (N1.xyz, matID bits), s1 = (N2.xyz, 0), s2 = (N3.xyz, 0), s3 spare
+//
+// child ref: >= 0 inner (pair index); < 0 leaf with ~ref = (first << 4) | count; YUNE_REF_EMPTY = never visit
+// (the reference's 'vert_len > 0 || child_idx > 0' filter, udpt.cl:316).
+#ifndef YUNE_TRAV_LAYOUT_H
+#define YUNE_TRAV_LAYOUT_H
+
+#include "yune_types.h"
+#include <vector>
+#include <string>
+
+#define YUNE_REF_EMPTY ((int)0x80000000)
+#define YUNE_STACK_SIZE 64
+
+namespace yune {
+
+struct F4 { float x, y, z, w; };
+
+struct TravLayoutHost {
+    std::vector<F4> pairs;       // 4 per inner node
+    std::vector<F4> tris;        // 3 per leaf-ordered triangle
+    std::vector<F4> shade;       // 4 per original triangle
+    int   n_inner = 0, n_leaf_tris = 0, n_tris = 0;
+    int   root_ref = YUNE_REF_EMPTY;
+    float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+    int   max_depth = 0;         // stack entries a depth-first walk can need
+};
+
+// Builds the layout; returns false and sets `err` when the input is malformed (child index out of range,
+// triangle index out of range, leaf with more than 10 slots, tree deeper than YUNE_STACK_SIZE).
+bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
+                     TravLayoutHost& out, std::string& err);
+
+} // namespace yune
+#endif

@@ -1,0 +1,95 @@
+// wavefront_types.h -- argument blocks shared by the kernels and the context (engine.cu).
+#ifndef YUNE_WAVEFRONT_TYPES_H
+#define YUNE_WAVEFRONT_TYPES_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lights.h"
+
+namespace yune {
+
+// Scene in its traversal/shading layout (trav_layout.h).  Passed to kernels BY VALUE (constant bank).
+struct DevScene {
+    const float4* pairs;     // 4 x float4 per inner node, breadth-first
+    const float4* tris;      // 3 x float4 per leaf-ordered triangle
+    const float4* shade;     // 4 x float4 per original triangle (normalised normals, matID)
+    const float4* mats;      // 5 x float4 per material (the 80-byte reference record, untouched)
+    int   n_inner, n_tris, n_mats, root_ref;
+    float root_lo[3], root_hi[3];
+    int   n_smem_pairs;      // pair records [0, n_smem_pairs) are staged in shared memory by the trace kernel
+};
+
+struct LightSet { LightDev l[YUNE_MAX_LIGHTS]; int n; };
+
+// Per-iteration queue heads/counters (double buffered by iteration parity) + running totals.
+struct IterCounters {
+    int n_extend, n_shadow, n_events, live;
+    int fetch_extend, fetch_shadow, pad0, pad1;
+};
+struct Totals {
+    unsigned long long next_sample;     // next global sample index to hand out
+    unsigned long long n_samples;       // samples to render in this call
+    unsigned long long samples_done;
+    unsigned long long extend_rays, shadow_rays, box_tests, tri_tests;
+    int live_last;                      // slots still busy after the last completed iteration
+    int iterations;
+};
+
+// path-state flags (meta.w)
+#define YS_FREE   0u      // needs a new sample
+#define YS_TRACE  1u      // an extension ray is in flight; hit[] holds its answer on the next visit
+#define YS_DRAIN  2u      // path ended but NEE answers are still in flight
+#define YS_DONE   3u      // no samples left for this slot
+#define YS_STATE_MASK 3u
+#define YF_PEND_L     4u    // pendL/visL hold an unresolved NEE light sample
+#define YF_PREV_SPEC  8u    // the vertex that launched the extension ray was specular (udpt.cl:490)
+#define YF_PEND_EVT  16u    // evt_idx points at an MIS event record
+
+// Structure-of-arrays path pool: one entry per slot, every array 16-byte wide so a warp's accesses coalesce.
+struct PathPool {
+    int      n_slots;
+    float4*  ray_o;      // xyz origin, w = ray length so far (t of an analytic light hit, or +inf)
+    float4*  ray_d;      // xyz direction, w = int bits: index of the light that owns that length, or -1
+    float4*  hit;        // t, u, v, int bits: original triangle index or -1     (written by the trace kernel)
+    float4*  thr;        // xyz throughput at the current vertex (after Russian roulette)
+    float4*  thr_next;   // xyz throughput once the in-flight extension ray lands on a surface
+    float4*  col;        // xyz radiance gathered so far for the current sample
+    float4*  pend_l;     // xyz unresolved NEE light sample (already MIS-weighted), valid with YF_PEND_L
+    uint4*   meta;       // x pixel, y sample, z index of the vertex the extension ray will reach, w flags
+    int*     evt_idx;    // valid with YF_PEND_EVT
+    unsigned char* vis_l;   // 1 = NEE shadow ray reached the light (written by the trace kernel)
+    // queues
+    int*     eq;         // extension queue: slot indices
+    float4*  sq_o;       // shadow queue: xyz origin, w = tmax
+    float4*  sq_d;       // xyz direction, w = int bits: target (>= 0 slot -> vis_l ; < 0 -> ~target = event*4 + which)
+    // MIS events (rare): 3 x float4 each: (Lv.xyz, flags), (BV.xyz, -), (BO.xyz, -); answers in evt_vis[4*e + which]
+    float4*  evt;
+    unsigned char* evt_vis;
+};
+
+#define YE_HAS_S      1     // a shadow ray toward the light sample is in flight (which = 0)
+#define YE_HAS_MV     2     // BRDF-sampled ray of the "light sample visible" branch (which = 1)
+#define YE_HAS_MO     4     // BRDF-sampled ray of the "light sample occluded" branch (which = 2)
+#define YE_MO_IS_MV   8     // both branches sampled the same direction: which = 1 answers for both
+
+struct RenderArgs {
+    DevScene  sc;
+    LightSet  lights;
+    PathPool  pool;
+    float4*   sum;            // W*H fp32 RGBA accumulation buffer (rgb sums, a = sample count)
+    IterCounters* ctr;        // [2]
+    Totals*   tot;
+    float     cam[20];        // the 80-byte Cam record
+    int       width, height;
+    int       spp_begin;
+    uint32_t  seed;
+    int       gi_check;
+    int       rr_threshold;
+    int       mis;
+    int       oren_nayar;
+    int       parity;         // iteration parity -> which IterCounters to use
+    int       count_work;
+};
+
+} // namespace yune
+#endif

@@ -1,0 +1,68 @@
+// host_capi.cpp -- C ABI of include/yune_host.h over yune::Scene / yune::Camera.
+#include "yune_host.h"
+#include "Scene.h"
+
+#include <string>
+#include <exception>
+
+struct yune_scene { yune::Scene scene; std::string err; };
+
+namespace { thread_local std::string g_create_err; }
+
+extern "C" {
+
+yune_scene* yune_scene_create(void)
+{
+    try { return new yune_scene(); } catch (const std::exception& e) { g_create_err = e.what(); return nullptr; }
+}
+void yune_scene_destroy(yune_scene* s) { delete s; }
+const char* yune_scene_last_error(const yune_scene* s) { return s ? s->err.c_str() : g_create_err.c_str(); }
+
+int yune_scene_load_model(yune_scene* s, const char* filepath, int bvh_bins)
+{
+    if (!s || !filepath) return -1;
+    try {
+        std::string fp(filepath);
+        std::string fn = fp.substr(fp.find_last_of("/") + 1);
+        s->scene.bvh.bins = 20;                       // loadModel always builds with the default (include/BVH.h:43) ...
+        if (bvh_bins == 0) s->scene.bvh.bins = 0;     // ... unless the BVH is disabled
+        s->scene.loadModel(fp, fn);
+        if (bvh_bins > 0 && bvh_bins != 20) s->scene.loadBVH(bvh_bins);
+    } catch (const std::exception& e) { s->err = e.what(); return -1; }
+    return 0;
+}
+int yune_scene_load_bvh(yune_scene* s, int bvh_bins)
+{
+    if (!s) return -1;
+    try { s->scene.loadBVH(bvh_bins); } catch (const std::exception& e) { s->err = e.what(); return -1; }
+    return 0;
+}
+int yune_scene_reload_mat_file(yune_scene* s)
+{
+    if (!s) return -1;
+    try { s->scene.reloadMatFile(); } catch (const std::exception& e) { s->err = e.what(); return -1; }
+    return 0;
+}
+int yune_scene_num_triangles(const yune_scene* s) { return (int)s->scene.vert_data.size(); }
+int yune_scene_num_materials(const yune_scene* s) { return (int)s->scene.mat_data.size(); }
+int yune_scene_num_bvh_nodes(const yune_scene* s) { return (int)s->scene.bvh.gpu_node_list.size(); }
+const yune_triangle* yune_scene_vert_data(const yune_scene* s) { return s->scene.vert_data.data(); }
+const yune_material* yune_scene_mat_data(const yune_scene* s) { return s->scene.mat_data.data(); }
+yune_material* yune_scene_mat_data_mut(yune_scene* s) { return s->scene.mat_data.data(); }
+const yune_bvh_node* yune_scene_bvh_data(const yune_scene* s) { return s->scene.bvh.gpu_node_list.data(); }
+void yune_scene_root_aabb(const yune_scene* s, yune_aabb* out) { *out = s->scene.root; }
+
+void yune_camera_default(float fov, yune_cam* out)
+{
+    yune::Camera cam(fov);
+    cam.setBuffer(out);
+}
+void yune_camera_set(const float side[4], const float up[4], const float look_at[4], const float eye[4], float fov, yune_cam* out)
+{
+    yune::Camera cam(fov);
+    cam.setViewMatrix(yune::Vec4{side[0], side[1], side[2], side[3]}, yune::Vec4{up[0], up[1], up[2], up[3]},
+                      yune::Vec4{look_at[0], look_at[1], look_at[2], look_at[3]}, yune::Vec4{eye[0], eye[1], eye[2], eye[3]});
+    cam.setBuffer(out);
+}
+
+}

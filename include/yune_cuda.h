@@ -103,11 +103,19 @@ int yune_trace_primary(yune_ctx* ctx, int jitter_mode, uint32_t rand, int32_t* t
 int yune_trace_rays(yune_ctx* ctx, int n, const float* od6, const float* tmax, int any_hit,
                     int32_t* tri_id, int32_t* light_id, float* t_hit);
 
+/* ---- measurement aid ----
+ * Arm a capture of (up to max_rays of each of) the extension and shadow rays of wavefront iteration `iteration` of the
+ * next yune_render; max_rays = 0 disarms.  After the render, read them back (which: 0 = extension rays, 1 = shadow rays;
+ * tmax = the length each ray starts with).  bench.py gives these rays to the CPU oracle, whose ordered walk counts the
+ * box / triangle tests that define the roofline's algorithmic bytes. */
+int yune_debug_capture_rays(yune_ctx* ctx, int iteration, int max_rays);
+int yune_debug_read_captured(yune_ctx* ctx, int which, float* od6, float* tmax, int* n_captured, int* n_in_queue);
+
 /* ---- metrics (the reference's benchmark window, src/RendererCore.cpp:483-505) ---- */
 typedef struct yune_stats {
     double   render_ms;        /* device time of the last yune_render (CUDA events on the context's stream) */
-    double   trace_ms;         /* ... of which: trace kernels (extend + shadow)                         */
-    double   shade_ms;         /* ... of which: logic/shade kernels                                      */
+    double   trace_ms;         /* sum over the TIMED iterations of the trace-kernel duration (option "time_stages" = n: every n-th) */
+    double   shade_ms;         /* same for the logic/shade kernel                                        */
     double   tonemap_ms;       /* device time of the last yune_tonemap                                   */
     uint64_t samples;          /* samples completed by the last yune_render                               */
     uint64_t extend_rays;      /* closest-hit rays traced                                                 */
@@ -117,7 +125,7 @@ typedef struct yune_stats {
     uint32_t iterations;       /* wavefront iterations                                                    */
     uint32_t kernel_launches;  /* kernels launched by the last yune_render                                */
     uint32_t trace_launches;   /* ... of which trace kernels                                              */
-    uint32_t reserved;
+    uint32_t timed_iterations; /* iterations that trace_ms / shade_ms were summed over                    */
 } yune_stats;
 int yune_get_stats(yune_ctx* ctx, yune_stats* out);
 

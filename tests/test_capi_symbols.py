@@ -1,0 +1,60 @@
+"""The drop-in boundary: the library loads, exports every entry point include/*.h declares, and refuses to run without
+a B200 instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from yune_b200 import _native
+from tests.helpers import ROOT
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yune_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = _declared("yune_cuda.h") + _declared("yune_host.h")
+    assert len(names) > 40
+    for n in names:
+        assert hasattr(lib, n), "include/ declares %s but the library does not export it" % n
+    assert set(names) == set(_native.CUDA_API) | set(_native.HOST_API), "ctypes tables and headers disagree"
+
+
+def test_library_is_sm100a_native_code():
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_pod_sizes_match_reference_layouts():
+    from yune_b200 import api
+    assert (api.TRI_DTYPE.itemsize, api.NODE_DTYPE.itemsize, api.MAT_DTYPE.itemsize, api.CAM_DTYPE.itemsize, api.QUAD_DTYPE.itemsize) == (112, 80, 80, 80, 128)
+    assert api.TRI_DTYPE.fields["matID"][1] == 96 and api.NODE_DTYPE.fields["child_idx"][1] == 72 and api.MAT_DTYPE.fields["is_specular"][1] == 72
+
+
+def test_no_cpu_fallback():
+    """Without a GPU yune_setup must fail with YUNE_ERR_NODEVICE; with one it must succeed -- never a silent CPU path."""
+    import torch
+    lib = _native.load()
+    ctx = C.c_void_p()
+    rc = lib.yune_setup(0, C.byref(ctx))
+    if torch.cuda.is_available():
+        assert rc == 0
+        lib.yune_destroy(ctx)
+    else:
+        assert rc == -5 and b"no CPU fallback" in lib.yune_last_error(None)
+        import yune_b200 as yb
+        with pytest.raises(yb.YuneError):
+            yb.CUDAManager().setup(0)
+
+
+def test_argument_errors_do_not_crash():
+    lib = _native.load()
+    assert lib.yune_setup(0, None) == -1
+    assert lib.yune_render(None, 0, 1, 1, 0, 1) == -1
+    assert lib.yune_get_stats(None, None) == -1

@@ -1,0 +1,126 @@
+"""Host data path: OBJ/MTL loader, SAH BVH, camera record -- byte-exact against what the
+REFERENCE's own host sources produce (golden fixtures made by tests/golden/make_golden.py; live comparison when
+oracle/_ref and /root/reference are present)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import yune_b200 as yb
+from tests.helpers import (REF_GEOMETRY, load_golden_scene, masked_nodes_equal, tris_equal, write_obj)
+
+
+@pytest.mark.parametrize("name", ["cornellbox", "teapot"])
+def test_loader_and_bvh_reproduce_golden_buffers(tmp_path, name):
+    """Export the golden triangles to OBJ/MTL text, load them with the product's Scene and rebuild the BVH: every buffer
+    must come back bit-identical to the reference-built golden (the builder is deterministic in the triangle list)."""
+    tris, mats, nodes = load_golden_scene(name)
+    obj = str(tmp_path / "scene.obj")
+    write_obj(obj, tris, mats)
+    s = yb.Scene().loadModel(obj)
+    assert s.num_triangles == tris.size
+    assert tris_equal(s.vert_data, tris)
+    assert s.mat_data.tobytes() == mats.tobytes()
+    assert masked_nodes_equal(nodes, s.bvh), "BVH differs from the reference's"
+
+
+def test_golden_shapes_match_survey():
+    """Known-good shapes from SURVEY.md 8c pin 1 (probed on the reference): 15 nodes (7 inner / 8 leaves), 2199 nodes
+    (1099 / 1012 / 88 empty), max leaf 10."""
+    for name, n_tris, n_nodes, kinds in (("cornellbox", 60, 15, (7, 8, 0)), ("teapot", 6380, 2199, (1099, 1012, 88))):
+        tris, mats, nodes = load_golden_scene(name)
+        assert tris.size == n_tris and nodes.size == n_nodes and mats.size == 7
+        inner = int((nodes["child_idx"] > 0).sum()); leaf = int((nodes["child_idx"] == -1).sum()); empty = int((nodes["child_idx"] == -2).sum())
+        assert (inner, leaf, empty) == kinds
+        assert nodes["vert_len"].max() == 10
+        np.testing.assert_allclose(nodes["p_min"][0][:3], [-1.02, -1.00383, -4.049096], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(nodes["p_max"][0][:3], [1.2, 1.18617, -2.019096], rtol=0, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GEOMETRY), reason="needs the reference tree")
+@pytest.mark.parametrize("fn", ["cornellbox.obj", "cornellbox-teapot.obj"])
+@pytest.mark.parametrize("bins", [20, 2, 8, 64])
+def test_live_against_reference_host_code(ref_host, fn, bins):
+    """Same .obj through the reference's Scene/BVH sources (oracle/_ref) and through ours, for several bin counts."""
+    path = os.path.join(REF_GEOMETRY, fn)
+    rt, rm, rn, rroot = ref_host.load(path, bins)
+    s = yb.Scene().loadModel(path, bvh_bins=bins)
+    assert tris_equal(s.vert_data, rt)
+    assert s.mat_data.tobytes() == rm.tobytes()
+    assert masked_nodes_equal(rn, s.bvh)
+    assert s.root.tobytes() == rroot.tobytes()
+
+
+def test_material_dialect_quirks(tmp_path):
+    """Lowercase custom keys; px/py crossed; unknown usemtl -> material 0; defaults of newMaterial (appendix B#3)."""
+    (tmp_path / "q.mtl").write_text("# comment\nnewmtl a\nkd 0.1 0.2 0.3\npx 7\npy 9\nis_specular 1\n\nnewmtl b\nks 0.5 0.5 0.5\nn 1.5\nalpha_x 0.25\n")
+    (tmp_path / "q.obj").write_text("mtllib q.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nusemtl b\nf 1//1 2//1 3//1\nusemtl nosuch\nf 1//1 2//1 4//1\no thing\nf 2/5/1 3/5/1 4/5/1\n")
+    s = yb.Scene().loadModel(str(tmp_path / "q.obj"))
+    m = s.mat_data
+    assert m.size == 2
+    assert (m["px"][0], m["py"][0]) == (9.0, 7.0)                 # crossed
+    assert m["is_specular"][0] == 1 and m["is_transmissive"][0] == 0
+    np.testing.assert_array_equal(m["kd"][1], np.float32([0.3, 0.3, 0.3, 1]))     # default kd
+    assert m["alpha_y"][1] == 100 and m["alpha_x"][1] == 0.25 and m["n"][1] == 1.5
+    assert list(s.vert_data["matID"]) == [1, 0, 0]                 # unknown name -> 0, and 'o' does not reset it
+    assert s.vert_data["v1"][0][3] == 1 and s.vert_data["vn1"][0][3] == 0
+    # flat triangles get the 0.2 slab on zero-extent axes (appendix B#4): triangle 0 lies in z = 0
+    assert s.bvh.size == 1 and s.bvh["vert_len"][0] == 3
+    assert s.bvh["p_max"][0][2] == np.float32(1.0)                 # union with the third triangle reaches z = 1
+    assert s.root[6] == np.float32(1.0)
+
+
+def test_missing_mtllib_uses_default_material_without_writing(tmp_path):
+    (tmp_path / "n.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n")
+    s = yb.Scene().loadModel(str(tmp_path / "n.obj"))
+    assert s.mat_data.size == 1 and s.vert_data["matID"][0] == 0
+    assert not (tmp_path / "n.mtl").exists()      # the reference would create it (src/Scene.cpp:139-168); we must not
+
+
+def test_error_behaviour(tmp_path):
+    with pytest.raises(yb.YuneError, match="Error opening"):
+        yb.Scene().loadModel(str(tmp_path / "nope.obj"))
+    (tmp_path / "m.obj").write_text("mtllib gone.mtl\nv 0 0 0\n")
+    with pytest.raises(yb.YuneError, match="Error opening material file"):
+        yb.Scene().loadModel(str(tmp_path / "m.obj"))
+    (tmp_path / "e.mtl").write_text("# nothing\n")
+    (tmp_path / "e.obj").write_text("mtllib e.mtl\n")
+    with pytest.raises(yb.YuneError, match="Bad Material file"):
+        yb.Scene().loadModel(str(tmp_path / "e.obj"))
+    (tmp_path / "f.mtl").write_text("newmtl a\n")
+    (tmp_path / "f.obj").write_text("mtllib f.mtl\nv 0 0 0\nv 1 0 0\nf 1 2\n")
+    with pytest.raises(yb.YuneError, match="fewer than 3"):
+        yb.Scene().loadModel(str(tmp_path / "f.obj"))
+    # RendererCore::loadScene reports instead of raising (src/RendererCore.cpp:124-137)
+    r = yb.RendererCore(yb.CUDAManager(), 8, 8)
+    assert r.loadScene(str(tmp_path / "nope.obj")) is False and "Error opening" in r.cl_manager.last_message
+
+
+def test_duplicate_geometry_terminates(tmp_path):
+    """The reference builder never terminates on > 10 coincident centroids (appendix B#20); ours must report it."""
+    (tmp_path / "d.mtl").write_text("newmtl a\n")
+    lines = ["mtllib d.mtl", "v 0 0 0", "v 1 0 0", "v 0 1 0", "vn 0 0 1"] + ["f 1//1 2//1 3//1"] * 11
+    (tmp_path / "d.obj").write_text("\n".join(lines) + "\n")
+    with pytest.raises(yb.YuneError, match="does not terminate"):
+        yb.Scene().loadModel(str(tmp_path / "d.obj"))
+
+
+def test_empty_scene_and_tiny_scene(tmp_path):
+    (tmp_path / "z.mtl").write_text("newmtl a\n")
+    (tmp_path / "z.obj").write_text("mtllib z.mtl\n")
+    s = yb.Scene().loadModel(str(tmp_path / "z.obj"))
+    assert s.num_triangles == 0 and s.bvh.size == 1 and s.bvh["child_idx"][0] == -2     # root stays "empty"
+    (tmp_path / "t.obj").write_text("mtllib z.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n")
+    s = yb.Scene().loadModel(str(tmp_path / "t.obj"))
+    assert s.bvh.size == 1 and s.bvh["child_idx"][0] == -1 and s.bvh["vert_len"][0] == 1
+
+
+def test_camera_record():
+    """Cam = rows of view2world + view_plane_dist = 1/tan(fov*3.14/360) evaluated in double (src/Camera.cpp:60-82, 93-103)."""
+    cam = yb.default_camera()
+    for i, r in enumerate(("r1", "r2", "r3", "r4")):
+        want = np.zeros(4, np.float32); want[i] = 1
+        np.testing.assert_array_equal(np.abs(cam[r][0]), want)
+    assert cam["view_plane_dist"][0] == np.float32(1 / math.tan(60.0 * 3.14 / 360))
+    assert yb.default_camera(90.0)["view_plane_dist"][0] == np.float32(1 / math.tan(90.0 * 3.14 / 360))

@@ -1,0 +1,70 @@
+"""Traversal LOGIC of the product (trace_core.h, lights.h, relayout.cpp compiled for the host by tests/hostcheck --
+a test-only build, never loaded by the package) against the oracle: depth-first ordered walk with pruning must return
+the reference's breadth-first answer bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import ROOT, GOLDEN, load_golden_scene
+from tests.refbind import Oracle, default_cam_array, ptr
+
+LIGHT_UDPT = np.zeros(32, np.float32)
+LIGHT_UDPT[0:4] = [-0.1979, 0.92, -3.1972, 1]; LIGHT_UDPT[4:8] = [0, -1, 0, 0]; LIGHT_UDPT[8:12] = [16, 16, 16, 0]
+LIGHT_UDPT[20:24] = [0.4, 0, 0, 0]; LIGHT_UDPT[24:28] = [0, 0, 0.4, 0]
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libyune_hostcheck.so"))
+
+
+def _trace(hc, od, tmax, any_hit, tris, nodes):
+    n = od.shape[0]
+    tri = np.zeros(n, np.int32); light = np.zeros(n, np.int32); t = np.zeros(n, np.float32); work = np.zeros(2, np.uint64)
+    rc = hc.hc_trace(n, ptr(od), ptr(tmax), int(any_hit), ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(LIGHT_UDPT), 1,
+                     ptr(tri), ptr(light), ptr(t), ptr(work))
+    assert rc == 0
+    return tri, light, t, work
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
+def test_primary_rays(hc, oracle, scene):
+    tris, mats, nodes = load_golden_scene(scene)
+    g = np.load(os.path.join(GOLDEN, "primary_%s.npz" % scene))
+    W = int(g["width"])
+    for jm in (0, 1):
+        otri, olight, ot, od, _ = oracle.primary(Oracle.config("udpt"), default_cam_array(), tris, nodes, int(g["rand"]), jm, W, W)
+        tri, light, t, work = _trace(hc, od, None, 0, tris, nodes)
+        assert (tri == g["tri_j%d" % jm]).all() and (light == g["light_j%d" % jm]).all()
+        assert (t.view(np.uint32) == ot.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
+def test_random_rays_closest_and_any(hc, oracle, scene):
+    tris, mats, nodes = load_golden_scene(scene)
+    rng = np.random.RandomState(11); n = 60000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:500, 0] = 0; d[500:1000, 1] = 0; d[1000:1500, 2] = 0; d[1500:1600, :2] = 0      # exercise the NaN-guarded slabs
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    tm = rng.uniform(0.01, 2.5, n).astype(np.float32)
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes)
+    assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all()
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, nodes)
+    atri, alight, _, _ = _trace(hc, od, tm, 1, tris, nodes)
+    assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
+
+
+def test_layout_rejects_malformed_input(hc):
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    od = np.zeros((1, 6), np.float32); od[0, 5] = -1
+    bad = nodes.copy(); bad["child_idx"][0] = 10 ** 6
+    tri = np.zeros(1, np.int32); light = np.zeros(1, np.int32)
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None) == -1
+    bad = nodes.copy(); leaf = int(np.nonzero(bad["vert_len"] > 0)[0][0]); bad["vert_list"][leaf, 0] = 9999
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None) == -1

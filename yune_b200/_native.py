@@ -16,7 +16,7 @@ class Stats(C.Structure):
     _fields_ = [("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("tonemap_ms", C.c_double),
                 ("samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("timed_iterations", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/*.h declares is listed here (tests check the export table against it)
@@ -45,6 +45,8 @@ CUDA_API = {
     "yune_synchronize": (C.c_int, [C.c_void_p]),
     "yune_trace_primary": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yune_trace_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yune_debug_capture_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "yune_debug_read_captured": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "yune_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
 }
 HOST_API = {

@@ -283,6 +283,17 @@ class RendererCore:
         a = np.ascontiguousarray(img, np.float32)
         self.cl_manager.check(self._lib.yune_write_sum(self._ctx, _ptr(a)))
 
+    def captureRays(self, iteration, max_rays):
+        self.cl_manager.check(self._lib.yune_debug_capture_rays(self._ctx, int(iteration), int(max_rays)))
+
+    def readCaptured(self, which):
+        n, nq = C.c_int(), C.c_int()
+        self.cl_manager.check(self._lib.yune_debug_read_captured(self._ctx, int(which), None, None, C.byref(n), C.byref(nq)))
+        od = np.zeros((n.value, 6), np.float32); tm = np.zeros(n.value, np.float32)
+        if n.value:
+            self.cl_manager.check(self._lib.yune_debug_read_captured(self._ctx, int(which), _ptr(od), _ptr(tm), C.byref(n), C.byref(nq)))
+        return od, tm, nq.value
+
     def tracePrimary(self, jitter_mode=0, rand=0):
         n = self.width * self.height
         tri = np.zeros(n, np.int32); light = np.zeros(n, np.int32); t = np.zeros(n, np.float32)

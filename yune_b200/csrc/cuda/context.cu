@@ -46,6 +46,7 @@ struct yune_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;          // 3 per sampled iteration: before shade, before trace, after trace
     std::string err;
 
     // host copies of the reference-layout buffers (re-laid-out lazily when both are present)
@@ -68,6 +69,10 @@ struct yune_ctx {
     // hook scratch
     float4 *hk_o = nullptr, *hk_d = nullptr, *hk_hit = nullptr; int *hk_tri = nullptr, *hk_light = nullptr; float *hk_t = nullptr, *hk_od = nullptr, *hk_tmax = nullptr;
     unsigned char* hk_vis = nullptr; int* hk_cnt = nullptr; int hk_cap = 0;
+
+    // ray capture (measurement aid)
+    float4 *cap_eo = nullptr, *cap_ed = nullptr, *cap_so = nullptr, *cap_sd = nullptr; int* cap_cnt = nullptr; int cap_alloc = 0;
+    int cap_iteration = -1, cap_max = 0; int cap_counts[4] = {0, 0, 0, 0};
 
     // options
     int opt_pool_slots = 1 << 20, opt_smem_nodes = 1024, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
@@ -213,11 +218,13 @@ void yune_destroy(yune_ctx* c)
     free_pool(c);
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats);
     dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_ctr); dfree(c->d_tot);
+    dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
     dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
     if (c->h_tot) cudaFreeHost(c->h_tot);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
+    for (auto& e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -382,7 +389,14 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     t.sq_o = c->pool.sq_o; t.sq_d = c->pool.sq_d; t.vis_a = c->pool.vis_l; t.vis_b = c->pool.evt_vis; t.tot = c->d_tot;
 
     yune_stats st{};
-    float shade_ms = 0.f, trace_ms = 0.f;
+    // Stage timing: every `time_stages`-th iteration is bracketed by CUDA events on the launching stream (no host
+    // synchronisation inside the loop); at most 128 iterations are sampled per call.
+    const int kMaxTimed = 128;
+    int n_timed = 0;
+    if (c->opt_time_stages > 0 && c->ev_pool.empty()) {
+        c->ev_pool.resize(3 * kMaxTimed);
+        for (auto& e : c->ev_pool) Y_CUDA(c, cudaEventCreate(&e));
+    }
     Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     int it = 0;
     bool done = spp_count == 0;
@@ -392,18 +406,14 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             a.parity = p;
             t.n_extend = &c->d_ctr[p].n_extend; t.fetch_extend = &c->d_ctr[p].fetch_extend;
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
-            if (c->opt_time_stages) Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+            const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
+            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
             Y_CUDA(c, launch_shade_udpt(a, c->stream));
-            if (c->opt_time_stages) {
-                Y_CUDA(c, cudaEventRecord(c->ev2, c->stream)); Y_CUDA(c, cudaEventSynchronize(c->ev2));
-                float ms = 0; cudaEventElapsedTime(&ms, c->ev1, c->ev2); shade_ms += ms;
-                Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-            }
+            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
+            if (it == c->cap_iteration && c->cap_max > 0)
+                Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));
             Y_CUDA(c, launch_trace(t, tl.grid, tl.smem, c->opt_count_work != 0, c->stream));
-            if (c->opt_time_stages) {
-                Y_CUDA(c, cudaEventRecord(c->ev2, c->stream)); Y_CUDA(c, cudaEventSynchronize(c->ev2));
-                float ms = 0; cudaEventElapsedTime(&ms, c->ev1, c->ev2); trace_ms += ms;
-            }
+            if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 2], c->stream)); n_timed++; }
             Y_CUDA(c, launch_iter_end(c->d_ctr, c->d_tot, p, c->stream));
             st.kernel_launches += 3; st.trace_launches += 1;
         }
@@ -412,6 +422,14 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
         if (c->h_tot->live_last == 0) done = true;
         else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
     }
+    float shade_ms = 0.f, trace_ms = 0.f;
+    for (int i = 0; i < n_timed; i++) {
+        float m1 = 0, m2 = 0;
+        cudaEventElapsedTime(&m1, c->ev_pool[3 * i], c->ev_pool[3 * i + 1]);
+        cudaEventElapsedTime(&m2, c->ev_pool[3 * i + 1], c->ev_pool[3 * i + 2]);
+        shade_ms += m1; trace_ms += m2;
+    }
+    st.timed_iterations = (uint32_t)n_timed;
     Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     Y_CUDA(c, cudaEventSynchronize(c->ev1));
     float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -476,6 +494,44 @@ int yune_sum_device_ptr(yune_ctx* c, void** dptr, size_t* n_bytes)
 int yune_stream(yune_ctx* c, void** s) { if (!c || !s) return YUNE_ERR_INVALID; *s = (void*)c->stream; return YUNE_OK; }
 int yune_synchronize(yune_ctx* c) { if (!c) return YUNE_ERR_INVALID; Y_CUDA(c, cudaSetDevice(c->device)); Y_CUDA(c, cudaStreamSynchronize(c->stream)); return YUNE_OK; }
 int yune_get_stats(yune_ctx* c, yune_stats* out) { if (!c || !out) return YUNE_ERR_INVALID; *out = c->stats; return YUNE_OK; }
+
+// ---- measurement aid: capture the rays of one wavefront iteration ----
+int yune_debug_capture_rays(yune_ctx* c, int iteration, int max_rays)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (max_rays < 0 || max_rays > (1 << 24)) Y_FAIL(c, YUNE_ERR_INVALID, "yune_debug_capture_rays: max_rays out of range");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    if (max_rays > c->cap_alloc) {
+        dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt); c->cap_alloc = 0;
+        const size_t N = (size_t)max_rays;
+        Y_CUDA(c, cudaMalloc(&c->cap_eo, N * 16)); Y_CUDA(c, cudaMalloc(&c->cap_ed, N * 16));
+        Y_CUDA(c, cudaMalloc(&c->cap_so, N * 16)); Y_CUDA(c, cudaMalloc(&c->cap_sd, N * 16)); Y_CUDA(c, cudaMalloc(&c->cap_cnt, 16));
+        c->cap_alloc = max_rays;
+    }
+    if (c->cap_cnt) Y_CUDA(c, cudaMemset(c->cap_cnt, 0, 16));
+    c->cap_iteration = max_rays > 0 ? iteration : -1; c->cap_max = max_rays;
+    return YUNE_OK;
+}
+int yune_debug_read_captured(yune_ctx* c, int which, float* od6, float* tmax, int* n_captured, int* n_in_queue)
+{
+    if (!c || !n_captured) return YUNE_ERR_INVALID;
+    if (!c->cap_cnt) Y_FAIL(c, YUNE_ERR_STATE, "no capture was armed");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    int cnt[4];
+    Y_CUDA(c, cudaMemcpy(cnt, c->cap_cnt, 16, cudaMemcpyDeviceToHost));
+    const int n = which ? cnt[1] : cnt[0];
+    *n_captured = n; if (n_in_queue) *n_in_queue = which ? cnt[3] : cnt[2];
+    if (n == 0 || !od6) return YUNE_OK;
+    std::vector<float> o((size_t)n * 4), d((size_t)n * 4);
+    Y_CUDA(c, cudaMemcpy(o.data(), which ? c->cap_so : c->cap_eo, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    Y_CUDA(c, cudaMemcpy(d.data(), which ? c->cap_sd : c->cap_ed, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        od6[6 * (size_t)i + 0] = o[4 * (size_t)i]; od6[6 * (size_t)i + 1] = o[4 * (size_t)i + 1]; od6[6 * (size_t)i + 2] = o[4 * (size_t)i + 2];
+        od6[6 * (size_t)i + 3] = d[4 * (size_t)i]; od6[6 * (size_t)i + 4] = d[4 * (size_t)i + 1]; od6[6 * (size_t)i + 5] = d[4 * (size_t)i + 2];
+        if (tmax) tmax[i] = o[4 * (size_t)i + 3];
+    }
+    return YUNE_OK;
+}
 
 // ---- parity hooks ----
 static int ensure_hook(yune_ctx* c, int n)

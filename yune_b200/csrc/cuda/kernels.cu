@@ -301,8 +301,10 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
                                 }
                             }
                             // Branch "light sample occluded": sample_glossy = false and brdf_prob = 0 keep their initial values
-                            // (:541-542), so the BRDF sample is cosine-distributed and evaluateBRDF divides by zero.  Reproduced
-                            // as is (it is why the reference's MIS images collect inf / pink pixels near shadow edges).
+                            // (:541-542), so the BRDF sample is cosine-distributed and evaluateBRDF divides by zero (:621).  In the
+                            // reference that makes brdf_sample = (inf, inf, inf, inf) * light ke (.., .., .., 0): the W LANE is inf*0 =
+                            // NaN, the kernel's any(isnan(color)) fires (:193) and the WHOLE SAMPLE becomes PINK.  We carry that outcome
+                            // as a NaN contribution (finalisation turns a NaN sample into PINK), not as the infinities of the xyz lanes.
                             const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
                             if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
                             if (pdfO > 0.0f) {
@@ -312,10 +314,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
                                     MO.o = vadd(hp, vscale(dq, YUNE_EPS)); MO.d = dq; MO.tmax = INFINITY;
                                     reaches = MO.has = (light_loop(lights, n_lights, MO.o, MO.d, MO.tmax) == j);
                                 }
-                                if (reaches) {
-                                    BO = vscale(vmul(eval_brdf(mat, dq, w_o, n, false, 0.0f, true, use_on), Lke), fmaxf(vdot(dq, n), 0.0f));
-                                    BO = vscale(BO, YF_DIV(power_heuristic(pdfO, light_pdf, pdfO), pdfO));
-                                }
+                                if (reaches) { const float qnan = __int_as_float(0x7fc00000); BO = v3(qnan, qnan, qnan); }
                             }
                         }
                         nee_pending = S.has || MV.has || MO.has;
@@ -529,6 +528,17 @@ __global__ void k_hook_finish(int n, int any_hit, const float4* ray_o, const flo
     }
 }
 
+// Copies the first `max_rays` rays of this iteration's two queues into side buffers (measurement aid: the bench hands
+// them to the oracle, which counts the box/triangle tests of ITS ordered walk -- the roofline's work model).
+__global__ void k_capture(PathPool P, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ne = min(c->n_extend, max_rays), ns = min(c->n_shadow, max_rays);
+    if (i == 0) { counts[0] = ne; counts[1] = ns; counts[2] = c->n_extend; counts[3] = c->n_shadow; }
+    if (i < ne) { const int s = P.eq[i]; ext_o[i] = P.ray_o[s]; ext_d[i] = P.ray_d[s]; }
+    if (i < ns) { sh_o[i] = P.sq_o[i]; sh_d[i] = P.sq_d[i]; }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------------------
@@ -562,6 +572,11 @@ cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st)
     const int grid = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
     if (a.mis) k_shade_udpt<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
     else       k_shade_udpt<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st)
+{
+    k_capture<<<ceil_div(max_rays, 256), 256, 0, st>>>(p, c, max_rays, ext_o, ext_d, sh_o, sh_d, counts);
     return cudaGetLastError();
 }
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st)

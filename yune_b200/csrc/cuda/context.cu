@@ -304,8 +304,13 @@ int yune_setup_image_buffers(yune_ctx* c, int W, int H)
 {
     if (!c || W <= 0 || H <= 0 || (long long)W * H > (1ll << 30)) { if (c) c->err = "yune_setup_image_buffers: bad size"; return YUNE_ERR_INVALID; }
     Y_CUDA(c, cudaSetDevice(c->device));
-    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr);
     const size_t n = (size_t)W * H;
+    if (c->d_sum && c->W == W && c->H == H) {          // same size: keep the allocation (and any pointer handed out), just clear
+        Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n * 16, c->stream));
+        Y_CUDA(c, cudaStreamSynchronize(c->stream));
+        return YUNE_OK;
+    }
+    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr);
     Y_CUDA(c, cudaMalloc(&c->d_sum, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_hdr, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_ldr, n * 16));
     Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n * 16, c->stream));
     Y_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, n * 16, c->stream));

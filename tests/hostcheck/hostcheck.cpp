@@ -40,14 +40,13 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
         V3 o = v3(r[0], r[1], r[2]), d = v3(r[3], r[4], r[5]);
         float t = tmax ? tmax[i] : INFINITY;
         int lid = light_loop(L, nlights, o, d, t);
-        RayPre ray = make_ray(o, d);
         WorkCount wc = {0, 0};
         if (any) {
-            bool occ = lid >= 0 || any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, ray, t, &wc);
+            bool occ = lid >= 0 || any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, &wc);
             tri_id[i] = occ ? 0 : -1; light_id[i] = lid; if (t_hit) t_hit[i] = t;
         } else {
             HitRec h;
-            closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, ray, t, h, &wc);
+            closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             tri_id[i] = h.tri; light_id[i] = h.tri >= 0 ? -1 : lid; if (t_hit) t_hit[i] = h.t;
         }
         nb += wc.box; nt += wc.tri;

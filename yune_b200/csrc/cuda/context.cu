@@ -75,7 +75,8 @@ struct yune_ctx {
     int cap_iteration = -1, cap_max = 0; int cap_counts[4] = {0, 0, 0, 0};
 
     // options
-    int opt_pool_slots = 1 << 20, opt_smem_nodes = 1024, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_pool_slots = 1 << 20, opt_smem_nodes = 2048, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
     yune_stats stats{};
@@ -149,7 +150,7 @@ static int ensure_scene(yune_ctx* c)
     return YUNE_OK;
 }
 
-struct TraceLaunch { int grid; size_t smem; };
+struct TraceLaunch { int grid, block; size_t smem; };
 static int trace_config(yune_ctx* c, TraceLaunch& tl)
 {
     int n_smem = c->opt_smem_nodes < c->sc.n_inner ? c->opt_smem_nodes : c->sc.n_inner;
@@ -158,8 +159,10 @@ static int trace_config(yune_ctx* c, TraceLaunch& tl)
     c->sc.n_smem_pairs = n_smem;
     tl.smem = (size_t)n_smem * 64;
     Y_CUDA(c, trace_set_smem(tl.smem > 0 ? tl.smem : 16));
-    int per_sm = trace_blocks_per_sm(tl.smem);
+    tl.block = c->opt_trace_block;
+    int per_sm = trace_blocks_per_sm(tl.block, tl.smem);
     if (per_sm < 1) Y_FAIL(c, YUNE_ERR_CUDA, "trace kernel does not fit on an SM with %zu bytes of shared memory", tl.smem);
+    if (c->opt_trace_blocks_per_sm > 0 && per_sm > c->opt_trace_blocks_per_sm) per_sm = c->opt_trace_blocks_per_sm;
     tl.grid = c->sm_count * per_sm;
     return YUNE_OK;
 }
@@ -338,7 +341,8 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"pool_slots", &c->opt_pool_slots}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
-        {"time_stages", &c->opt_time_stages},
+        {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -350,6 +354,8 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
     const int v = (int)value;
     if (p == &c->opt_pool_slots && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be in [1024, 2^26]");
+    if (p == &c->opt_trace_block && (v < 32 || v > YUNE_TRACE_MAX_BLOCK || (v & 31))) Y_FAIL(c, YUNE_ERR_INVALID, "trace_block must be a multiple of 32 in [32, 1024]");
+    if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
     *p = v;
@@ -392,6 +398,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     TraceArgs t{};
     t.sc = c->sc; t.eq = c->pool.eq; t.ray_o = c->pool.ray_o; t.ray_d = c->pool.ray_d; t.hit = c->pool.hit;
     t.sq_o = c->pool.sq_o; t.sq_d = c->pool.sq_d; t.vis_a = c->pool.vis_l; t.vis_b = c->pool.evt_vis; t.tot = c->d_tot;
+    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min;
 
     yune_stats st{};
     // Stage timing: every `time_stages`-th iteration is bracketed by CUDA events on the launching stream (no host
@@ -417,7 +424,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));
-            Y_CUDA(c, launch_trace(t, tl.grid, tl.smem, c->opt_count_work != 0, c->stream));
+            Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, c->opt_count_work != 0, c->stream));
             if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 2], c->stream)); n_timed++; }
             Y_CUDA(c, launch_iter_end(c->d_ctr, c->d_tot, p, c->stream));
             st.kernel_launches += 3; st.trace_launches += 1;
@@ -564,7 +571,8 @@ static int hook_trace(yune_ctx* c, int n, int any)
     t.sc = c->sc; t.eq = nullptr; t.ray_o = c->hk_o; t.ray_d = c->hk_d; t.hit = c->hk_hit;
     t.n_extend = c->hk_cnt + 0; t.fetch_extend = c->hk_cnt + 1; t.n_shadow = c->hk_cnt + 2; t.fetch_shadow = c->hk_cnt + 3;
     t.sq_o = c->hk_o; t.sq_d = c->hk_d; t.vis_a = c->hk_vis; t.vis_b = c->hk_vis; t.tot = nullptr;
-    Y_CUDA(c, launch_trace(t, tl.grid, tl.smem, false, c->stream));
+    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min;
+    Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, false, c->stream));
     return YUNE_OK;
 }
 

@@ -70,59 +70,213 @@ struct DevTriFetch {
     }
 };
 
+// ---- device-side walk: the same state machine as trace_core.h (tests/hostcheck validates that one against the oracle;
+// tests/test_gpu_parity.py validates this one), written branch-free so that a warp's lanes stay converged. ----
+//
+// Per-lane state: `cur` >= 0 = pair index to visit (INNER); cur < 0 with leaf_pos < leaf_end = triangles pending (TRI);
+// cur = YUNE_REF_DONE (-1, "a leaf with no triangles") = finished.
+#define YUNE_REF_DONE (-1)
+
+struct Lane {
+    V3 o, d, inv;
+    float t_best, t_prune, u, v;
+    int tri, best_pos, cur, leaf_pos, leaf_end, sp;
+    bool guard;
+};
+
+__device__ __forceinline__ void lane_enter(Lane& L, int ref)
+{
+    const int x = ~ref;
+    const bool leaf = ref < 0;
+    L.cur = ref;
+    L.leaf_pos = leaf ? (x >> 4) : 0;
+    L.leaf_end = leaf ? (x >> 4) + (x & 15) : 0;
+}
+
+__device__ __forceinline__ bool box_fast(V3 o, V3 inv, float lox, float hix, float loy, float hiy, float loz, float hiz, float& entry)
+{
+    const float ax = YF_MUL(YF_SUB(lox, o.x), inv.x), bx = YF_MUL(YF_SUB(hix, o.x), inv.x);
+    const float ay = YF_MUL(YF_SUB(loy, o.y), inv.y), by = YF_MUL(YF_SUB(hiy, o.y), inv.y);
+    const float az = YF_MUL(YF_SUB(loz, o.z), inv.z), bz = YF_MUL(YF_SUB(hiz, o.z), inv.z);
+    const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    entry = fmaxf(t_min, 0.0f);
+    return t_max > entry;
+}
+__device__ __noinline__ float box_guarded(V3 o, V3 inv, float lox, float hix, float loy, float hiy, float loz, float hiz)
+{
+    float t_min = -INFINITY, t_max = INFINITY;       // the reference's per-axis NaN guards (udpt.cl:400-416), rare path
+    slab_guarded(lox, hix, o.x, inv.x, t_min, t_max);
+    slab_guarded(loy, hiy, o.y, inv.y, t_min, t_max);
+    slab_guarded(loz, hiz, o.z, inv.z, t_min, t_max);
+    const float entry = fmaxf(t_min, 0.0f);
+    return (t_max > entry) ? entry : -1.0f;          // entry >= 0 on a hit, -1 on a miss
+}
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o, float4 d, WorkCount& wc)
+{
+    L.o = xyz(o); L.d = xyz(d);
+    L.inv = v3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));       // correctly rounded 1/x == '1 / ray->dir' (udpt.cl:395)
+    L.guard = !(fabsf(L.inv.x) < INFINITY && fabsf(L.inv.y) < INFINITY && fabsf(L.inv.z) < INFINITY);
+    L.t_best = o.w; L.t_prune = o.w * 1.00001f;
+    L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = 0;
+    float entry; bool hit = false;
+    if (sc.root_ref != YUNE_REF_EMPTY) {
+        if (COUNT) wc.box++;
+        if (L.guard) { entry = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]); hit = entry >= 0.0f; }
+        else hit = box_fast(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
+    }
+    lane_enter(L, hit ? sc.root_ref : YUNE_REF_DONE);
+}
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const float4* s_pairs, WorkCount& wc)
+{
+    float4 q0, q1, q2, q3;
+    if (L.cur < sc.n_smem_pairs) { const float4* p = s_pairs + 4 * L.cur; q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3]; }
+    else { const float4* p = sc.pairs + 4 * (size_t)L.cur; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3); }
+    const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
+    float e0, e1; bool h0, h1;
+    if (!L.guard) {
+        h0 = box_fast(L.o, L.inv, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
+        h1 = box_fast(L.o, L.inv, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
+    } else {
+        e0 = box_guarded(L.o, L.inv, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y); h0 = e0 >= 0.0f;
+        e1 = box_guarded(L.o, L.inv, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w); h1 = e1 >= 0.0f;
+    }
+    if (COUNT) wc.box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
+    h0 = h0 && (ref0 != YUNE_REF_EMPTY) && !(e0 > L.t_prune);
+    h1 = h1 && (ref1 != YUNE_REF_EMPTY) && !(e1 > L.t_prune);
+    const bool both = h0 && h1;
+    const bool swap = !ANY && both && (e1 < e0);
+    int next = (h0 && !swap) ? ref0 : ref1;
+    if (both) stack[L.sp++] = swap ? ref0 : ref1;
+    if (!(h0 || h1)) { next = YUNE_REF_DONE; if (L.sp > 0) next = stack[--L.sp]; }
+    lane_enter(L, next);
+}
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, WorkCount& wc)
+{
+    const int pos = L.leaf_pos++;
+    const float4* p = sc.tris + 3 * (size_t)pos;
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    if (COUNT) wc.tri++;
+    // rayTriangleIntersection (udpt.cl:326-373), evaluated without early exits: the rejected lanes would idle anyway, and
+    // NaNs (det == 0) fall through the comparisons exactly as in the sequential form.
+    const V3 e1 = xyz(b), e2 = xyz(c);
+    const V3 pvec = vcross(L.d, e2);
+    const float det = vdot(e1, pvec);
+    const float inv_det = __frcp_rn(det);
+    const V3 dist = vsub(L.o, xyz(a));
+    const float u = YF_MUL(vdot(pvec, dist), inv_det);
+    const V3 qvec = vcross(dist, e1);
+    const float v = YF_MUL(vdot(qvec, L.d), inv_det);
+    const float t = YF_MUL(vdot(e2, qvec), inv_det);
+    const bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
+    bool finished_leaf = L.leaf_pos >= L.leaf_end;
+    if (ANY) {
+        if (inside && t > 0.0f && t < L.t_best) { L.tri = 0; L.sp = 0; finished_leaf = true; }        // udpt.cl:306-308
+    } else {
+        const bool accept = inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && pos < L.best_pos));
+        if (accept) { L.t_best = t; L.u = u; L.v = v; L.tri = __float_as_int(a.w); L.best_pos = pos; L.t_prune = t * 1.00001f; }
+    }
+    if (finished_leaf) {
+        int next = YUNE_REF_DONE;
+        if (L.sp > 0) next = stack[--L.sp];
+        lane_enter(L, next);
+    }
+}
+
+// Drains one ray queue with a persistent warp.  Lanes hold one ray each; the warp alternates between an INNER phase and a
+// TRI phase, and stays in a phase as long as at least `phase_min` lanes still want that operation, so that every executed
+// instruction of the two hot bodies has many lanes behind it.  Lanes that finish are refilled from the queue head (one
+// atomicAdd per warp, ballot/popc ranks) once `refill_idle` of them are idle.
+#define YUNE_PHASE_MAX   8
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_pairs, WorkCount& wc)
+{
+    const DevScene& sc = A.sc;
+    const int lane = threadIdx.x & 31;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    const int n = ANY ? *A.n_shadow : *A.n_extend;
+    int* fetch = ANY ? A.fetch_shadow : A.fetch_extend;
+    int stack[YUNE_STACK_SIZE];
+    Lane L; L.cur = YUNE_REF_DONE; L.leaf_pos = L.leaf_end = 0; L.sp = 0; L.tri = -1; L.guard = false;
+    bool have = false;          // this lane holds a ray
+    int  where = 0;             // extension: slot index; shadow: answer target
+    bool exhausted = (n == 0);
+    const int refill_idle = A.refill_idle, phase_min = A.phase_min;
+
+    for (;;) {
+        // ---- retire finished rays ----
+        if (have && L.cur == YUNE_REF_DONE) {
+            if (ANY) {
+                const unsigned char vis = L.tri >= 0 ? 0 : 1;
+                if (where >= 0) A.vis_a[where] = vis; else A.vis_b[~where] = vis;
+            } else A.hit[where] = make_float4(L.t_best, L.u, L.v, __int_as_float(L.tri));
+            have = false;
+        }
+        // ---- refill ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_idle)) {
+            const int n_idle = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fetch, n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + n_idle >= n;
+            const int q = base + __popc(idle & lane_lt);
+            if (!have && q < n) {
+                float4 o, d;
+                if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
+                else { where = A.eq ? A.eq[q] : q; o = A.ray_o[where]; d = A.ray_d[where]; }
+                lane_init<ANY, COUNT>(L, sc, o, d, wc);
+                have = true;
+            }
+        }
+        // ---- INNER phase ----
+        bool progressed = false;
+        #pragma unroll 1
+        for (int k = 0; k < YUNE_PHASE_MAX; k++) {        // bounded so that finished lanes are retired / refilled regularly
+            const bool want = L.cur >= 0;
+            if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
+            if (want) lane_inner_step<ANY, COUNT>(L, stack, sc, s_pairs, wc);
+            progressed = true;
+        }
+        // ---- TRI phase ----
+        #pragma unroll 1
+        for (int k = 0; k < YUNE_PHASE_MAX; k++) {
+            const bool want = L.leaf_pos < L.leaf_end;
+            if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
+            if (want) lane_tri_step<ANY, COUNT>(L, stack, sc, wc);
+            progressed = true;
+        }
+        // ---- thin warp (fewer than phase_min lanes in either mode): one step of each kind ----
+        if (!progressed) {
+            if (L.cur >= 0) lane_inner_step<ANY, COUNT>(L, stack, sc, s_pairs, wc);
+            __syncwarp();
+            if (L.leaf_pos < L.leaf_end) lane_tri_step<ANY, COUNT>(L, stack, sc, wc);
+            __syncwarp();
+        }
+    }
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(YUNE_TRACE_BLOCK, YUNE_TRACE_MIN_BLOCKS) k_trace(TraceArgs A)
+__global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
 {
     extern __shared__ float4 s_pairs[];
     const DevScene& sc = A.sc;
     for (int i = threadIdx.x; i < sc.n_smem_pairs * 4; i += blockDim.x) s_pairs[i] = __ldg(sc.pairs + i);
     __syncthreads();
 
-    DevPairFetch pf; pf.smem = s_pairs; pf.gmem = sc.pairs; pf.n_smem = sc.n_smem_pairs;
-    DevTriFetch tf; tf.gmem = sc.tris;
-    const int lane = threadIdx.x & 31;
     WorkCount wc; wc.box = 0; wc.tri = 0;
-
-    // ---- shadow queue: any-hit ----
-    {
-        const int n = *A.n_shadow;
-        for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(A.fetch_shadow, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const int q = base + lane;
-            if (q < n) {
-                const float4 o = A.sq_o[q], d = A.sq_d[q];
-                const RayPre r = make_ray(xyz(o), xyz(d));
-                const bool occluded = any_hit<DevPairFetch, DevTriFetch, COUNT>(pf, tf, sc.root_ref, sc.root_lo, sc.root_hi, r, o.w, &wc);
-                const int target = __float_as_int(d.w);
-                if (target >= 0) A.vis_a[target] = occluded ? 0 : 1;
-                else A.vis_b[~target] = occluded ? 0 : 1;
-            }
-        }
-    }
-    // ---- extension queue: closest hit ----
-    {
-        const int n = *A.n_extend;
-        for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(A.fetch_extend, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const int q = base + lane;
-            if (q < n) {
-                const int s = A.eq ? A.eq[q] : q;
-                const float4 o = A.ray_o[s], d = A.ray_d[s];
-                const RayPre r = make_ray(xyz(o), xyz(d));
-                HitRec h;
-                closest_hit<DevPairFetch, DevTriFetch, COUNT>(pf, tf, sc.root_ref, sc.root_lo, sc.root_hi, r, o.w, h, &wc);
-                A.hit[s] = make_float4(h.t, h.u, h.v, __int_as_float(h.tri));
-            }
-        }
-    }
+    trace_queue<true, COUNT>(A, s_pairs, wc);      // shadow rays: any hit
+    trace_queue<false, COUNT>(A, s_pairs, wc);     // extension rays: closest hit
     if (COUNT) {
-        // warp-reduce then one atomic per warp
+        const int lane = threadIdx.x & 31;
         unsigned long long b = wc.box, t = wc.tri;
         for (int o = 16; o > 0; o >>= 1) { b += __shfl_down_sync(0xffffffffu, b, o); t += __shfl_down_sync(0xffffffffu, t, o); }
         if (lane == 0 && A.tot) { atomicAdd(&A.tot->box_tests, b); atomicAdd(&A.tot->tri_tests, t); }
@@ -544,10 +698,10 @@ __global__ void k_capture(PathPool P, const IterCounters* c, int max_rays, float
 // ------------------------------------------------------------------------------------------------------------
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
 
-cudaError_t launch_trace(const TraceArgs& a, int grid, size_t smem_bytes, bool count, cudaStream_t st)
+cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
-    if (count) k_trace<true><<<grid, YUNE_TRACE_BLOCK, smem_bytes, st>>>(a);
-    else       k_trace<false><<<grid, YUNE_TRACE_BLOCK, smem_bytes, st>>>(a);
+    if (count) k_trace<true><<<grid, block, smem_bytes, st>>>(a);
+    else       k_trace<false><<<grid, block, smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t trace_set_smem(size_t smem_bytes)
@@ -556,10 +710,10 @@ cudaError_t trace_set_smem(size_t smem_bytes)
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
-int trace_blocks_per_sm(size_t smem_bytes)
+int trace_blocks_per_sm(int block, size_t smem_bytes)
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, YUNE_TRACE_BLOCK, smem_bytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, block, smem_bytes) != cudaSuccess) return 0;
     return n;
 }
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st)

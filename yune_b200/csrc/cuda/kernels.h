@@ -4,8 +4,7 @@
 
 #include "wavefront_types.h"
 
-#define YUNE_TRACE_BLOCK      256
-#define YUNE_TRACE_MIN_BLOCKS 2
+#define YUNE_TRACE_MAX_BLOCK  1024     /* k_trace is compiled for <= 64 registers so any block size up to this fits */
 #define YUNE_SHADE_BLOCK      256
 
 namespace yune {
@@ -21,11 +20,13 @@ struct TraceArgs {
     const float4* sq_o; const float4* sq_d; unsigned char* vis_a; unsigned char* vis_b;
     const int* n_shadow; int* fetch_shadow;
     Totals* tot;
+    int refill_idle;      // refill a warp once this many of its lanes are idle
+    int phase_min;        // stay in the INNER / TRI phase while at least this many lanes want that operation
 };
 
-cudaError_t launch_trace(const TraceArgs& a, int grid, size_t smem_bytes, bool count, cudaStream_t st);
+cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st);
 cudaError_t trace_set_smem(size_t smem_bytes);
-int         trace_blocks_per_sm(size_t smem_bytes);
+int         trace_blocks_per_sm(int block, size_t smem_bytes);
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
 cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st);
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);

@@ -89,101 +89,125 @@ struct HitRec { float t, u, v; int tri; };   // tri = original triangle index, -
 
 struct WorkCount { unsigned box, tri; };
 
-// Closest hit.  `fetch_pair(idx, q0..q3)` and `fetch_tri(pos, t0, t1, t2)` load one record each.
-template <class PairFetch, class TriFetch, bool COUNT>
-YUNE_HD void closest_hit(const PairFetch& fetch_pair, const TriFetch& fetch_tri, int root_ref,
-                         const float* root_lo, const float* root_hi,
-                         const RayPre& r, float t_in, HitRec& out, WorkCount* wc)
-{
-    out.t = t_in; out.u = 0.0f; out.v = 0.0f; out.tri = -1;
-    if (root_ref == YUNE_REF_EMPTY) return;
-    float entry;
-    if (COUNT) wc->box++;
-    if (!box_hit(r, root_lo[0], root_hi[0], root_lo[1], root_hi[1], root_lo[2], root_hi[2], entry)) return;   // udpt.cl:295-296
+// ------------------------------------------------------------------------------------------------------------------
+// The walk as a per-ray STATE MACHINE whose transitions are two fixed-size operations:
+//     inner step = fetch one pair record, test both child boxes, descend / push / pop
+//     tri step   = fetch one triangle record, Moller-Trumbore, maybe accept
+// A ray is always in exactly one of three modes: INNER (cur >= 0), TRI (leaf_pos < leaf_end) or done.  Written this way
+// the GPU kernel can schedule a warp by majority vote -- every pass executes the ONE operation most lanes are waiting for,
+// with all those lanes converged -- instead of letting 32 rays serialise through divergent loops (the first version of
+// this kernel ran with 4.4 of 32 threads active per instruction; profiles/ has the ncu capture).  The host wrappers
+// below drive the same machine one ray at a time, which is what tests/hostcheck compares against the oracle.
+// ------------------------------------------------------------------------------------------------------------------
+#define YUNE_MODE_NONE  0
+#define YUNE_MODE_INNER 1
+#define YUNE_MODE_TRI   2
 
-    int stack[YUNE_STACK_SIZE];
-    int sp = 0, cur = root_ref, best_pos = -1;
-    float t_prune = t_in * 1.00001f;          // inf stays inf
-    for (;;) {
-        if (cur >= 0) {
-            F4 q0, q1, q2, q3;
-            fetch_pair(cur, q0, q1, q2, q3);
-            const int ref0 = YF_ASINT(q3.x), ref1 = YF_ASINT(q3.y);
-            float e0, e1;
-            if (COUNT) wc->box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
-            bool h0 = (ref0 != YUNE_REF_EMPTY) && box_hit(r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
-            bool h1 = (ref1 != YUNE_REF_EMPTY) && box_hit(r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
-            h0 = h0 && !(e0 > t_prune);
-            h1 = h1 && !(e1 > t_prune);
-            if (h0 && h1) {
-                const bool swap = e1 < e0;
-                stack[sp++] = swap ? ref0 : ref1;
-                cur = swap ? ref1 : ref0;
-                continue;
-            }
-            if (h0) { cur = ref0; continue; }
-            if (h1) { cur = ref1; continue; }
-        } else {
-            const int first = (~cur) >> 4, count = (~cur) & 15;
-            for (int k = 0; k < count; k++) {
-                F4 a, b, c;
-                fetch_tri(first + k, a, b, c);
-                float t, u, v;
-                if (COUNT) wc->tri++;
-                if (!tri_test(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) continue;
-                // udpt.cl:373 't > 0 && t < ray->length', with the reference's first-come rule for exact ties
-                if (t > 0.0f && (t < out.t || (t == out.t && best_pos >= 0 && first + k < best_pos))) {
-                    out.t = t; out.u = u; out.v = v; out.tri = YF_ASINT(a.w); best_pos = first + k;
-                    t_prune = t * 1.00001f;
-                }
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
-    }
+struct TraceState {
+    RayPre r;
+    float t_best, t_prune;      // current ray length; pruning bound = t_best * (1 + 1e-5)
+    float u, v;
+    int   tri, best_pos;        // accepted triangle (original index) and its breadth-first rank; -1 = none
+    int   cur;                  // INNER mode: pair index
+    int   leaf_pos, leaf_end;   // TRI mode: triangles [leaf_pos, leaf_end) of the current leaf are still to be tested
+    int   sp;
+    bool  done;
+};
+
+YUNE_HD int ts_mode(const TraceState& s) { return s.done ? YUNE_MODE_NONE : (s.leaf_pos < s.leaf_end ? YUNE_MODE_TRI : YUNE_MODE_INNER); }
+
+YUNE_HD void ts_enter(TraceState& s, int ref)
+{
+    if (ref >= 0) { s.cur = ref; s.leaf_pos = s.leaf_end = 0; }
+    else { const int x = ~ref; s.leaf_pos = x >> 4; s.leaf_end = (x >> 4) + (x & 15); }
+}
+YUNE_HD void ts_pop(TraceState& s, const int* stack)
+{
+    if (s.sp == 0) { s.done = true; s.leaf_pos = s.leaf_end = 0; return; }
+    ts_enter(s, stack[--s.sp]);
 }
 
-// Any hit in (0, t_in): the reference's shadow-ray early-out (udpt.cl:306-308).
-template <class PairFetch, class TriFetch, bool COUNT>
-YUNE_HD bool any_hit(const PairFetch& fetch_pair, const TriFetch& fetch_tri, int root_ref,
-                     const float* root_lo, const float* root_hi, const RayPre& r, float t_in, WorkCount* wc)
+template <bool COUNT>
+YUNE_HD void ts_init(TraceState& s, V3 o, V3 d, float t_in, int root_ref, const float* root_lo, const float* root_hi, WorkCount* wc)
 {
-    if (root_ref == YUNE_REF_EMPTY) return false;
+    s.r = make_ray(o, d);
+    s.t_best = t_in; s.t_prune = t_in * 1.00001f;      // inf stays inf
+    s.u = 0.0f; s.v = 0.0f; s.tri = -1; s.best_pos = -1;
+    s.cur = 0; s.leaf_pos = s.leaf_end = 0; s.sp = 0; s.done = false;
+    if (root_ref == YUNE_REF_EMPTY) { s.done = true; return; }
     float entry;
     if (COUNT) wc->box++;
-    if (!box_hit(r, root_lo[0], root_hi[0], root_lo[1], root_hi[1], root_lo[2], root_hi[2], entry)) return false;
-    int stack[YUNE_STACK_SIZE];
-    int sp = 0, cur = root_ref;
-    const float t_prune = t_in * 1.00001f;
-    for (;;) {
-        if (cur >= 0) {
-            F4 q0, q1, q2, q3;
-            fetch_pair(cur, q0, q1, q2, q3);
-            const int ref0 = YF_ASINT(q3.x), ref1 = YF_ASINT(q3.y);
-            float e0, e1;
-            if (COUNT) wc->box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
-            bool h0 = (ref0 != YUNE_REF_EMPTY) && box_hit(r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
-            bool h1 = (ref1 != YUNE_REF_EMPTY) && box_hit(r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
-            h0 = h0 && !(e0 > t_prune);
-            h1 = h1 && !(e1 > t_prune);
-            if (h0 && h1) { stack[sp++] = ref1; cur = ref0; continue; }
-            if (h0) { cur = ref0; continue; }
-            if (h1) { cur = ref1; continue; }
-        } else {
-            const int first = (~cur) >> 4, count = (~cur) & 15;
-            for (int k = 0; k < count; k++) {
-                F4 a, b, c;
-                fetch_tri(first + k, a, b, c);
-                float t, u, v;
-                if (COUNT) wc->tri++;
-                if (tri_test(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v) && t > 0.0f && t < t_in)
-                    return true;
-            }
+    if (!box_hit(s.r, root_lo[0], root_hi[0], root_lo[1], root_hi[1], root_lo[2], root_hi[2], entry)) { s.done = true; return; }   // udpt.cl:295-296
+    ts_enter(s, root_ref);
+}
+
+// One inner step.  ANY = shadow query (no near/far ordering needed, keeps the reference's child order).
+template <class PairFetch, bool ANY, bool COUNT>
+YUNE_HD void ts_inner_step(TraceState& s, int* stack, const PairFetch& fetch_pair, WorkCount* wc)
+{
+    F4 q0, q1, q2, q3;
+    fetch_pair(s.cur, q0, q1, q2, q3);
+    const int ref0 = YF_ASINT(q3.x), ref1 = YF_ASINT(q3.y);
+    float e0, e1;
+    if (COUNT) wc->box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
+    bool h0 = (ref0 != YUNE_REF_EMPTY) && box_hit(s.r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
+    bool h1 = (ref1 != YUNE_REF_EMPTY) && box_hit(s.r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
+    h0 = h0 && !(e0 > s.t_prune);
+    h1 = h1 && !(e1 > s.t_prune);
+    if (h0 && h1) {
+        const bool swap = !ANY && (e1 < e0);
+        stack[s.sp++] = swap ? ref0 : ref1;
+        ts_enter(s, swap ? ref1 : ref0);
+    } else if (h0) ts_enter(s, ref0);
+    else if (h1) ts_enter(s, ref1);
+    else ts_pop(s, stack);
+}
+
+// One triangle step.
+template <class TriFetch, bool ANY, bool COUNT>
+YUNE_HD void ts_tri_step(TraceState& s, const int* stack, const TriFetch& fetch_tri, WorkCount* wc)
+{
+    const int pos = s.leaf_pos++;
+    F4 a, b, c;
+    fetch_tri(pos, a, b, c);
+    float t, u, v;
+    if (COUNT) wc->tri++;
+    if (tri_test(s.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+        if (ANY) {
+            if (t > 0.0f && t < s.t_best) { s.tri = 0; s.done = true; s.leaf_pos = s.leaf_end = 0; return; }   // udpt.cl:306-308
+        } else if (t > 0.0f && (t < s.t_best || (t == s.t_best && s.best_pos >= 0 && pos < s.best_pos))) {
+            // udpt.cl:373 't > 0 && t < ray->length', with the reference's first-come rule for exact ties
+            s.t_best = t; s.u = u; s.v = v; s.tri = YF_ASINT(a.w); s.best_pos = pos;
+            s.t_prune = t * 1.00001f;
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
-    return false;
+    if (s.leaf_pos >= s.leaf_end) ts_pop(s, stack);
+}
+
+// ---- whole-ray wrappers (host check, hooks): drive the machine until done ----
+template <class PairFetch, class TriFetch, bool COUNT>
+YUNE_HD void closest_hit(const PairFetch& fetch_pair, const TriFetch& fetch_tri, int root_ref,
+                         const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)
+{
+    TraceState s; int stack[YUNE_STACK_SIZE];
+    ts_init<COUNT>(s, o, d, t_in, root_ref, root_lo, root_hi, wc);
+    while (!s.done) {
+        if (s.leaf_pos < s.leaf_end) ts_tri_step<TriFetch, false, COUNT>(s, stack, fetch_tri, wc);
+        else ts_inner_step<PairFetch, false, COUNT>(s, stack, fetch_pair, wc);
+    }
+    out.t = s.t_best; out.u = s.u; out.v = s.v; out.tri = s.tri;
+}
+template <class PairFetch, class TriFetch, bool COUNT>
+YUNE_HD bool any_hit(const PairFetch& fetch_pair, const TriFetch& fetch_tri, int root_ref,
+                     const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, WorkCount* wc)
+{
+    TraceState s; int stack[YUNE_STACK_SIZE];
+    ts_init<COUNT>(s, o, d, t_in, root_ref, root_lo, root_hi, wc);
+    while (!s.done) {
+        if (s.leaf_pos < s.leaf_end) ts_tri_step<TriFetch, true, COUNT>(s, stack, fetch_tri, wc);
+        else ts_inner_step<PairFetch, true, COUNT>(s, stack, fetch_pair, wc);
+    }
+    return s.tri >= 0;
 }
 
 } // namespace yune

@@ -64,8 +64,11 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
 /* Tunables that the reference exposes as '#define's at the top of its kernels or as GUI widgets:
  *   "rr_threshold" (udpt.cl:6 / bdpt.cl:4), "bdpt_bounces" (bdpt.cl:7), "oren_nayar" (0/1: use
  *   udpt-primitives.cl:681-725 for pure-diffuse lobes with sigma^2 = alpha_x),
- *   and engine knobs: "pool_slots", "smem_nodes", "isect" (0 = reference Moller-Trumbore, 1 = watertight),
- *   "max_iterations".  Unknown key -> YUNE_ERR_INVALID. */
+ *   and engine knobs: "pool_slots" (path slots in flight), "smem_nodes" (pair records staged in shared memory),
+ *   "leaf_split" (refine reference leaves holding more than N triangles with padded private subtrees; 0 = off),
+ *   "trace_block", "trace_blocks_per_sm", "refill_idle", "phase_min" (trace-kernel launch shape / warp scheduling),
+ *   "isect" (0 = reference Moller-Trumbore), "max_iterations", "sync_every", "time_stages", "count_work".
+ *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);
 int yune_get_option(yune_ctx* ctx, const char* key, double* value);
 

@@ -27,10 +27,10 @@ LightDev unpack(const yune_quad_light& q)
 
 extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
                         const yune_bvh_node* nodes, int nnodes, const yune_quad_light* lights, int nlights,
-                        int* tri_id, int* light_id, float* t_hit, unsigned long long* work2)
+                        int* tri_id, int* light_id, float* t_hit, unsigned long long* work2, int leaf_split)
 {
     TravLayoutHost lay; std::string err;
-    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err)) return -1;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split)) return -1;
     HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()};
     LightDev L[YUNE_MAX_LIGHTS];
     for (int i = 0; i < nlights; i++) L[i] = unpack(lights[i]);

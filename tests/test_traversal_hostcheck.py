@@ -20,11 +20,11 @@ def hc():
     return C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libyune_hostcheck.so"))
 
 
-def _trace(hc, od, tmax, any_hit, tris, nodes):
+def _trace(hc, od, tmax, any_hit, tris, nodes, leaf_split=0):
     n = od.shape[0]
     tri = np.zeros(n, np.int32); light = np.zeros(n, np.int32); t = np.zeros(n, np.float32); work = np.zeros(2, np.uint64)
     rc = hc.hc_trace(n, ptr(od), ptr(tmax), int(any_hit), ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(LIGHT_UDPT), 1,
-                     ptr(tri), ptr(light), ptr(t), ptr(work))
+                     ptr(tri), ptr(light), ptr(t), ptr(work), int(leaf_split))
     assert rc == 0
     return tri, light, t, work
 
@@ -65,6 +65,6 @@ def test_layout_rejects_malformed_input(hc):
     od = np.zeros((1, 6), np.float32); od[0, 5] = -1
     bad = nodes.copy(); bad["child_idx"][0] = 10 ** 6
     tri = np.zeros(1, np.int32); light = np.zeros(1, np.int32)
-    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None) == -1
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0) == -1
     bad = nodes.copy(); leaf = int(np.nonzero(bad["vert_len"] > 0)[0][0]); bad["vert_list"][leaf, 0] = 9999
-    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None) == -1
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0) == -1

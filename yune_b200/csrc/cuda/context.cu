@@ -77,6 +77,7 @@ struct yune_ctx {
     // options
     int opt_pool_slots = 1 << 20, opt_smem_nodes = 2048, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
+    int opt_leaf_split = 2;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
     yune_stats stats{};
@@ -129,7 +130,7 @@ static int ensure_scene(yune_ctx* c)
         Y_FAIL(c, YUNE_ERR_STATE, "scene incomplete: vertex, material and BVH buffers must all be set up before rendering");
     if (!c->layout_dirty) return YUNE_OK;
     std::string err;
-    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err))
+    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     for (const yune_triangle& t : c->h_tris)
         if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
@@ -342,7 +343,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -358,6 +359,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
+    if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     *p = v;
     return YUNE_OK;
 }

@@ -179,8 +179,9 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     if (ANY) {
         if (inside && t > 0.0f && t < L.t_best) { L.tri = 0; L.sp = 0; finished_leaf = true; }        // udpt.cl:306-308
     } else {
-        const bool accept = inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && pos < L.best_pos));
-        if (accept) { L.t_best = t; L.u = u; L.v = v; L.tri = __float_as_int(a.w); L.best_pos = pos; L.t_prune = t * 1.00001f; }
+        const int rank = __float_as_int(b.w);
+        const bool accept = inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && rank < L.best_pos));
+        if (accept) { L.t_best = t; L.u = u; L.v = v; L.tri = __float_as_int(a.w); L.best_pos = rank; L.t_prune = t * 1.00001f; }
     }
     if (finished_leaf) {
         int next = YUNE_REF_DONE;

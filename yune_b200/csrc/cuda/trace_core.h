@@ -107,7 +107,7 @@ struct TraceState {
     RayPre r;
     float t_best, t_prune;      // current ray length; pruning bound = t_best * (1 + 1e-5)
     float u, v;
-    int   tri, best_pos;        // accepted triangle (original index) and its breadth-first rank; -1 = none
+    int   tri, best_pos;        // accepted triangle (original index) and its reference visiting rank; -1 = none
     int   cur;                  // INNER mode: pair index
     int   leaf_pos, leaf_end;   // TRI mode: triangles [leaf_pos, leaf_end) of the current leaf are still to be tested
     int   sp;
@@ -175,9 +175,9 @@ YUNE_HD void ts_tri_step(TraceState& s, const int* stack, const TriFetch& fetch_
     if (tri_test(s.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
         if (ANY) {
             if (t > 0.0f && t < s.t_best) { s.tri = 0; s.done = true; s.leaf_pos = s.leaf_end = 0; return; }   // udpt.cl:306-308
-        } else if (t > 0.0f && (t < s.t_best || (t == s.t_best && s.best_pos >= 0 && pos < s.best_pos))) {
+        } else if (t > 0.0f && (t < s.t_best || (t == s.t_best && s.best_pos >= 0 && YF_ASINT(b.w) < s.best_pos))) {
             // udpt.cl:373 't > 0 && t < ray->length', with the reference's first-come rule for exact ties
-            s.t_best = t; s.u = u; s.v = v; s.tri = YF_ASINT(a.w); s.best_pos = pos;
+            s.t_best = t; s.u = u; s.v = v; s.tri = YF_ASINT(a.w); s.best_pos = YF_ASINT(b.w);
             s.t_prune = t * 1.00001f;
         }
     }

@@ -10,10 +10,10 @@
 //       q3 = (ref0, ref1, -, -) as int bits
 //     one fetch of four 16-byte vectors tests both children; the 40 dead bytes of vert_list are gone and no
 //     node is read twice (the reference reads each node as a child and again as a parent, udpt.cl:300-316).
-//   triangle records (48 B, LEAF ORDER: leaves sorted by node index, slots in vert_list order):
-//       t0 = (v1.xyz, original triangle index as int bits), t1 = (v2 - v1, 0), t2 = (v3 - v1, 0)
-//     The position in this array equals the reference's breadth-first visiting rank, which is what breaks exact
-//     ties in t the way the reference's first-come-first-kept rule does (udpt.cl:373).
+//   triangle records (48 B, grouped by leaf, leaves in node-index order):
+//       t0 = (v1.xyz, original triangle index as int bits), t1 = (v2 - v1, RANK as int bits), t2 = (v3 - v1, 0)
+//     RANK = the reference's breadth-first visiting order of that triangle slot; it breaks exact ties in t the way the
+//     reference's first-come-first-kept rule does (udpt.cl:373).
 //   shading records (64 B, by ORIGINAL triangle index): normalised vertex normals + matID
 //       s0 = (N1.xyz, matID bits), s1 = (N2.xyz, 0), s2 = (N3.xyz, 0), s3 spare
 //
@@ -37,7 +37,7 @@ struct TravLayoutHost {
     std::vector<F4> pairs;       // 4 per inner node
     std::vector<F4> tris;        // 3 per leaf-ordered triangle
     std::vector<F4> shade;       // 4 per original triangle
-    int   n_inner = 0, n_leaf_tris = 0, n_tris = 0;
+    int   n_inner = 0, n_inner_ref = 0, n_leaf_tris = 0, n_tris = 0;   // n_inner counts refinement pairs too; n_inner_ref = reference inner nodes
     int   root_ref = YUNE_REF_EMPTY;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     int   max_depth = 0;         // stack entries a depth-first walk can need
@@ -45,8 +45,10 @@ struct TravLayoutHost {
 
 // Builds the layout; returns false and sets `err` when the input is malformed (child index out of range,
 // triangle index out of range, leaf with more than 10 slots, tree deeper than YUNE_STACK_SIZE).
+// leaf_split: 0 = keep the reference's leaves (up to 10 triangles); N > 0 = refine every leaf holding more than N triangles
+// with a private, padded subtree (see relayout.cpp) -- same hits, fewer triangle tests.
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err);
+                     TravLayoutHost& out, std::string& err, int leaf_split = 0);
 
 } // namespace yune
 #endif

@@ -100,6 +100,36 @@ def test_per_sample_radiance_matches_oracle(gpu_manager, oracle, scene, variant,
     assert abs(lum_ours - lum_ref) / lum_ref < 2e-3
 
 
+def test_extensions_two_lights_and_oren_nayar_match_oracle(gpu_manager, oracle):
+    """Config C3's ingredients on the unidirectional integrator: a second quad light (sampleLights' N-light branch,
+    udpt.cl:667-697, with the light-pick draw) and Oren-Nayar on pure-diffuse lobes (udpt-primitives.cl:681-725,
+    sigma^2 = alpha_x), both sides fed the same light list / materials."""
+    lights = np.concatenate([yb.LIGHT_UDPT, yb.quad_light((0.6, 0.0, -3.6), (-1, 0, 0), (8, 8, 8), (0, 0.3, 0), (0, 0, 0.3))])
+    m = gpu_manager
+    for variant, opts in (("udpt", ""), ("udpt_mis", "-DMIS")):
+        r, sc = _renderer(m, "teapot", 80, 80, opts=opts)
+        mats = sc.mat_data.copy(); mats["alpha_x"] = 0.25            # sigma^2 for the diffuse walls
+        assert m.setupMatBuffer(mats) and m.setLightSources(lights)
+        m.setOption("oren_nayar", 1)
+        try:
+            r.seed = 404
+            cfg = Oracle.config(variant, rng_mode=1, seed=404, lights=lights, oren_nayar=1)
+            fr = []
+            for s in (0, 3):
+                m.check(r._lib.yune_render(r._ctx, s, 1, 1, r.seed, 1))
+                ours = r.readSum()
+                ref = oracle.samples(cfg, CAM, sc.vert_data, mats, sc.bvh, 80, 80, s, lights=lights)
+                close = (np.abs(ours[..., :3] - ref[..., :3]) <= 1e-3 * np.abs(ref[..., :3]) + 1e-6).all(-1)
+                fr.append(close.mean())
+            assert min(fr) >= 0.995, fr
+            # the second light is really used: the image differs from the single-light render
+            m.setLightSources(None)
+            m.check(r._lib.yune_render(r._ctx, 3, 1, 1, r.seed, 1))
+            assert np.abs(r.readSum()[..., :3] - ours[..., :3]).mean() > 1e-3
+        finally:
+            m.setOption("oren_nayar", 0); m.setLightSources(None)
+
+
 def test_direct_light_only_mode(gpu_manager, oracle):
     """GI_CHECK = 0 (kernel arg 8, udpt.cl:458): direct lighting at the first hit only."""
     r, sc = _renderer(gpu_manager, "cornellbox", 64, 64)

@@ -16,4 +16,6 @@ assert m.createRenderProgram("udpt.cl", compiler_opts="-DMIS")
 sc = yb.Scene(); sc.vert_data, sc.mat_data, sc.bvh = tris, mats, nodes
 assert r.setup(sc)
 st = r.enqueueKernels(spp)
+n=max(st.timed_iterations,1)
+print("timed iters", st.timed_iterations, "avg shade ms", st.shade_ms/n, "avg trace ms", st.trace_ms/n)
 print("spp", spp, "ms", st.render_ms, "Msamples/s", st.samples / st.render_ms / 1e3, "iters", st.iterations, "ext", st.extend_rays, "shadow", st.shadow_rays)

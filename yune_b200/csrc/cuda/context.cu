@@ -63,7 +63,8 @@ struct yune_ctx {
     int W = 0, H = 0;
     float4 *d_sum = nullptr, *d_hdr = nullptr, *d_ldr = nullptr;
 
-    PathPool pool{}; int pool_alloc = 0;
+    PathPool pool{}; int pool_alloc = 0; int pool_integrator = 0;
+    BdptPool bdpt{};
     IterCounters* d_ctr = nullptr; Totals* d_tot = nullptr; Totals* h_tot = nullptr;
 
     // hook scratch
@@ -96,23 +97,30 @@ static void free_pool(yune_ctx* c)
     PathPool& P = c->pool;
     dfree(P.ray_o); dfree(P.ray_d); dfree(P.hit); dfree(P.thr); dfree(P.thr_next); dfree(P.col); dfree(P.pend_l);
     dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
+    dfree(c->bdpt.lp); dfree(c->bdpt.pend_c); dfree(c->bdpt.bmeta);
     P.n_slots = 0; c->pool_alloc = 0;
 }
 
 static int ensure_pool(yune_ctx* c)
 {
     const int n = c->opt_pool_slots;
-    if (c->pool_alloc == n) return YUNE_OK;
+    if (c->pool_alloc == n && c->pool_integrator == c->integrator) return YUNE_OK;
     free_pool(c);
     PathPool& P = c->pool;
     const size_t N = (size_t)n;
+    const bool bd = c->integrator == INTEGRATOR_BDPT;
+    const size_t V = 32;                         // YB_MAXV of bdpt.cu: vertices stored per slot
+    const size_t rays_per_slot = bd ? 3 + V : 3; // shadow rays one slot can emit per iteration
     Y_CUDA(c, cudaMalloc(&P.ray_o, N * 16)); Y_CUDA(c, cudaMalloc(&P.ray_d, N * 16)); Y_CUDA(c, cudaMalloc(&P.hit, N * 16));
     Y_CUDA(c, cudaMalloc(&P.thr, N * 16)); Y_CUDA(c, cudaMalloc(&P.thr_next, N * 16)); Y_CUDA(c, cudaMalloc(&P.col, N * 16));
     Y_CUDA(c, cudaMalloc(&P.pend_l, N * 16)); Y_CUDA(c, cudaMalloc(&P.meta, N * 16));
-    Y_CUDA(c, cudaMalloc(&P.evt_idx, N * 4)); Y_CUDA(c, cudaMalloc(&P.vis_l, N)); Y_CUDA(c, cudaMalloc(&P.eq, N * 4));
-    Y_CUDA(c, cudaMalloc(&P.sq_o, 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.sq_d, 3 * N * 16));
+    Y_CUDA(c, cudaMalloc(&P.evt_idx, N * 4)); Y_CUDA(c, cudaMalloc(&P.vis_l, bd ? N * (1 + V) : N)); Y_CUDA(c, cudaMalloc(&P.eq, N * 4));
+    Y_CUDA(c, cudaMalloc(&P.sq_o, rays_per_slot * N * 16)); Y_CUDA(c, cudaMalloc(&P.sq_d, rays_per_slot * N * 16));
+    if (bd) {
+        Y_CUDA(c, cudaMalloc(&c->bdpt.lp, N * V * 4 * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.pend_c, N * V * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.bmeta, N * 16));
+    }
     Y_CUDA(c, cudaMalloc(&P.evt, 2 * 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.evt_vis, 2 * 4 * N));
-    P.n_slots = n; c->pool_alloc = n;
+    P.n_slots = n; c->pool_alloc = n; c->pool_integrator = c->integrator;
     return YUNE_OK;
 }
 
@@ -251,7 +259,6 @@ int yune_create_render_program(yune_ctx* c, const char* kernel, const char* opts
         if (std::strcmp(opts, "-DMIS") == 0 || std::strcmp(opts, "-D MIS") == 0) mis = 1;
         else Y_FAIL(c, YUNE_ERR_INVALID, "unsupported compiler-opts '%s' (supported: -DMIS)", opts);
     }
-    if (integ == INTEGRATOR_BDPT) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt.cl: the bidirectional integrator is not built into this revision");
     c->integrator = integ; c->mis = mis;
     set_builtin_lights(c);
     return YUNE_OK;
@@ -357,6 +364,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_pool_slots && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be in [1024, 2^26]");
     if (p == &c->opt_trace_block && (v < 32 || v > YUNE_TRACE_MAX_BLOCK || (v & 31))) Y_FAIL(c, YUNE_ERR_INVALID, "trace_block must be a multiple of 32 in [32, 1024]");
     if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
+    if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
@@ -376,7 +384,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
 {
     if (!c) return YUNE_ERR_INVALID;
     if (spp_begin < 0 || spp_count < 0) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: negative sample range");
-    if (c->integrator != INTEGRATOR_UDPT) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: no render program selected");
+    if (c->integrator != INTEGRATOR_UDPT && c->integrator != INTEGRATOR_BDPT) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: no render program selected");
     if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: image buffers not set up");
     if (!c->have_cam) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: camera buffer not set up");
     Y_CUDA(c, cudaSetDevice(c->device));
@@ -397,6 +405,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
 
     RenderArgs a = make_args(c);
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
+    c->bdpt.bounces = c->opt_bdpt_bounces;
     TraceArgs t{};
     t.sc = c->sc; t.eq = c->pool.eq; t.ray_o = c->pool.ray_o; t.ray_d = c->pool.ray_d; t.hit = c->pool.hit;
     t.sq_o = c->pool.sq_o; t.sq_d = c->pool.sq_d; t.vis_a = c->pool.vis_l; t.vis_b = c->pool.evt_vis; t.tot = c->d_tot;
@@ -422,7 +431,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
             const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
-            Y_CUDA(c, launch_shade_udpt(a, c->stream));
+            if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->stream));
+            else Y_CUDA(c, launch_shade_udpt(a, c->stream));
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));

@@ -1,0 +1,143 @@
+// kernel_common.cuh -- device helpers shared by the shade kernels (kernels.cu, bdpt.cu).
+#ifndef YUNE_KERNEL_COMMON_CUH
+#define YUNE_KERNEL_COMMON_CUH
+
+#include "kernels.h"
+#include "shade_core.h"
+#include "rng.h"
+
+namespace yune {
+
+__device__ __forceinline__ V3 xyz(const float4& f) { return v3(f.x, f.y, f.z); }
+__device__ __forceinline__ float4 f4(V3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+
+// warp-aggregated slot allocation in a global counter: returns this lane's index, or -1 for lanes with want == false
+__device__ __forceinline__ int warp_alloc(int* counter, bool want)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return want ? base + __popc(m & ((1u << lane) - 1)) : -1;
+}
+__device__ __forceinline__ long long warp_alloc64(unsigned long long* counter, bool want)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
+}
+
+// camera ray (createRay, udpt.cl:213-238); fp64 where the kernel's literals make it fp64
+__device__ __forceinline__ void create_ray(const float* cam, int W, int H, float pixel_x, float pixel_y, V3& o, V3& d)
+{
+    const float aspect_ratio = (float)(((double)W * 1.0) / (double)H);
+    V3 dir;
+    dir.x = (float)((double)aspect_ratio * ((2.0 * (double)pixel_x / (double)W) - 1.0));
+    dir.y = (float)((2.0 * (double)pixel_y / (double)H) - 1.0);
+    dir.z = -cam[16];
+    V3 w;
+    w.x = vdot(v3(cam[0], cam[1], cam[2]), dir);
+    w.y = vdot(v3(cam[4], cam[5], cam[6]), dir);
+    w.z = vdot(v3(cam[8], cam[9], cam[10]), dir);
+    d = vnormalize(w);
+    o = v3(cam[3], cam[7], cam[11]);
+}
+
+__device__ __forceinline__ MatDev load_material(const float4* mats, int id)
+{
+    const float4* p = mats + 5 * (size_t)id;
+    const float4 ke = __ldg(p), kd = __ldg(p + 1), ks = __ldg(p + 2), a = __ldg(p + 3), b = __ldg(p + 4);
+    MatDev m;
+    m.ke = xyz(ke); m.kd = xyz(kd); m.ks = xyz(ks);
+    m.n = a.x; m.px = a.z; m.py = a.w; m.alpha_x = b.x;
+    m.is_specular = __float_as_int(b.z); m.is_transmissive = __float_as_int(b.w);
+    return m;
+}
+
+struct ShadowOut { bool has; V3 o, d; float tmax; };
+
+// What evaluateDirectLighting (udpt.cl:535-609 == bdpt.cl:642-716) leaves to be resolved by rays:
+//   visible(S) ? Lv + (visible(MV) ? BV : 0) : (visible(MO) ? BO : 0)
+// S = shadow ray to the light sample; MV / MO = BRDF-sampled ray of the branch "S visible" / "S occluded" (MIS only), present
+// only when it meets light j analytically.  mo_is_mv: both branches sampled the same direction, MV answers for MO.
+struct NeeOut {
+    ShadowOut S, MV, MO;
+    bool mo_is_mv;
+    V3 Lv, BV, BO;
+};
+
+// BDPT = the variants bdpt.cl uses inside the same function: un-flipped reflection (bdpt.cl:723, 814), padded lobe
+// probabilities (bdpt.cl:1089-1104).
+template <bool MIS, bool BDPT>
+__device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights, const MatDev& mat, V3 hp, V3 n, V3 w_o,
+                                           U4 u_nee, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t vertex, bool use_on, NeeOut& R)
+{
+    R.S.has = R.MV.has = R.MO.has = false; R.mo_is_mv = false;
+    R.Lv = v3(0, 0, 0); R.BV = v3(0, 0, 0); R.BO = v3(0, 0, 0);
+    float u_l[2 * YUNE_MAX_LIGHTS]; float u_pick = 0.0f;
+    for (int i = 0; i < n_lights; i++) {
+        const U4 ul = draw4(seed, pixel, sample, vertex, YUNE_BLK_LIGHT + i);
+        u_l[2 * i] = u01(ul.x); u_l[2 * i + 1] = u01(ul.y);
+        if (i == 0) u_pick = u01(ul.z);
+    }
+    float light_pdf = 0.0f; V3 w_i = v3(0, 0, 0);
+    const int j = sample_lights(lights, n_lights, hp, n, u_l, u_pick, light_pdf, w_i);
+    if (j == -1 || light_pdf <= 0.0f) return;
+    float len = vlength(w_i);
+    len = YF_SUB(len, YF_MUL(YUNE_EPS, 1.5f));
+    w_i = vnormalize(w_i);
+    R.S.o = vadd(hp, vscale(w_i, YUNE_EPS)); R.S.d = w_i; R.S.tmax = len;
+    float tl = len;
+    R.S.has = !(light_loop(lights, n_lights, R.S.o, R.S.d, tl) >= 0);        // traceRay's light loop (:244-276) can already block it
+    // branch "light sample visible": lobe selection happens only then (:559-561)
+    float prob = 0.0f;
+    const bool glossy = select_lobe(mat, u01(u_nee.y), BDPT, prob);
+    const bool v_alive = prob != 0.0f;
+    const V3 Lke = lights[j].ke;
+    if (v_alive) {
+        R.Lv = vscale(vmul(eval_brdf(mat, w_i, w_o, n, glossy, prob, !BDPT, use_on), Lke), fmaxf(vdot(w_i, n), 0.0f));
+        R.Lv = vscale(R.Lv, YF_DIV(1.0f, light_pdf));
+    }
+    if (!MIS) return;
+    const float r1 = u01(u_nee.z), r2 = u01(u_nee.w);
+    float pdfV = 0.0f, pdfO = 0.0f;
+    V3 dv = v3(0, 0, 1), dq;
+    if (v_alive) {
+        const float brdf_pdf = glossy ? phong_pdf(mat, w_i, w_o, n) : cos_pdf(w_i, n);
+        R.Lv = vscale(R.Lv, power_heuristic(light_pdf, light_pdf, brdf_pdf));                       // :570-577
+        dv = glossy ? sample_phong(w_o, n, mat.px, mat.py, r1, r2, !BDPT, pdfV) : sample_cosine(n, r1, r2, pdfV);
+        if (pdfV > 0.0f) {                                                                          // :587-588
+            R.MV.o = vadd(hp, vscale(dv, YUNE_EPS)); R.MV.d = dv; R.MV.tmax = INFINITY;
+            if (light_loop(lights, n_lights, R.MV.o, R.MV.d, R.MV.tmax) == j) {                     // closest light must be j (:594)
+                R.MV.has = true;
+                R.BV = vscale(vmul(eval_brdf(mat, dv, w_o, n, glossy, prob, !BDPT, use_on), Lke), fmaxf(vdot(dv, n), 0.0f));
+                R.BV = vscale(R.BV, YF_DIV(power_heuristic(pdfV, light_pdf, pdfV), pdfV));          // :597-600
+            }
+        }
+    }
+    // Branch "light sample occluded": sample_glossy = false and brdf_prob = 0 keep their initial values (:541-542), so the
+    // BRDF sample is cosine-distributed and evaluateBRDF divides by zero (:621).  In the reference that makes brdf_sample =
+    // (inf, inf, inf, inf) * light ke (.., .., .., 0): the W LANE is inf*0 = NaN, the kernel's any(isnan(color)) fires (:193)
+    // and the WHOLE SAMPLE becomes PINK.  We carry that outcome as a NaN contribution (finalisation turns a NaN sample into
+    // PINK), not as the infinities of the xyz lanes.
+    const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
+    if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
+    if (pdfO > 0.0f) {
+        bool reaches = false;
+        if (same_dir) { reaches = R.MV.has; R.mo_is_mv = R.MV.has; }
+        else {
+            R.MO.o = vadd(hp, vscale(dq, YUNE_EPS)); R.MO.d = dq; R.MO.tmax = INFINITY;
+            reaches = R.MO.has = (light_loop(lights, n_lights, R.MO.o, R.MO.d, R.MO.tmax) == j);
+        }
+        if (reaches) { const float qnan = __int_as_float(0x7fc00000); R.BO = v3(qnan, qnan, qnan); }
+    }
+}
+
+} // namespace yune
+#endif

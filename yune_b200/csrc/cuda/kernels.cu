@@ -12,63 +12,10 @@
 //   k_hook_*       parity hooks: primary rays / arbitrary rays through the same k_trace.
 //
 // Tensor cores are not used: no stage is a dense contraction (every ray gathers its own nodes/triangles).
-#include "kernels.h"
+#include "kernel_common.cuh"
 #include "trace_core.h"
-#include "shade_core.h"
-#include "rng.h"
 
 namespace yune {
-
-// ------------------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ V3 xyz(const float4& f) { return v3(f.x, f.y, f.z); }
-__device__ __forceinline__ float4 f4(V3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
-__device__ __forceinline__ F4 toF4(const float4& f) { F4 r; r.x = f.x; r.y = f.y; r.z = f.z; r.w = f.w; return r; }
-
-// warp-aggregated slot allocation in a global counter: returns this lane's index, or -1 for lanes with want == false
-__device__ __forceinline__ int warp_alloc(int* counter, bool want)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return -1;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    return want ? base + __popc(m & ((1u << lane) - 1)) : -1;
-}
-__device__ __forceinline__ long long warp_alloc64(unsigned long long* counter, bool want)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return -1;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// trace kernel
-// ------------------------------------------------------------------------------------------------------------
-struct DevPairFetch {
-    const float4* smem; const float4* gmem; int n_smem;
-    __device__ __forceinline__ void operator()(int i, F4& a, F4& b, F4& c, F4& d) const
-    {
-        float4 q0, q1, q2, q3;
-        if (i < n_smem) { const float4* p = smem + 4 * i; q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3]; }
-        else { const float4* p = gmem + 4 * (size_t)i; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3); }
-        a = toF4(q0); b = toF4(q1); c = toF4(q2); d = toF4(q3);
-    }
-};
-struct DevTriFetch {
-    const float4* gmem;
-    __device__ __forceinline__ void operator()(int i, F4& a, F4& b, F4& c) const
-    {
-        const float4* p = gmem + 3 * (size_t)i;
-        a = toF4(__ldg(p)); b = toF4(__ldg(p + 1)); c = toF4(__ldg(p + 2));
-    }
-};
 
 // ---- device-side walk: the same state machine as trace_core.h (tests/hostcheck validates that one against the oracle;
 // tests/test_gpu_parity.py validates this one), written branch-free so that a warp's lanes stay converged. ----
@@ -298,39 +245,8 @@ __global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// camera ray (createRay, udpt.cl:213-238); fp64 where the kernel's literals make it fp64
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void create_ray(const float* cam, int W, int H, float pixel_x, float pixel_y, V3& o, V3& d)
-{
-    const float aspect_ratio = (float)(((double)W * 1.0) / (double)H);
-    V3 dir;
-    dir.x = (float)((double)aspect_ratio * ((2.0 * (double)pixel_x / (double)W) - 1.0));
-    dir.y = (float)((2.0 * (double)pixel_y / (double)H) - 1.0);
-    dir.z = -cam[16];
-    V3 w;
-    w.x = vdot(v3(cam[0], cam[1], cam[2]), dir);
-    w.y = vdot(v3(cam[4], cam[5], cam[6]), dir);
-    w.z = vdot(v3(cam[8], cam[9], cam[10]), dir);
-    d = vnormalize(w);
-    o = v3(cam[3], cam[7], cam[11]);
-}
-
-__device__ __forceinline__ MatDev load_material(const float4* mats, int id)
-{
-    const float4* p = mats + 5 * (size_t)id;
-    const float4 ke = __ldg(p), kd = __ldg(p + 1), ks = __ldg(p + 2), a = __ldg(p + 3), b = __ldg(p + 4);
-    MatDev m;
-    m.ke = xyz(ke); m.kd = xyz(kd); m.ks = xyz(ks);
-    m.n = a.x; m.px = a.z; m.py = a.w; m.alpha_x = b.x;
-    m.is_specular = __float_as_int(b.z); m.is_transmissive = __float_as_int(b.w);
-    return m;
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // shade kernel (unidirectional path tracing, with or without MIS)
 // ------------------------------------------------------------------------------------------------------------
-struct ShadowOut { bool has; V3 o, d; float tmax; };
-
 template <bool MIS>
 __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
 {
@@ -412,68 +328,10 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
                 // ---- 3. next-event estimation at this vertex (evaluateDirectLighting, :535-609)
                 if (!mat.is_specular) {
                     col = vadd(col, vmul(T, mat.ke));                           // the 'emission' term of every return path
-                    float u_l[2 * YUNE_MAX_LIGHTS]; float u_pick = 0.0f;
-                    for (int i = 0; i < n_lights; i++) {
-                        const U4 ul = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_LIGHT + i);
-                        u_l[2 * i] = u01(ul.x); u_l[2 * i + 1] = u01(ul.y);
-                        if (i == 0) u_pick = u01(ul.z);
-                    }
-                    float light_pdf = 0.0f; V3 w_i = v3(0, 0, 0);
-                    const int j = sample_lights(lights, n_lights, hp, n, u_l, u_pick, light_pdf, w_i);
-                    if (!(j == -1 || light_pdf <= 0.0f)) {
-                        float len = vlength(w_i);
-                        len = YF_SUB(len, YF_MUL(YUNE_EPS, 1.5f));
-                        w_i = vnormalize(w_i);
-                        S.o = vadd(hp, vscale(w_i, YUNE_EPS)); S.d = w_i; S.tmax = len;
-                        float tl = len;
-                        const bool s_blocked = light_loop(lights, n_lights, S.o, S.d, tl) >= 0;     // traceRay's light loop (:244-276)
-                        S.has = !s_blocked;
-                        // branch "light sample visible": lobe selection happens only then (:559-561)
-                        float prob = 0.0f;
-                        const bool glossy = select_lobe(mat, u01(u_nee.y), false, prob);
-                        const bool v_alive = prob != 0.0f;
-                        const V3 Lke = lights[j].ke;
-                        if (v_alive) {
-                            Lv = vscale(vmul(eval_brdf(mat, w_i, w_o, n, glossy, prob, true, A.oren_nayar != 0), Lke), fmaxf(vdot(w_i, n), 0.0f));
-                            Lv = vscale(Lv, YF_DIV(1.0f, light_pdf));
-                        }
-                        if (MIS) {
-                            const float r1 = u01(u_nee.z), r2 = u01(u_nee.w);
-                            const bool use_on = A.oren_nayar != 0;
-                            float pdfV = 0.0f, pdfO = 0.0f;
-                            V3 dv = v3(0, 0, 1), dq;
-                            if (v_alive) {
-                                const float brdf_pdf = glossy ? phong_pdf(mat, w_i, w_o, n) : cos_pdf(w_i, n);
-                                Lv = vscale(Lv, power_heuristic(light_pdf, light_pdf, brdf_pdf));                    // :570-577
-                                dv = glossy ? sample_phong(w_o, n, mat.px, mat.py, r1, r2, true, pdfV) : sample_cosine(n, r1, r2, pdfV);
-                                if (pdfV > 0.0f) {                                                                   // :587-588
-                                    MV.o = vadd(hp, vscale(dv, YUNE_EPS)); MV.d = dv; MV.tmax = INFINITY;
-                                    if (light_loop(lights, n_lights, MV.o, MV.d, MV.tmax) == j) {                    // closest light must be j (:594)
-                                        MV.has = true;
-                                        BV = vscale(vmul(eval_brdf(mat, dv, w_o, n, glossy, prob, true, use_on), Lke), fmaxf(vdot(dv, n), 0.0f));
-                                        BV = vscale(BV, YF_DIV(power_heuristic(pdfV, light_pdf, pdfV), pdfV));       // :597-600
-                                    }
-                                }
-                            }
-                            // Branch "light sample occluded": sample_glossy = false and brdf_prob = 0 keep their initial values
-                            // (:541-542), so the BRDF sample is cosine-distributed and evaluateBRDF divides by zero (:621).  In the
-                            // reference that makes brdf_sample = (inf, inf, inf, inf) * light ke (.., .., .., 0): the W LANE is inf*0 =
-                            // NaN, the kernel's any(isnan(color)) fires (:193) and the WHOLE SAMPLE becomes PINK.  We carry that outcome
-                            // as a NaN contribution (finalisation turns a NaN sample into PINK), not as the infinities of the xyz lanes.
-                            const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
-                            if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
-                            if (pdfO > 0.0f) {
-                                bool reaches = false;
-                                if (same_dir) { reaches = MV.has; mo_is_mv = MV.has; }
-                                else {
-                                    MO.o = vadd(hp, vscale(dq, YUNE_EPS)); MO.d = dq; MO.tmax = INFINITY;
-                                    reaches = MO.has = (light_loop(lights, n_lights, MO.o, MO.d, MO.tmax) == j);
-                                }
-                                if (reaches) { const float qnan = __int_as_float(0x7fc00000); BO = v3(qnan, qnan, qnan); }
-                            }
-                        }
-                        nee_pending = S.has || MV.has || MO.has;
-                    }
+                    NeeOut N;
+                    nee_sample<MIS, false>(lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
+                    S = N.S; MV = N.MV; MO = N.MO; mo_is_mv = N.mo_is_mv; Lv = N.Lv; BV = N.BV; BO = N.BO;
+                    nee_pending = S.has || MV.has || MO.has;
                 }
                 // ---- 4. continue the path (udpt.cl:463-530)
                 if (!A.gi_check) terminate = true;

@@ -67,6 +67,14 @@ struct PathPool {
     unsigned char* evt_vis;
 };
 
+// Extra per-slot storage of the bidirectional integrator (bdpt.cu).  Stride YB_MAXV = 32 vertices per slot.
+struct BdptPool {
+    float4* lp;        // light path: 4 x float4 per vertex: (point, triangle bits) (normal, -) (arriving direction, -) (contribution, -)
+    float4* pend_c;    // [0] = emission of the eye vertex being resolved; [j] = unresolved contribution of the connection to light vertex j
+    int4*   bmeta;     // x = light-path length, y = mask of connection rays in flight, z = bits(eye_path_weight), w = bits(ks)
+    int     bounces;   // BDPT_BOUNCES (bdpt.cl:7)
+};
+
 #define YE_HAS_S      1     // a shadow ray toward the light sample is in flight (which = 0)
 #define YE_HAS_MV     2     // BRDF-sampled ray of the "light sample visible" branch (which = 1)
 #define YE_HAS_MO     4     // BRDF-sampled ray of the "light sample occluded" branch (which = 2)

@@ -21,6 +21,9 @@ const char* yune_scene_last_error(const yune_scene* s);
 /* Scene::loadModel(filepath, filename) (src/Scene.cpp:133-383); bins = BVH bin count (reference default 20;
  * 0 = no BVH, <= 2 = median splits only). */
 int yune_scene_load_model(yune_scene* s, const char* filepath, int bvh_bins);
+/* Same result as loadModel for geometry that is already in memory (synthetic scenes): per-triangle centroid + padded box
+ * (src/TriangleCPU.cpp:41-71), scene box (src/Scene.cpp:352-356), BVH (src/BVH.cpp:56-173).  Buffers are copied. */
+int yune_scene_set_geometry(yune_scene* s, const yune_triangle* tris, int n_triangles, const yune_material* mats, int n_materials, int bvh_bins);
 /* Scene::loadBVH(bins) (src/Scene.cpp:413-416). */
 int yune_scene_load_bvh(yune_scene* s, int bvh_bins);
 /* Scene::reloadMatFile() (src/Scene.cpp:62-131). */

@@ -180,6 +180,35 @@ def test_bdpt_image_agrees_with_reference_kernel_statistically(gpu_manager):
         assert gpu_manager.createRenderProgram("udpt.cl")
 
 
+def test_synthetic_c4_scene_hits_and_samples(gpu_manager, oracle):
+    """configs[3] at subdivision 6 (163,880 triangles): deep tree, leaves refined, nodes beyond the shared-memory prefix.
+    Hits bit-exact against the oracle's breadth-first walk (queue unbounded: the reference's 1500-entry cap would silently
+    drop subtrees on big scenes, SURVEY.md appendix B#13), per-sample radiance within tolerance."""
+    from yune_b200.scenes import synthetic_c4
+    m = gpu_manager
+    tris, mats, _ = load_golden_scene("cornellbox")
+    sc = yb.Scene().setGeometry(synthetic_c4(tris, 6), mats)
+    W = 160
+    r = yb.RendererCore(m, W, W)
+    assert m.createRenderProgram("udpt.cl") and r.setup(sc), m.last_message
+    cfg = Oracle.config("udpt", heap_size=0)
+    tri, light, t = r.tracePrimary(1, 999)
+    otri, olight, ot, od, work = oracle.primary(cfg, CAM, sc.vert_data, sc.bvh, 999, 1, W, W)
+    assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all()
+    rng = np.random.RandomState(2); n = 100000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od6 = np.concatenate([o, d], 1).astype(np.float32)
+    a = r.traceRays(od6); b = oracle.trace(cfg, od6, None, 0, sc.vert_data, sc.bvh)
+    assert (a[0] == b[0]).all() and (_bits(a[2]) == _bits(b[2])).all()
+    r.seed = 3
+    m.check(r._lib.yune_render(r._ctx, 0, 1, 1, r.seed, 1))
+    ours = r.readSum()
+    ref = oracle.samples(Oracle.config("udpt", rng_mode=1, seed=3, heap_size=0), CAM, sc.vert_data, sc.mat_data, sc.bvh, W, W, 0)
+    close = (np.abs(ours[..., :3] - ref[..., :3]) <= 1e-3 * np.abs(ref[..., :3]) + 1e-6).all(-1)
+    assert close.mean() >= 0.995, close.mean()
+
+
 def test_direct_light_only_mode(gpu_manager, oracle):
     """GI_CHECK = 0 (kernel arg 8, udpt.cl:458): direct lighting at the first hit only."""
     r, sc = _renderer(gpu_manager, "cornellbox", 64, 64)

@@ -124,3 +124,27 @@ def test_camera_record():
         np.testing.assert_array_equal(np.abs(cam[r][0]), want)
     assert cam["view_plane_dist"][0] == np.float32(1 / math.tan(60.0 * 3.14 / 360))
     assert yb.default_camera(90.0)["view_plane_dist"][0] == np.float32(1 / math.tan(90.0 * 3.14 / 360))
+
+
+def test_synthetic_c4_scene_and_in_memory_geometry(tmp_path):
+    """configs[3] generator at a small subdivision: 40 wall triangles + 2 icospheres; setGeometry (no OBJ text) must build
+    exactly what loadModel builds from the equivalent OBJ, and -- when the reference is present -- what the reference builds."""
+    from yune_b200.scenes import synthetic_c4, icosphere
+    from tests.refbind import have_ref, RefHost
+    v, f = icosphere(3)
+    assert v.shape == (642, 3) and f.shape == (1280, 3)
+    np.testing.assert_allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-12)
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    T = synthetic_c4(tris, 3)
+    assert T.size == 40 + 2 * 1280 and (T["matID"][40:] == 3).all()
+    a = yb.Scene().setGeometry(T, mats)
+    obj = str(tmp_path / "c4.obj")
+    write_obj(obj, T, mats)
+    b = yb.Scene().loadModel(obj)
+    assert tris_equal(a.vert_data, b.vert_data) and a.bvh.tobytes() == b.bvh.tobytes() and a.root.tobytes() == b.root.tobytes()
+    if have_ref():
+        rt, rm, rn, rroot = RefHost().load(obj)
+        assert tris_equal(rt, a.vert_data) and masked_nodes_equal(rn, a.bvh)
+    # spheres rest inside the box and do not touch each other (SURVEY.md 8d)
+    p = np.stack([T["v1"], T["v2"], T["v3"]], 1)[40:, :, :3]
+    assert p[..., 1].min() > -1.0039 and np.abs(p[: 1280].mean((0, 1)) - [-0.45, -0.55, -3.2]).max() < 1e-3

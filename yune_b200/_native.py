@@ -54,6 +54,7 @@ HOST_API = {
     "yune_scene_destroy": (None, [C.c_void_p]),
     "yune_scene_last_error": (C.c_char_p, [C.c_void_p]),
     "yune_scene_load_model": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "yune_scene_set_geometry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "yune_scene_load_bvh": (C.c_int, [C.c_void_p, C.c_int]),
     "yune_scene_reload_mat_file": (C.c_int, [C.c_void_p]),
     "yune_scene_num_triangles": (C.c_int, [C.c_void_p]),

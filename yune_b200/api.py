@@ -101,6 +101,14 @@ class Scene:
         self._refresh()
         return self
 
+    def setGeometry(self, vert_data, mat_data, bvh_bins=20):
+        """loadModel for geometry already in memory (synthetic scenes): same centroid/AABB/BVH code path."""
+        t = np.ascontiguousarray(vert_data, TRI_DTYPE); m = np.ascontiguousarray(mat_data, MAT_DTYPE)
+        if self._lib.yune_scene_set_geometry(self._h, _ptr(t), int(t.size), _ptr(m), int(m.size), int(bvh_bins)) != 0:
+            raise YuneError(self._lib.yune_scene_last_error(self._h).decode())
+        self._refresh()
+        return self
+
     def loadBVH(self, bvh_bins):
         if self._lib.yune_scene_load_bvh(self._h, int(bvh_bins)) != 0:
             raise YuneError(self._lib.yune_scene_last_error(self._h).decode())

@@ -198,5 +198,30 @@ namespace yune
         scene_size_mb = scene_size_kb / 1024;
     }
 
+    void Scene::setGeometry(const TriangleGPU* tris, int n_tris, const Material* mats, int n_mats, int bvh_bins)
+    {
+        clearValues();
+        if (n_mats <= 0 || !mats) throw std::runtime_error("Bad Material file.");
+        mat_data.assign(mats, mats + n_mats);
+        const float inf = std::numeric_limits<float>::max();
+        root.p_min = {{inf, inf, inf, 1.0f}};
+        root.p_max = {{-inf, -inf, -inf, 1.0f}};
+        cpu_tri_list.resize(n_tris);
+        for (int i = 0; i < n_tris; i++) {
+            TriangleCPU& t = cpu_tri_list[i];
+            t.props = tris[i];
+            t.computeCentroid();
+            for (int k = 0; k < 3; k++) {
+                root.p_min.s[k] = std::min(root.p_min.s[k], t.aabb.p_min.s[k]);
+                root.p_max.s[k] = std::max(root.p_max.s[k], t.aabb.p_max.s[k]);
+            }
+        }
+        vert_data.assign(tris, tris + n_tris);
+        if (bvh_bins > 0) bvh.createBVH(root, cpu_tri_list, bvh_bins);
+        num_triangles = n_tris;
+        scene_size_kb = (float)vert_data.size() * sizeof(TriangleGPU) / 1024 + (float)mat_data.size() * sizeof(Material) / 1024;
+        scene_size_mb = scene_size_kb / 1024;
+    }
+
     void Scene::loadBVH(int bvh_bins) { bvh.createBVH(root, cpu_tri_list, bvh_bins); }
 }

@@ -22,6 +22,8 @@ namespace yune
              *  with the reference's messages on unreadable files.  Unlike the reference it never WRITES a default .mtl next
              *  to an .obj that has no mtllib line (src/Scene.cpp:139-168): the default material is used in memory only. */
             void loadModel(std::string filepath, std::string filename);
+            /** loadModel without the parsing: take device-layout triangles and materials that are already in memory. */
+            void setGeometry(const TriangleGPU* tris, int n_tris, const Material* mats, int n_mats, int bvh_bins);
             void loadBVH(int bvh_bins);                 /**< Rebuild with another bin count (src/Scene.cpp:413-416). */
             void reloadMatFile();                       /**< Re-read mat_file into mat_data (src/Scene.cpp:62-131). */
 

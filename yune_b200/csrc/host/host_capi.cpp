@@ -31,6 +31,12 @@ int yune_scene_load_model(yune_scene* s, const char* filepath, int bvh_bins)
     } catch (const std::exception& e) { s->err = e.what(); return -1; }
     return 0;
 }
+int yune_scene_set_geometry(yune_scene* s, const yune_triangle* tris, int n_triangles, const yune_material* mats, int n_materials, int bvh_bins)
+{
+    if (!s || n_triangles < 0 || (n_triangles > 0 && !tris)) return -1;
+    try { s->scene.setGeometry(tris, n_triangles, mats, n_materials, bvh_bins); } catch (const std::exception& e) { s->err = e.what(); return -1; }
+    return 0;
+}
 int yune_scene_load_bvh(yune_scene* s, int bvh_bins)
 {
     if (!s) return -1;

@@ -142,8 +142,8 @@ def algorithmic_bytes_per_ray(r, tris, nodes):
     t-pruning over the reference BVH, on rays captured from one steady-state wavefront iteration of this very render."""
     from tests.refbind import Oracle
     o = Oracle()
-    r.captureRays(24, 1 << 17)
-    r.enqueueKernels(8, reset=True)
+    r.captureRays(40, 1 << 17)          # iteration 40 of a 64-spp render: pool full, path mix stationary
+    r.enqueueKernels(64, reset=True)
     out = {}
     for which, name in ((0, "extend"), (1, "shadow")):
         od, tm, nq = r.readCaptured(which)

@@ -266,6 +266,42 @@ def test_sample_ranges_add_up_and_pool_size_is_invisible(gpu_manager):
     m.check(r._lib.yune_render(r._ctx, 0, 0, 1, r.seed, 0))
 
 
+def test_fused_and_split_shade_kernels_agree(gpu_manager):
+    """The stage can run as one fused kernel or as k_logic + k_surface + k_regen; same samples either way."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 96, 96, opts="-DMIS", transmissive_teapot=True)
+    r.seed = 11
+    try:
+        m.setOption("fused_shade", 0); m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); a = r.readSum()
+        m.setOption("fused_shade", 1); m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); b = r.readSum()
+    finally:
+        m.setOption("fused_shade", 0)
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-5)
+
+
+def test_headless_cli(gpu_manager, tmp_path):
+    """C++ front end (csrc/app/yune_headless.cpp over csrc/host/RendererCore.cpp): OBJ in, .pfm out, same image as the
+    Python harness renders through the same C ABI."""
+    import subprocess
+    from tests.helpers import write_obj, ROOT
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    obj = str(tmp_path / "cb.obj"); out = str(tmp_path / "cb.pfm")
+    write_obj(obj, tris, mats)
+    exe = os.path.join(ROOT, "yune_b200", "yune_headless")
+    p = subprocess.run([exe, "--obj", obj, "--width", "64", "--height", "48", "--spp", "8", "--seed", "5", "--out", out], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Total Triangles Loaded: 60" in p.stdout and "BVH Size: 15 Nodes" in p.stdout
+    with open(out, "rb") as f:
+        assert f.readline() == b"PF\n" and f.readline() == b"64 48\n" and f.readline() == b"-1.0\n"
+        img = np.frombuffer(f.read(), "<f4").reshape(48, 64, 3)
+    r, sc = _renderer(gpu_manager, "cornellbox", 64, 48)
+    r.seed = 5
+    r.enqueueKernels(8)
+    np.testing.assert_allclose(img, r.readHDR()[..., :3], rtol=1e-4, atol=1e-5)
+    bad = subprocess.run([exe, "--obj", str(tmp_path / "missing.obj")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Error opening" in bad.stderr
+
+
 def test_tonemap_matches_oracle(gpu_manager, oracle):
     r, sc = _renderer(gpu_manager, "cornellbox", 64, 64)
     r.enqueueKernels(4)

@@ -13,7 +13,8 @@ CSRC = os.path.join(ROOT, "yune_b200", "csrc")
 LIB = os.path.join(ROOT, "yune_b200", "libyune_b200.so")
 
 CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu"]
-HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/host_capi.cpp"]
+HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/RendererCore.cpp", "host/host_capi.cpp"]
+APP = os.path.join(ROOT, "yune_b200", "yune_headless")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false",                    # parity: products and sums are never fused (see strict_math.h)
@@ -29,7 +30,7 @@ def _newer(target, deps):
 
 def _all_deps():
     deps = []
-    for d in ("cuda", "host"):
+    for d in ("cuda", "host", "app"):
         for f in os.listdir(os.path.join(CSRC, d)):
             deps.append(os.path.join(CSRC, d, f))
     for f in os.listdir(os.path.join(ROOT, "include")):
@@ -53,6 +54,10 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     with open(os.path.join(ROOT, "yune_b200", "build_ptxas.log"), "w") as f:
         f.write(r.stdout + r.stderr)
+    # headless command-line front end (C++ host, links the library)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CSRC, "host"),
+                           os.path.join(CSRC, "app", "yune_headless.cpp"), "-o", APP, "-L", os.path.join(ROOT, "yune_b200"),
+                           "-lyune_b200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

@@ -24,7 +24,7 @@ struct LightSet { LightDev l[YUNE_MAX_LIGHTS]; int n; };
 // Per-iteration queue heads/counters (double buffered by iteration parity) + running totals.
 struct IterCounters {
     int n_extend, n_shadow, n_events, live;
-    int fetch_extend, fetch_shadow, pad0, pad1;
+    int fetch_extend, fetch_shadow, n_shade, n_regen;
 };
 struct Totals {
     unsigned long long next_sample;     // next global sample index to hand out
@@ -59,6 +59,8 @@ struct PathPool {
     int*     evt_idx;    // valid with YF_PEND_EVT
     unsigned char* vis_l;   // 1 = NEE shadow ray reached the light (written by the trace kernel)
     // queues
+    int*     shade_q;    // slots with a surface hit to shade this iteration (k_logic -> k_surface)
+    int*     regen_q;    // slots to regenerate this iteration (k_logic, k_surface -> k_regen)
     int*     eq;         // extension queue: slot indices
     float4*  sq_o;       // shadow queue: xyz origin, w = tmax
     float4*  sq_d;       // xyz direction, w = int bits: target (>= 0 slot -> vis_l ; < 0 -> ~target = event*4 + which)

@@ -1,0 +1,157 @@
+#include "RendererCore.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace yune
+{
+    CUDAManager::CUDAManager() : ctx(nullptr) {}
+    CUDAManager::~CUDAManager() { if (ctx) yune_destroy(ctx); }
+
+    void CUDAManager::checkError(int err_code, yune_ctx* c, std::string filename, int line_number)
+    {
+        if (err_code >= 0) return;
+        std::ostringstream ss;
+        ss << yune_last_error(c) << " in File: " << filename << " at Line number: " << line_number;   // src/CLManager.cpp:755-855
+        throw std::runtime_error(ss.str());
+    }
+    bool CUDAManager::report(int rc)
+    {
+        if (rc == YUNE_OK) return true;
+        last_message = yune_last_error(ctx);          // the reference pushes this to the GUI callback (src/CLManager.cpp:261-265)
+        return false;
+    }
+    void CUDAManager::setup(int device)
+    {
+        if (yune_setup(device, &ctx) != YUNE_OK) throw std::runtime_error(yune_last_error(nullptr));
+    }
+    bool CUDAManager::createRenderProgram(std::string fn, std::string path, bool)
+    {
+        // '#yune-preproc compiler-opts <one token>' (src/CLManager.cpp:182-204)
+        if (!path.empty()) {
+            std::ifstream f(path);
+            std::string line, a, b, c;
+            while (f.is_open() && std::getline(f, line)) {
+                std::istringstream ss(line);
+                if ((ss >> a >> b >> c) && a == "#yune-preproc" && b == "compiler-opts") rk_compiler_opts = c;
+            }
+        }
+        if (!report(yune_create_render_program(ctx, fn.c_str(), rk_compiler_opts.c_str()))) return false;
+        rk_file = fn;
+        return true;
+    }
+    bool CUDAManager::createPostProcProgram(std::string fn, std::string, bool)
+    {
+        if (!report(yune_create_postproc_program(ctx, fn.c_str(), ""))) return false;
+        ppk_file = fn;
+        return true;
+    }
+    void CUDAManager::setupCameraBuffer(Cam* cam) { checkError(yune_setup_camera_buffer(ctx, cam), ctx, __FILE__, __LINE__); }
+    bool CUDAManager::setupImageBuffers(int w, int h) { return report(yune_setup_image_buffers(ctx, w, h)); }
+    bool CUDAManager::setupBVHBuffer(std::vector<BVHNodeGPU>& v, float, float) { return report(yune_setup_bvh_buffer(ctx, v.data(), (int)v.size())); }
+    bool CUDAManager::setupVertexBuffer(std::vector<TriangleGPU>& v, float) { return report(yune_setup_vertex_buffer(ctx, v.data(), (int)v.size())); }
+    bool CUDAManager::setupMatBuffer(std::vector<Material>& v) { return report(yune_setup_mat_buffer(ctx, v.data(), (int)v.size())); }
+
+    RendererCore::RendererCore(CUDAManager& m, int w, int h)
+        : seed(12345), samples_taken(0), mspf_avg(0), ms_per_rk(0), ms_per_ppk(0), time_passed(0), msamples_per_s(0), mrays_per_s(0),
+          cl_manager(m), width(w), height(h), gi_check(true)
+    {
+        std::memset(&stats, 0, sizeof(stats));
+    }
+
+    bool RendererCore::loadScene(std::string path, std::string fn)
+    {
+        try { render_scene.loadModel(path, fn); }
+        catch (const std::exception& e) { cl_manager.last_message = e.what(); return false; }
+        return true;
+    }
+
+    bool RendererCore::setup(bool gi)
+    {
+        if (!cl_manager.setupVertexBuffer(render_scene.vert_data, render_scene.scene_size_mb)) return false;
+        if (!cl_manager.setupMatBuffer(render_scene.mat_data)) return false;
+        if (!cl_manager.setupBVHBuffer(render_scene.bvh.gpu_node_list, render_scene.bvh.bvh_size_mb, render_scene.scene_size_mb)) return false;
+        if (!cl_manager.setupImageBuffers(width, height)) return false;
+        Cam cam;
+        render_scene.main_camera.setBuffer(&cam);
+        cl_manager.setupCameraBuffer(&cam);
+        gi_check = gi; samples_taken = 0; time_passed = 0;
+        return true;
+    }
+
+    bool RendererCore::enqueueKernels(int frames, bool new_gi_check)
+    {
+        bool reset = samples_taken == 0;
+        if (render_scene.main_camera.is_changed) {                      // src/RendererCore.cpp:531-553
+            Cam cam; render_scene.main_camera.setBuffer(&cam); cl_manager.setupCameraBuffer(&cam); reset = true;
+        }
+        if (new_gi_check != gi_check) { gi_check = new_gi_check; reset = true; }      // :556-565
+        if (reset) samples_taken = 0;
+        if (yune_render(cl_manager.ctx, samples_taken, frames, gi_check ? 1 : 0, seed, reset ? 1 : 0) != YUNE_OK) {
+            cl_manager.last_message = yune_last_error(cl_manager.ctx);
+            return false;
+        }
+        samples_taken += frames;
+        yune_get_stats(cl_manager.ctx, &stats);
+        // endFrame() metrics (:483-505): one frame = one sample per pixel
+        mspf_avg = frames > 0 ? (float)(stats.render_ms / frames) : 0.0f;
+        ms_per_rk = mspf_avg;
+        time_passed += (float)(stats.render_ms / 1000.0);
+        msamples_per_s = stats.render_ms > 0 ? stats.samples / stats.render_ms / 1e3 : 0;
+        mrays_per_s = stats.render_ms > 0 ? (stats.extend_rays + stats.shadow_rays) / stats.render_ms / 1e3 : 0;
+        return true;
+    }
+
+    bool RendererCore::postProcess()
+    {
+        if (yune_tonemap(cl_manager.ctx) != YUNE_OK) { cl_manager.last_message = yune_last_error(cl_manager.ctx); return false; }
+        yune_get_stats(cl_manager.ctx, &stats);
+        ms_per_ppk = (float)stats.tonemap_ms;
+        return true;
+    }
+
+    bool RendererCore::saveImage(const std::string& path)
+    {
+        const size_t n = (size_t)width * height;
+        std::vector<float> img(n * 4);
+        const std::string ext = path.size() >= 4 ? path.substr(path.size() - 4) : "";
+        const bool ldr = ext == ".ppm";
+        if (ldr) { if (!postProcess()) return false; }
+        const int rc = ldr ? yune_read_ldr(cl_manager.ctx, img.data()) : yune_read_hdr(cl_manager.ctx, img.data());
+        if (rc != YUNE_OK) { cl_manager.last_message = yune_last_error(cl_manager.ctx); return false; }
+        std::ofstream f(path, std::ios::binary);
+        if (!f.is_open()) { cl_manager.last_message = "Error opening image file for writing."; return false; }
+        if (ext == ".pfm") {                                   // bottom-up float RGB, little endian: our row order as is
+            f << "PF\n" << width << " " << height << "\n-1.0\n";
+            for (size_t i = 0; i < n; i++) f.write(reinterpret_cast<const char*>(&img[4 * i]), 12);
+        } else if (ext == ".hdr") {                            // Radiance RGBE, flat (no RLE), top-down
+            f << "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y " << height << " +X " << width << "\n";
+            for (int y = height - 1; y >= 0; y--)
+                for (int x = 0; x < width; x++) {
+                    const float* p = &img[4 * ((size_t)y * width + x)];
+                    const float m = std::fmax(p[0], std::fmax(p[1], p[2]));
+                    unsigned char px[4] = {0, 0, 0, 0};
+                    if (m > 1e-32f && std::isfinite(m)) {
+                        int e; const float s = std::frexp(m, &e) * 256.0f / m;
+                        px[0] = (unsigned char)(p[0] * s); px[1] = (unsigned char)(p[1] * s); px[2] = (unsigned char)(p[2] * s); px[3] = (unsigned char)(e + 128);
+                    }
+                    f.write(reinterpret_cast<const char*>(px), 4);
+                }
+        } else if (ldr) {                                      // 8-bit tonemapped, top-down
+            f << "P6\n" << width << " " << height << "\n255\n";
+            for (int y = height - 1; y >= 0; y--)
+                for (int x = 0; x < width; x++) {
+                    const float* p = &img[4 * ((size_t)y * width + x)];
+                    unsigned char px[3];
+                    for (int k = 0; k < 3; k++) { float v = p[k]; v = v != v ? 0.0f : (v < 0 ? 0 : (v > 1 ? 1 : v)); px[k] = (unsigned char)(v * 255.0f + 0.5f); }
+                    f.write(reinterpret_cast<const char*>(px), 3);
+                }
+        } else { cl_manager.last_message = "unsupported image extension (use .hdr, .pfm or .ppm)"; return false; }
+        return true;
+    }
+}

@@ -1,0 +1,62 @@
+// RendererCore.h -- headless frame scheduler: the launch protocol of yune::RendererCore (include/RendererCore.h:46-90,
+// src/RendererCore.cpp:155-246 setup, :248-469 enqueueKernels, :483-505 endFrame metrics, :608-646 saveImage) without the
+// GLFW/GL window, driving the C ABI of include/yune_cuda.h instead of raw cl_kernel / cl_mem handles.
+#ifndef YUNE_RENDERERCORE_H
+#define YUNE_RENDERERCORE_H
+
+#include "Scene.h"
+#include "yune_cuda.h"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace yune
+{
+    /** Thin C++ owner of a yune_ctx with CLManager's public method set (include/CLManager.h:50-88). */
+    class CUDAManager
+    {
+        public:
+            CUDAManager();
+            ~CUDAManager();
+            void setup(int device = 0);                                                   /**< throws std::runtime_error like CLManager::setup */
+            bool createRenderProgram(std::string fn, std::string path = "", bool reload = false);   /**< honours '#yune-preproc compiler-opts' of `path` */
+            bool createPostProcProgram(std::string fn, std::string path = "", bool reload = false);
+            void setupCameraBuffer(Cam* cam_data);
+            bool setupImageBuffers(int width, int height);
+            bool setupBVHBuffer(std::vector<BVHNodeGPU>& bvh_data, float bvh_size = 0, float scene_size = 0);
+            bool setupVertexBuffer(std::vector<TriangleGPU>& vert_data, float scene_size = 0);
+            bool setupMatBuffer(std::vector<Material>& mat_data);
+            static void checkError(int err_code, yune_ctx* ctx, std::string filename, int line_number);   /**< negative code -> std::runtime_error */
+
+            std::string rk_file, rk_compiler_opts, ppk_file, last_message;
+            yune_ctx* ctx;
+        private:
+            bool report(int rc);
+    };
+
+    class RendererCore
+    {
+        public:
+            RendererCore(CUDAManager& cuda_manager, int width, int height);
+            bool loadScene(std::string path, std::string fn);                             /**< src/RendererCore.cpp:124-137 */
+            bool setup(bool gi_check);                                                    /**< upload scene + camera, allocate images */
+            bool enqueueKernels(int frames, bool new_gi_check);                           /**< `frames` more samples per pixel; blocks until done */
+            bool postProcess();
+            /** src/RendererCore.cpp:608-646 without stb: ".hdr" (Radiance RGBE), ".pfm" (float RGB), ".ppm" (8-bit, tonemapped). Rows are
+             *  flipped to top-down on the way out like the reference does. */
+            bool saveImage(const std::string& path);
+
+            Scene render_scene;
+            std::uint32_t seed;
+            int samples_taken;
+            float mspf_avg, ms_per_rk, ms_per_ppk, time_passed;                           /**< endFrame() metrics, :483-505 */
+            double msamples_per_s, mrays_per_s;
+            yune_stats stats;
+        private:
+            CUDAManager& cl_manager;
+            int width, height;
+            bool gi_check;
+    };
+}
+#endif

@@ -33,6 +33,41 @@ __device__ __forceinline__ long long warp_alloc64(unsigned long long* counter, b
     return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
 }
 
+// Block-wide queue allocation: every thread of the block calls it with up to K request counts (0..3 each); ONE global
+// atomic per counter per block.  s_cnt is shared memory of K * (warps + 1) ints.  Returns, per counter, the first index this
+// thread owns (contiguous run of `cnt[k]` entries).  Two __syncthreads.  (One atomic per WARP on the same line was the
+// bottleneck of the shade stage: ~260 K same-line L2 atomics per iteration.)
+template <int K, int NWARPS>
+__device__ __forceinline__ void block_alloc(int* const (&counters)[K], const int (&cnt)[K], int (&first)[K], int* s_cnt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int excl[K];
+    #pragma unroll
+    for (int k = 0; k < K; k++) {
+        int incl = cnt[k];
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        excl[k] = incl - cnt[k];
+        if (lane == 31) s_cnt[k * (NWARPS + 1) + warp] = incl;
+    }
+    __syncthreads();
+    if (warp < K) {
+        const int k = warp;
+        const int v = lane < NWARPS ? s_cnt[k * (NWARPS + 1) + lane] : 0;
+        int incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(counters[k], total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < NWARPS) s_cnt[k * (NWARPS + 1) + lane] = base + incl - v;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < K; k++) first[k] = s_cnt[k * (NWARPS + 1) + warp] + excl[k];
+}
+
 // camera ray (createRay, udpt.cl:213-238); fp64 where the kernel's literals make it fp64
 __device__ __forceinline__ void create_ray(const float* cam, int W, int H, float pixel_x, float pixel_y, V3& o, V3& d)
 {
@@ -81,6 +116,7 @@ __device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights,
     R.S.has = R.MV.has = R.MO.has = false; R.mo_is_mv = false;
     R.Lv = v3(0, 0, 0); R.BV = v3(0, 0, 0); R.BO = v3(0, 0, 0);
     float u_l[2 * YUNE_MAX_LIGHTS]; float u_pick = 0.0f;
+    YUNE_NO_UNROLL
     for (int i = 0; i < n_lights; i++) {
         const U4 ul = draw4(seed, pixel, sample, vertex, YUNE_BLK_LIGHT + i);
         u_l[2 * i] = u01(ul.x); u_l[2 * i + 1] = u01(ul.y);

@@ -142,6 +142,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 // instruction of the two hot bodies has many lanes behind it.  Lanes that finish are refilled from the queue head (one
 // atomicAdd per warp, ballot/popc ranks) once `refill_idle` of them are idle.
 #define YUNE_PHASE_MAX   8
+#define YUNE_FETCH_CHUNK 128
 
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_pairs, WorkCount& wc)
@@ -155,7 +156,8 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
     Lane L; L.cur = YUNE_REF_DONE; L.leaf_pos = L.leaf_end = 0; L.sp = 0; L.tri = -1; L.guard = false;
     bool have = false;          // this lane holds a ray
     int  where = 0;             // extension: slot index; shadow: answer target
-    bool exhausted = (n == 0);
+    bool exhausted = (n == 0), last_chunk = false;
+    int chunk_next = 0, chunk_end = 0;            // warp-uniform: the private range of queue entries still to hand out
     const int refill_idle = A.refill_idle, phase_min = A.phase_min;
 
     for (;;) {
@@ -167,23 +169,27 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
             } else A.hit[where] = make_float4(L.t_best, L.u, L.v, __int_as_float(L.tri));
             have = false;
         }
-        // ---- refill ----
+        // ---- refill: lanes take rays from the warp's private chunk; a new chunk costs one atomic per YUNE_FETCH_CHUNK rays ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         if (idle == 0xffffffffu && exhausted) break;
         if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_idle)) {
-            const int n_idle = __popc(idle);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(fetch, n_idle);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            exhausted = base + n_idle >= n;
-            const int q = base + __popc(idle & lane_lt);
-            if (!have && q < n) {
+            if (chunk_next >= chunk_end) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fetch, YUNE_FETCH_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base; chunk_end = min(base + YUNE_FETCH_CHUNK, n);
+                last_chunk = base + YUNE_FETCH_CHUNK >= n;
+            }
+            const int q = chunk_next + __popc(idle & lane_lt);
+            if (!have && q < chunk_end) {
                 float4 o, d;
                 if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
                 else { where = A.eq ? A.eq[q] : q; o = A.ray_o[where]; d = A.ray_d[where]; }
                 lane_init<ANY, COUNT>(L, sc, o, d, wc);
                 have = true;
             }
+            chunk_next = min(chunk_next + __popc(idle), chunk_end);
+            exhausted = last_chunk && chunk_next >= chunk_end;
         }
         // ---- INNER phase ----
         bool progressed = false;
@@ -248,7 +254,7 @@ __global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
 // shade kernel (unidirectional path tracing, with or without MIS)
 // ------------------------------------------------------------------------------------------------------------
 template <bool MIS>
-__global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
+__global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_shade_udpt(RenderArgs A)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s < A.pool.n_slots;
@@ -379,14 +385,30 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
     need_new = valid && (finished || state == YS_FREE) && !has_ext && new_flags == 0;
 
     // ---- 6. regenerate: next (pixel, sample) in global order + camera ray (udpt.cl:164-189)
+    __shared__ int s_cnt[4 * (YUNE_SHADE_BLOCK / 32 + 1)];
+    __shared__ unsigned long long s_sample_base;
     {
-        const long long g = warp_alloc64(&A.tot->next_sample, need_new);
+        // one 64-bit atomic per block: block-wide rank of the lanes that need a sample
+        int* const c1[1] = { &s_cnt[3 * (YUNE_SHADE_BLOCK / 32 + 1)] };       // dummy smem counter: only the ranks are used
+        (void)c1;
+        const unsigned m = __ballot_sync(0xffffffffu, need_new);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) s_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int total = 0;
+            for (int w = 0; w < YUNE_SHADE_BLOCK / 32; w++) { const int v = s_cnt[w]; s_cnt[w] = total; total += v; }
+            s_sample_base = total > 0 ? atomicAdd(&A.tot->next_sample, (unsigned long long)total) : 0ull;
+        }
+        __syncthreads();
+        const unsigned long long g = s_sample_base + (unsigned long long)(s_cnt[warp] + __popc(m & ((1u << lane) - 1u)));
+        __syncthreads();
         if (need_new) {
-            if ((unsigned long long)g >= A.tot->n_samples) new_flags = YS_DONE;
+            if (g >= A.tot->n_samples) new_flags = YS_DONE;
             else {
                 const unsigned long long n_pix = (unsigned long long)A.width * A.height;
-                const unsigned pixel = (unsigned)((unsigned long long)g % n_pix);
-                const unsigned sample = (unsigned)(A.spp_begin + (int)((unsigned long long)g / n_pix));
+                const unsigned pixel = (unsigned)(g % n_pix);
+                const unsigned sample = (unsigned)(A.spp_begin + (int)(g / n_pix));
                 const int px = pixel % A.width, py = pixel / A.width;
                 const U4 uj = draw4(A.seed, pixel, sample, YUNE_VERTEX_CAMERA, 0u);
                 create_ray(A.cam, A.width, A.height, (float)px + u01(uj.x), (float)py + u01(uj.y), ext_o, ext_d);
@@ -400,16 +422,19 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
         }
     }
 
-    // ---- 7. queue pushes (ballot/popc compaction) and state write-back
-    const int qe = warp_alloc(&C->n_extend, has_ext);
+    // ---- 7. queue pushes (block-wide compaction: warp scans + one atomic per counter per block) and state write-back
+    const bool is_event = MV.has || MO.has;
+    const bool live_now = valid && (new_flags & YS_STATE_MASK) != YS_DONE && (meta.w & YS_STATE_MASK) != YS_DONE;
+    int* const counters[4] = { &C->n_extend, &C->n_shadow, &C->n_events, &C->live };
+    const int cnt[4] = { has_ext ? 1 : 0, (S.has ? 1 : 0) + (MV.has ? 1 : 0) + (MO.has ? 1 : 0), is_event ? 1 : 0, live_now ? 1 : 0 };
+    int first[4];
+    block_alloc<4, YUNE_SHADE_BLOCK / 32>(counters, cnt, first, s_cnt);
     if (has_ext) {
-        P.eq[qe] = s;
+        P.eq[first[0]] = s;
         P.ray_o[s] = f4(ext_o, ext_t);
         P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
     }
-    const bool is_event = MV.has || MO.has;
-    // event records and their answers are double-buffered by iteration parity: this visit still READS last iteration's
-    const int ev = A.parity * P.n_slots + warp_alloc(&C->n_events, is_event);
+    const int ev = A.parity * P.n_slots + first[2];
     if (is_event) {
         int ef = (S.has ? YE_HAS_S : 0) | (MV.has ? YE_HAS_MV : 0) | (MO.has ? YE_HAS_MO : 0) | (mo_is_mv ? YE_MO_IS_MV : 0);
         P.evt[3 * (size_t)ev] = f4(Lv, __int_as_float(ef));
@@ -418,17 +443,16 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
         P.evt_idx[s] = ev;
         new_flags |= YF_PEND_EVT;
     } else if (S.has) new_flags |= YF_PEND_L;
-    const int qs = warp_alloc(&C->n_shadow, S.has);
+    int qs = first[1];
     if (S.has) {
         P.sq_o[qs] = f4(S.o, S.tmax);
         P.sq_d[qs] = f4(S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
         if (!is_event) P.pend_l[s] = f4(Lv, 0.0f);
+        qs++;
     }
     if (MIS) {
-        const int qv = warp_alloc(&C->n_shadow, MV.has);
-        if (MV.has) { P.sq_o[qv] = f4(MV.o, MV.tmax); P.sq_d[qv] = f4(MV.d, __int_as_float(~(4 * ev + 1))); }
-        const int qo = warp_alloc(&C->n_shadow, MO.has);
-        if (MO.has) { P.sq_o[qo] = f4(MO.o, MO.tmax); P.sq_d[qo] = f4(MO.d, __int_as_float(~(4 * ev + 2))); }
+        if (MV.has) { P.sq_o[qs] = f4(MV.o, MV.tmax); P.sq_d[qs] = f4(MV.d, __int_as_float(~(4 * ev + 1))); qs++; }
+        if (MO.has) { P.sq_o[qs] = f4(MO.o, MO.tmax); P.sq_d[qs] = f4(MO.d, __int_as_float(~(4 * ev + 2))); qs++; }
     }
     if (valid && (meta.w & YS_STATE_MASK) != YS_DONE) {
         meta.w = new_flags;
@@ -439,9 +463,6 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_udpt(RenderArgs A)
             if (has_ext) P.thr_next[s] = f4(Tn, 0.0f);
         }
     }
-    const bool live = valid && (new_flags & YS_STATE_MASK) != YS_DONE && (meta.w & YS_STATE_MASK) != YS_DONE;
-    const unsigned lm = __ballot_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0 && lm) atomicAdd(&C->live, __popc(lm));
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -6,6 +6,9 @@
 
 #define YUNE_TRACE_MAX_BLOCK  1024     /* k_trace is compiled for <= 64 registers so any block size up to this fits */
 #define YUNE_SHADE_BLOCK      256
+#ifndef YUNE_SHADE_MIN_BLOCKS
+#define YUNE_SHADE_MIN_BLOCKS 3
+#endif
 
 namespace yune {
 

@@ -17,9 +17,10 @@ struct LightDev {           // unpacked yune_quad_light + the two edge lengths (
 
 // Loops the lights in index order with the reference's strict comparisons.  On return `t` is the (possibly
 // shortened) ray length and the result is the index of the light that owns it, or -1.
-YUNE_HD int light_loop(const LightDev* lights, int n_lights, V3 o, V3 d, float& t_len)
+YUNE_HD_CALL int light_loop(const LightDev* lights, int n_lights, V3 o, V3 d, float& t_len)
 {
     int id = -1;
+    YUNE_NO_UNROLL
     for (int i = 0; i < n_lights; i++) {
         const LightDev& L = lights[i];
         const float DdotN = vdot(d, L.normal);

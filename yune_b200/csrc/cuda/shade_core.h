@@ -62,7 +62,7 @@ YUNE_HD V3 onb_to_world(V3 Nx, V3 Ny, V3 Nz, float x, float y, float z)
 }
 
 // cosineWeightedHemisphere (udpt.cl:843-910): direction about the shading normal, pdf = cos/pi.
-YUNE_HD V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
+YUNE_HD_CALL V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
 {
     V3 Nx, Ny; onb(n, Nx, Ny);
     const float phi = YF_MUL(YF_MUL(2.0f, YUNE_PI), r2);
@@ -74,7 +74,7 @@ YUNE_HD V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
 
 // phongSampleHemisphere (udpt.cl:700-771): lobe about the mirror direction of w (w = direction back along the
 // arriving ray).  flip_normal = udpt behaviour (reflect()), false = bdpt.cl:814.  pdf = 0 below the surface.
-YUNE_HD V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal, float& pdf)
+YUNE_HD_CALL V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal, float& pdf)
 {
     V3 Nz = flip_normal ? reflect_flip(w, n) : reflect_noflip(w, n);
     Nz = vnormalize(Nz);
@@ -93,7 +93,7 @@ YUNE_HD V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool
 
 // sampleGlossyPdf (udpt.cl:1062-1119; bdpt variant bdpt.cl:1048-1105): choose diffuse or glossy lobe with the
 // uniform r; returns true for glossy and the selection probability (0 = absorbed, udpt only).
-YUNE_HD bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float& prob)
+YUNE_HD_CALL bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float& prob)
 {
     const V3 ks = m.ks, kd = m.kd;
     if (vlength(ks) == 0.0f) { prob = 1.0f; return false; }
@@ -118,7 +118,7 @@ YUNE_HD bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float& pro
 YUNE_HD float on_sin_theta(V3 w) { return YF_SQRT(YF_SUB(1.0f, YF_MUL(w.z, w.z))); }
 YUNE_HD float on_cos_phi(V3 w) { const float s = on_sin_theta(w); if (s <= YUNE_EPS && s >= -YUNE_EPS) return 0.0f; return fminf(fmaxf(YF_DIV(w.x, s), -1.0f), 1.0f); }
 YUNE_HD float on_sin_phi(V3 w) { const float s = on_sin_theta(w); if (s <= YUNE_EPS && s >= -YUNE_EPS) return 0.0f; return fminf(fmaxf(YF_DIV(w.y, s), -1.0f), 1.0f); }
-YUNE_HD V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
+YUNE_HD_CALL V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
 {
     V3 Nx, Ny; onb(n, Nx, Ny);
     const V3 wi = v3(vdot(Nx, w_i), vdot(Ny, w_i), vdot(n, w_i));
@@ -138,7 +138,7 @@ YUNE_HD V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
 
 // evaluateBRDF (udpt.cl:611-630; bdpt.cl:718-737 does not flip the normal).  rr_prob = lobe-selection probability.
 // rr_prob == 0 divides by zero exactly like the reference does in its MIS branch (see engine notes).
-YUNE_HD V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, float rr_prob, bool flip_normal, bool use_oren_nayar)
+YUNE_HD_CALL V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, float rr_prob, bool flip_normal, bool use_oren_nayar)
 {
     if (!glossy) {
         if (use_oren_nayar && rr_prob == 1.0f) return oren_nayar(m, w_i, w_o, n);       // udpt-primitives.cl:681-686
@@ -156,7 +156,7 @@ YUNE_HD V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, float r
 }
 
 // calcPhongPDF (udpt.cl:1033-1045, including the cos() of the dot product) and calcCosPDF (:1047-1050)
-YUNE_HD float phong_pdf(const MatDev& m, V3 w_i, V3 w_o, V3 n)
+YUNE_HD_CALL float phong_pdf(const MatDev& m, V3 w_i, V3 w_o, V3 n)
 {
     V3 refl = vsub(vscale(n, YF_MUL(2.0f, vdot(w_o, n))), w_o);
     refl = vnormalize(refl);
@@ -169,7 +169,7 @@ YUNE_HD float cos_pdf(V3 w_i, V3 n) { return YF_MUL(fmaxf(vdot(w_i, n), 0.0f), Y
 YUNE_HD float power_heuristic(float w, float a, float b) { return YF_DIV(YF_MUL(w, w), YF_ADD(YF_MUL(a, a), YF_MUL(b, b))); }
 
 // evalFresnelReflectance (udpt.cl:992-1031).  Returns R; ior_factor is only written when no total internal reflection.
-YUNE_HD float fresnel_reflectance(const MatDev& m, V3 w_i, V3 n, float& ior_factor)
+YUNE_HD_CALL float fresnel_reflectance(const MatDev& m, V3 w_i, V3 n, float& ior_factor)
 {
     float n1, n2;
     if (vdot(w_i, n) < 0.0f) { n1 = m.n; n2 = 1.0f; n = vscale(n, -1.0f); }
@@ -186,7 +186,7 @@ YUNE_HD float fresnel_reflectance(const MatDev& m, V3 w_i, V3 n, float& ior_fact
     return YF_ADD(r0, YF_MUL(YF_SUB(1.0f, r0), YF_SUB(1.0f, powf(c, 5.0f))));
 }
 // refract (udpt.cl:963-990)
-YUNE_HD V3 refract_dir(const MatDev& m, V3 w_i, V3 n)
+YUNE_HD_CALL V3 refract_dir(const MatDev& m, V3 w_i, V3 n)
 {
     float n1, n2;
     if (vdot(w_i, n) < 0.0f) { n1 = m.n; n2 = 1.0f; n = vscale(n, -1.0f); }
@@ -197,7 +197,7 @@ YUNE_HD V3 refract_dir(const MatDev& m, V3 w_i, V3 n)
     return vnormalize(vadd(wt_perp, wt_parallel));
 }
 // sampleFresnelIncidence (udpt.cl:912-947): mirror or dielectric.  r is consumed only when 0 <= R < 1 decides.
-YUNE_HD V3 sample_specular(const MatDev& m, V3 w_i, V3 n, float r, float& ior_factor)
+YUNE_HD_CALL V3 sample_specular(const MatDev& m, V3 w_i, V3 n, float r, float& ior_factor)
 {
     ior_factor = 1.0f;
     if (m.is_transmissive) {
@@ -213,11 +213,12 @@ YUNE_HD V3 sample_specular(const MatDev& m, V3 w_i, V3 n, float r, float& ior_fa
 
 // sampleLights (udpt.cl:632-698).  u[2*i], u[2*i+1] = point on light i; u_pick = light choice (n_lights > 1).
 // Returns the chosen light or -1; w_i is NOT normalised (the caller needs its length), pdf is w.r.t. solid angle.
-YUNE_HD int sample_lights(const LightDev* lights, int n_lights, V3 p, V3 n, const float* u, float u_pick, float& light_pdf, V3& w_i)
+YUNE_HD_CALL int sample_lights(const LightDev* lights, int n_lights, V3 p, V3 n, const float* u, float u_pick, float& light_pdf, V3& w_i)
 {
     float sum = 0.0f;
     float weights[YUNE_MAX_LIGHTS];
     V3 w_is[YUNE_MAX_LIGHTS];
+    YUNE_NO_UNROLL
     for (int i = 0; i < n_lights; i++) {
         const LightDev& L = lights[i];
         const float r1 = u[2 * i], r2 = u[2 * i + 1];
@@ -240,6 +241,7 @@ YUNE_HD int sample_lights(const LightDev* lights, int n_lights, V3 p, V3 n, cons
     }
     if (sum == 0.0f) return -1;
     float cumulative = 0.0f;
+    YUNE_NO_UNROLL
     for (int i = 0; i < n_lights; i++) {
         const float weight = YF_DIV(weights[i], sum);
         if (u_pick >= cumulative && u_pick < YF_ADD(cumulative, weight)) {

@@ -22,13 +22,21 @@ struct DevScene {
 struct LightSet { LightDev l[YUNE_MAX_LIGHTS]; int n; };
 
 // Per-iteration queue heads/counters (double buffered by iteration parity) + running totals.
+// Every counter sits in its own 128-byte line: they are hit by one atomic per block (shade) or per ray chunk (trace), and
+// atomics on the same line serialise in one L2 slice.
 struct IterCounters {
-    int n_extend, n_shadow, n_events, live;
-    int fetch_extend, fetch_shadow, n_shade, n_regen;
+    alignas(128) int n_extend;
+    alignas(128) int n_shadow;
+    alignas(128) int n_events;
+    alignas(128) int live;
+    alignas(128) int fetch_extend;
+    alignas(128) int fetch_shadow;
+    alignas(128) int n_shade;
+    alignas(128) int n_regen;
 };
 struct Totals {
-    unsigned long long next_sample;     // next global sample index to hand out
-    unsigned long long n_samples;       // samples to render in this call
+    alignas(128) unsigned long long next_sample;     // next global sample index to hand out (own line: atomics)
+    alignas(128) unsigned long long n_samples;       // samples to render in this call
     unsigned long long samples_done;
     unsigned long long extend_rays, shadow_rays, box_tests, tri_tests;
     int live_last;                      // slots still busy after the last completed iteration

@@ -80,7 +80,7 @@ __device__ __forceinline__ void create_ray(const float* cam, int W, int H, float
     w.x = vdot(v3(cam[0], cam[1], cam[2]), dir);
     w.y = vdot(v3(cam[4], cam[5], cam[6]), dir);
     w.z = vdot(v3(cam[8], cam[9], cam[10]), dir);
-    d = vnormalize(w);
+    d = vnormalize(w)                  /* exact: primary rays are compared bit for bit */;
     o = v3(cam[3], cam[7], cam[11]);
 }
 

@@ -54,7 +54,7 @@ YUNE_HD V3 vadd(V3 a, V3 b) { return v3(YF_ADD(a.x, b.x), YF_ADD(a.y, b.y), YF_A
 YUNE_HD V3 vsub(V3 a, V3 b) { return v3(YF_SUB(a.x, b.x), YF_SUB(a.y, b.y), YF_SUB(a.z, b.z)); }
 YUNE_HD V3 vmul(V3 a, V3 b) { return v3(YF_MUL(a.x, b.x), YF_MUL(a.y, b.y), YF_MUL(a.z, b.z)); }
 YUNE_HD V3 vscale(V3 a, float s) { return v3(YF_MUL(a.x, s), YF_MUL(a.y, s), YF_MUL(a.z, s)); }
-YUNE_HD V3 vdivs(V3 a, float s) { return v3(YF_DIV(a.x, s), YF_DIV(a.y, s), YF_DIV(a.z, s)); }
+
 YUNE_HD V3 vneg(V3 a) { return v3(-a.x, -a.y, -a.z); }
 // OpenCL dot() of two float4 whose w product is +0: ((x*x' + y*y') + z*z') [+ 0]
 YUNE_HD float vdot(V3 a, V3 b) { return YF_ADD(YF_ADD(YF_MUL(a.x, b.x), YF_MUL(a.y, b.y)), YF_MUL(a.z, b.z)); }
@@ -65,6 +65,21 @@ YUNE_HD V3 vcross(V3 a, V3 b)
               YF_SUB(YF_MUL(a.x, b.y), YF_MUL(a.y, b.x)));
 }
 YUNE_HD float vlength(V3 a) { return YF_SQRT(vdot(a, a)); }
+
+
+// Exact x / s for s > 0 that never enters the division's slow path because of a ZERO NUMERATOR.  IEEE division on the GPU is a
+// reciprocal + refinement guarded by a range check (FCHK) that sends zero / denormal / huge operands to a ~30-instruction
+// subroutine; axis-aligned normals and coloured albedos are full of zeros, and ncu attributed 18 % of the shade kernel's
+// instructions to that subroutine.  0 / s is just the (signed) zero, so the division is fed a harmless 1 instead and the zero is
+// put back.  Same bits as x / s in every case (s <= 0 or NaN falls through to the true division).
+YUNE_HD float div_pos(float x, float s)
+{
+    const bool z = (x == 0.0f) && (s > 0.0f);
+    const float q = YF_DIV(z ? 1.0f : x, s);
+    return z ? x : q;
+}
+
+YUNE_HD V3 vdivs(V3 a, float s) { return v3(div_pos(a.x, s), div_pos(a.y, s), div_pos(a.z, s)); }
 YUNE_HD V3 vnormalize(V3 a) { float l = YF_SQRT(vdot(a, a)); return vdivs(a, l); }
 
 // OpenCL min/max per the specification text (clc_shim.inc): only used where a NaN may reach them.

@@ -65,7 +65,8 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "rr_threshold" (udpt.cl:6 / bdpt.cl:4), "bdpt_bounces" (bdpt.cl:7), "oren_nayar" (0/1: use
  *   udpt-primitives.cl:681-725 for pure-diffuse lobes with sigma^2 = alpha_x),
  *   and engine knobs: "pool_slots" (path slots in flight), "smem_nodes" (pair records staged in shared memory),
- *   "leaf_split" (refine reference leaves holding more than N triangles with padded private subtrees; 0 = off),
+ *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
+ *   0 = walk the reference tree itself), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
  *   "trace_block", "trace_blocks_per_sm", "refill_idle", "phase_min" (trace-kernel launch shape / warp scheduling),
  *   "isect" (0 = reference Moller-Trumbore), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */

@@ -12,6 +12,7 @@ using namespace yune;
 namespace {
 struct HostPairFetch { const F4* p; void operator()(int i, F4& a, F4& b, F4& c, F4& d) const { const F4* q = p + (size_t)i * 4; a = q[0]; b = q[1]; c = q[2]; d = q[3]; } };
 struct HostTriFetch { const F4* p; void operator()(int i, F4& a, F4& b, F4& c) const { const F4* q = p + (size_t)i * 3; a = q[0]; b = q[1]; c = q[2]; } };
+struct HostLeafFetch { const F4* p; void operator()(int i, F4& lo, F4& hi) const { lo = p[2 * (size_t)i]; hi = p[2 * (size_t)i + 1]; } };
 LightDev unpack(const yune_quad_light& q)
 {
     LightDev L;
@@ -27,10 +28,11 @@ LightDev unpack(const yune_quad_light& q)
 
 extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
                         const yune_bvh_node* nodes, int nnodes, const yune_quad_light* lights, int nlights,
-                        int* tri_id, int* light_id, float* t_hit, unsigned long long* work2, int leaf_split)
+                        int* tri_id, int* light_id, float* t_hit, unsigned long long* work2, int leaf_split, int accel)
 {
     TravLayoutHost lay; std::string err;
-    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split)) return -1;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    HostLeafFetch lf{lay.leaf_boxes.data()};
     HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()};
     LightDev L[YUNE_MAX_LIGHTS];
     for (int i = 0; i < nlights; i++) L[i] = unpack(lights[i]);
@@ -42,11 +44,16 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
         int lid = light_loop(L, nlights, o, d, t);
         WorkCount wc = {0, 0};
         if (any) {
-            bool occ = lid >= 0 || any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, &wc);
+            bool occ = lid >= 0;
+            if (!occ) {
+                if (accel == 1) { HitRec h; trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
+                else occ = any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, &wc);
+            }
             tri_id[i] = occ ? 0 : -1; light_id[i] = lid; if (t_hit) t_hit[i] = t;
         } else {
             HitRec h;
-            closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
+            if (accel == 1) trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, false, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
+            else closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             tri_id[i] = h.tri; light_id[i] = h.tri >= 0 ? -1 : lid; if (t_hit) t_hit[i] = h.t;
         }
         nb += wc.box; nt += wc.tri;

@@ -267,6 +267,30 @@ def test_sample_ranges_add_up_and_pool_size_is_invisible(gpu_manager):
     m.check(r._lib.yune_render(r._ctx, 0, 0, 1, r.seed, 0))
 
 
+@pytest.mark.parametrize("accel,leaf_split", [(0, 0), (0, 2), (1, 0)])
+def test_every_acceleration_mode_is_bit_exact(gpu_manager, oracle, accel, leaf_split):
+    """The three walks (reference tree as is / with refined leaves / own tree + exact leaf-box filter) against the oracle."""
+    m = gpu_manager
+    old = (m.getOption("accel"), m.getOption("leaf_split"))
+    try:
+        m.setOption("accel", accel); m.setOption("leaf_split", leaf_split)
+        r, sc = _renderer(m, "teapot", 256, 256)
+        tri, light, t = r.tracePrimary(1, 4711)
+        otri, olight, ot, od, _ = oracle.primary(Oracle.config("udpt"), CAM, sc.vert_data, sc.bvh, 4711, 1, 256, 256)
+        assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all()
+        rng = np.random.RandomState(17); n = 200000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:1000, 0] = 0; d[1000:2000, 1] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od6 = np.concatenate([o, d], 1).astype(np.float32)
+        a = r.traceRays(od6); b = oracle.trace(Oracle.config("udpt"), od6, None, 0, sc.vert_data, sc.bvh)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (_bits(a[2]) == _bits(b[2])).all()
+        tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
+        sa = r.traceRays(od6, tm, any_hit=True); sb = oracle.trace(Oracle.config("udpt"), od6, tm, 1, sc.vert_data, sc.bvh)
+        assert (((sb[0] >= 0) | (sb[1] >= 0)) == (sa[0] >= 0)).all()
+    finally:
+        m.setOption("accel", old[0]); m.setOption("leaf_split", old[1])
+
+
 def test_fused_and_split_shade_kernels_agree(gpu_manager):
     """The stage can run as one fused kernel or as k_logic + k_surface + k_regen; same samples either way."""
     m = gpu_manager

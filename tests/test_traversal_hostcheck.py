@@ -20,11 +20,11 @@ def hc():
     return C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libyune_hostcheck.so"))
 
 
-def _trace(hc, od, tmax, any_hit, tris, nodes, leaf_split=0):
+def _trace(hc, od, tmax, any_hit, tris, nodes, leaf_split=0, accel=0):
     n = od.shape[0]
     tri = np.zeros(n, np.int32); light = np.zeros(n, np.int32); t = np.zeros(n, np.float32); work = np.zeros(2, np.uint64)
     rc = hc.hc_trace(n, ptr(od), ptr(tmax), int(any_hit), ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(LIGHT_UDPT), 1,
-                     ptr(tri), ptr(light), ptr(t), ptr(work), int(leaf_split))
+                     ptr(tri), ptr(light), ptr(t), ptr(work), int(leaf_split), int(accel))
     assert rc == 0
     return tri, light, t, work
 
@@ -60,11 +60,35 @@ def test_random_rays_closest_and_any(hc, oracle, scene):
     assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
 
 
+@pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
+@pytest.mark.parametrize("leaf_split,accel", [(2, 0), (1, 0), (0, 1)])
+def test_refined_leaves_and_own_tree_return_the_same_hits(hc, oracle, scene, leaf_split, accel):
+    """Both accelerations of the reference walk -- padded subtrees inside big leaves (accel 0, leaf_split) and our own SAH
+    tree with the exact leaf-box filter (accel 1) -- must give the reference's hit record bit for bit while testing far
+    fewer triangles."""
+    tris, mats, nodes = load_golden_scene(scene)
+    rng = np.random.RandomState(23); n = 40000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d[:300, 0] = 0; d[300:600, 1] = 0; d[600:900, 2] = 0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    tm = rng.uniform(0.01, 2.5, n).astype(np.float32)
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    tri, light, t, work = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
+    assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all()
+    _, _, _, work0 = _trace(hc, od, None, 0, tris, nodes, 0, 0)
+    assert work[1] < 0.6 * work0[1]                       # triangle tests
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, nodes)
+    atri, alight, _, _ = _trace(hc, od, tm, 1, tris, nodes, leaf_split, accel)
+    assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
+
+
 def test_layout_rejects_malformed_input(hc):
     tris, mats, nodes = load_golden_scene("cornellbox")
     od = np.zeros((1, 6), np.float32); od[0, 5] = -1
     bad = nodes.copy(); bad["child_idx"][0] = 10 ** 6
     tri = np.zeros(1, np.int32); light = np.zeros(1, np.int32)
-    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0) == -1
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0, 0) == -1
     bad = nodes.copy(); leaf = int(np.nonzero(bad["vert_len"] > 0)[0][0]); bad["vert_list"][leaf, 0] = 9999
-    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0) == -1
+    assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0, 0) == -1

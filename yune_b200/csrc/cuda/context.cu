@@ -53,7 +53,7 @@ struct yune_ctx {
     std::vector<yune_triangle> h_tris; std::vector<yune_bvh_node> h_nodes; std::vector<yune_material> h_mats;
     bool layout_dirty = true, have_tris = false, have_nodes = false, have_mats = false, have_cam = false;
     TravLayoutHost lay;
-    float4 *d_pairs = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_mats = nullptr;
+    float4 *d_pairs = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_mats = nullptr, *d_leaf_boxes = nullptr;
     DevScene sc{};
     yune_cam cam{};
 
@@ -78,7 +78,7 @@ struct yune_ctx {
     // options
     int opt_pool_slots = 1 << 21, opt_smem_nodes = 2048, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
-    int opt_leaf_split = 2, opt_fused_shade = 1;
+    int opt_leaf_split = 2, opt_fused_shade = 1, opt_accel = 1;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
     yune_stats stats{};
@@ -139,12 +139,14 @@ static int ensure_scene(yune_ctx* c)
         Y_FAIL(c, YUNE_ERR_STATE, "scene incomplete: vertex, material and BVH buffers must all be set up before rendering");
     if (!c->layout_dirty) return YUNE_OK;
     std::string err;
-    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split))
+    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     for (const yune_triangle& t : c->h_tris)
         if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
-    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade);
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
     const TravLayoutHost& L = c->lay;
+    Y_CUDA(c, cudaMalloc(&c->d_leaf_boxes, std::max<size_t>(L.leaf_boxes.size(), 2) * 16));
+    if (!L.leaf_boxes.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_leaf_boxes, L.leaf_boxes.data(), L.leaf_boxes.size() * 16, cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaMalloc(&c->d_pairs, std::max<size_t>(L.pairs.size(), 4) * 16));
     Y_CUDA(c, cudaMalloc(&c->d_tris, std::max<size_t>(L.tris.size(), 3) * 16));
     Y_CUDA(c, cudaMalloc(&c->d_shade, std::max<size_t>(L.shade.size(), 4) * 16));
@@ -153,7 +155,7 @@ static int ensure_scene(yune_ctx* c)
     if (!L.shade.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_shade, L.shade.data(), L.shade.size() * 16, cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
     DevScene& s = c->sc;
-    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats;
+    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats; s.leaf_boxes = c->d_leaf_boxes; s.accel = L.accel;
     s.n_inner = L.n_inner; s.n_tris = L.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = L.root_ref;
     for (int k = 0; k < 3; k++) { s.root_lo[k] = L.root_lo[k]; s.root_hi[k] = L.root_hi[k]; }
     c->layout_dirty = false;
@@ -229,7 +231,7 @@ void yune_destroy(yune_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_pool(c);
-    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats);
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes);
     dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_ctr); dfree(c->d_tot);
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
     dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
@@ -351,7 +353,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split}, {"fused_shade", &c->opt_fused_shade},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split}, {"fused_shade", &c->opt_fused_shade}, {"accel", &c->opt_accel},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -368,6 +370,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
+    if (p == &c->opt_accel) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree) or 1 (own tree + exact leaf-box filter)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     *p = v;
     return YUNE_OK;

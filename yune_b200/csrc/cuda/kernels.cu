@@ -25,7 +25,7 @@ namespace yune {
 #define YUNE_REF_DONE (-1)
 
 struct Lane {
-    V3 o, d, inv;
+    V3 o, d, inv, oi;       // oi = o * inv: fused slab test of our own tree (ACCEL 1)
     float t_best, t_prune, u, v;
     int tri, best_pos, cur, leaf_pos, leaf_end, sp;
     bool guard;
@@ -60,7 +60,19 @@ __device__ __noinline__ float box_guarded(V3 o, V3 inv, float lox, float hix, fl
     return (t_max > entry) ? entry : -1.0f;          // entry >= 0 on a hit, -1 on a miss
 }
 
-template <bool ANY, bool COUNT>
+// Conservative slab test for OUR boxes (trace_core.h: box_hit_own): one FFMA per plane, pruning distance folded in.
+__device__ __forceinline__ bool box_own(const Lane& L, float lox, float hix, float loy, float hiy, float loz, float hiz, float& entry)
+{
+    const float ax = __fmaf_rn(lox, L.inv.x, -L.oi.x), bx = __fmaf_rn(hix, L.inv.x, -L.oi.x);
+    const float ay = __fmaf_rn(loy, L.inv.y, -L.oi.y), by = __fmaf_rn(hiy, L.inv.y, -L.oi.y);
+    const float az = __fmaf_rn(loz, L.inv.z, -L.oi.z), bz = __fmaf_rn(hiz, L.inv.z, -L.oi.z);
+    const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.t_prune));
+    entry = t_min;
+    return YF_MUL(t_max, 1.000001f) >= YF_MUL(t_min, 0.999999f);
+}
+
+template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o, float4 d, WorkCount& wc)
 {
     L.o = xyz(o); L.d = xyz(d);
@@ -68,8 +80,15 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
     L.guard = !(fabsf(L.inv.x) < INFINITY && fabsf(L.inv.y) < INFINITY && fabsf(L.inv.z) < INFINITY);
     L.t_best = o.w; L.t_prune = o.w * 1.00001f;
     L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = 0;
+    L.oi = v3(YF_MUL(L.o.x, L.inv.x), YF_MUL(L.o.y, L.inv.y), YF_MUL(L.o.z, L.inv.z));
     float entry; bool hit = false;
-    if (sc.root_ref != YUNE_REF_EMPTY) {
+    if (ACCEL == 1) {
+        if (sc.root_ref != YUNE_REF_EMPTY) {
+            if (COUNT) wc.box++;
+            if (!L.guard) hit = box_own(L, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
+            else hit = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]) >= 0.0f;
+        }
+    } else if (sc.root_ref != YUNE_REF_EMPTY) {
         if (COUNT) wc.box++;
         if (L.guard) { entry = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]); hit = entry >= 0.0f; }
         else hit = box_fast(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
@@ -77,7 +96,7 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
     lane_enter(L, hit ? sc.root_ref : YUNE_REF_DONE);
 }
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const float4* s_pairs, WorkCount& wc)
 {
     float4 q0, q1, q2, q3;
@@ -85,7 +104,10 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
     else { const float4* p = sc.pairs + 4 * (size_t)L.cur; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3); }
     const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
     float e0, e1; bool h0, h1;
-    if (!L.guard) {
+    if (ACCEL == 1 && !L.guard) {
+        h0 = box_own(L, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
+        h1 = box_own(L, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
+    } else if (!L.guard) {
         h0 = box_fast(L.o, L.inv, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
         h1 = box_fast(L.o, L.inv, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
     } else {
@@ -93,8 +115,10 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
         e1 = box_guarded(L.o, L.inv, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w); h1 = e1 >= 0.0f;
     }
     if (COUNT) wc.box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
-    h0 = h0 && (ref0 != YUNE_REF_EMPTY) && !(e0 > L.t_prune);
-    h1 = h1 && (ref1 != YUNE_REF_EMPTY) && !(e1 > L.t_prune);
+    if (ACCEL == 0 || L.guard) {        // (ACCEL 1 folds the pruning distance into box_own; its guarded fallback does not)
+        h0 = h0 && (ref0 != YUNE_REF_EMPTY) && !(e0 > L.t_prune);
+        h1 = h1 && (ref1 != YUNE_REF_EMPTY) && !(e1 > L.t_prune);
+    }
     const bool both = h0 && h1;
     const bool swap = !ANY && both && (e1 < e0);
     int next = (h0 && !swap) ? ref0 : ref1;
@@ -103,7 +127,7 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
     lane_enter(L, next);
 }
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, WorkCount& wc)
 {
     const int pos = L.leaf_pos++;
@@ -121,7 +145,18 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     const V3 qvec = vcross(dist, e1);
     const float v = YF_MUL(vdot(qvec, L.d), inv_det);
     const float t = YF_MUL(vdot(e2, qvec), inv_det);
-    const bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
+    bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
+    if (ACCEL == 1) {
+        // Would the reference have reached this triangle?  <=> the uploaded box of its reference leaf passes the reference's
+        // own predicate (its ancestors' boxes contain it exactly, so they pass too).
+        const float4* lb = sc.leaf_boxes + 2 * (size_t)__float_as_int(c.w);
+        const float4 lo = __ldg(lb), hi = __ldg(lb + 1);
+        float entry; bool reach;
+        if (COUNT) wc.box++;
+        if (!L.guard) reach = box_fast(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
+        else reach = box_guarded(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) >= 0.0f;
+        inside = inside && reach;
+    }
     bool finished_leaf = L.leaf_pos >= L.leaf_end;
     if (ANY) {
         if (inside && t > 0.0f && t < L.t_best) { L.tri = 0; L.sp = 0; finished_leaf = true; }        // udpt.cl:306-308
@@ -144,7 +179,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 #define YUNE_PHASE_MAX   8
 #define YUNE_FETCH_CHUNK 128
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_pairs, WorkCount& wc)
 {
     const DevScene& sc = A.sc;
@@ -185,7 +220,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
                 float4 o, d;
                 if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
                 else { where = A.eq ? A.eq[q] : q; o = A.ray_o[where]; d = A.ray_d[where]; }
-                lane_init<ANY, COUNT>(L, sc, o, d, wc);
+                lane_init<ANY, COUNT, ACCEL>(L, sc, o, d, wc);
                 have = true;
             }
             chunk_next = min(chunk_next + __popc(idle), chunk_end);
@@ -197,7 +232,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
         for (int k = 0; k < YUNE_PHASE_MAX; k++) {        // bounded so that finished lanes are retired / refilled regularly
             const bool want = L.cur >= 0;
             if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
-            if (want) lane_inner_step<ANY, COUNT>(L, stack, sc, s_pairs, wc);
+            if (want) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_pairs, wc);
             progressed = true;
         }
         // ---- TRI phase ----
@@ -205,20 +240,20 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
         for (int k = 0; k < YUNE_PHASE_MAX; k++) {
             const bool want = L.leaf_pos < L.leaf_end;
             if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
-            if (want) lane_tri_step<ANY, COUNT>(L, stack, sc, wc);
+            if (want) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc);
             progressed = true;
         }
         // ---- thin warp (fewer than phase_min lanes in either mode): one step of each kind ----
         if (!progressed) {
-            if (L.cur >= 0) lane_inner_step<ANY, COUNT>(L, stack, sc, s_pairs, wc);
+            if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_pairs, wc);
             __syncwarp();
-            if (L.leaf_pos < L.leaf_end) lane_tri_step<ANY, COUNT>(L, stack, sc, wc);
+            if (L.leaf_pos < L.leaf_end) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc);
             __syncwarp();
         }
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, int ACCEL>
 __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
 {
     extern __shared__ float4 s_pairs[];
@@ -227,8 +262,8 @@ __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
     __syncthreads();
 
     WorkCount wc; wc.box = 0; wc.tri = 0;
-    trace_queue<true, COUNT>(A, s_pairs, wc);      // shadow rays: any hit
-    trace_queue<false, COUNT>(A, s_pairs, wc);     // extension rays: closest hit
+    trace_queue<true, COUNT, ACCEL>(A, s_pairs, wc);      // shadow rays: any hit
+    trace_queue<false, COUNT, ACCEL>(A, s_pairs, wc);     // extension rays: closest hit
     if (COUNT) {
         const int lane = threadIdx.x & 31;
         unsigned long long b = wc.box, t = wc.tri;
@@ -814,20 +849,22 @@ static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); 
 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
-    if (count) k_trace<true><<<grid, block, smem_bytes, st>>>(a);
-    else       k_trace<false><<<grid, block, smem_bytes, st>>>(a);
+    if (a.sc.accel == 1) { if (count) k_trace<true, 1><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 1><<<grid, block, smem_bytes, st>>>(a); }
+    else                 { if (count) k_trace<true, 0><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 0><<<grid, block, smem_bytes, st>>>(a); }
     return cudaGetLastError();
 }
 cudaError_t trace_set_smem(size_t smem_bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_trace<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    return e;
 }
 int trace_blocks_per_sm(int block, size_t smem_bytes)
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, block, smem_bytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, 1>, block, smem_bytes) != cudaSuccess) return 0;
     return n;
 }
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st)

@@ -88,17 +88,171 @@ struct Refiner {
     }
 };
 
+// ---- accel 1: our own tree ---------------------------------------------------------------------------------------------
+struct OwnTri { float lo[3], hi[3], c[3]; int tri, rank, leaf; };
+struct OwnNode { float lo[3], hi[3]; int left, right, first, count; };   // left < 0: leaf [first, first + count)
+
+struct OwnBuilder {
+    std::vector<OwnTri>& t; std::vector<OwnNode> nodes; int depth_max = 0;
+    explicit OwnBuilder(std::vector<OwnTri>& tt) : t(tt) {}
+    static float area(const float* lo, const float* hi) { float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx * dy + dx * dz + dy * dz; }
+    int build(int b, int e, int depth)
+    {
+        if (depth > depth_max) depth_max = depth;
+        OwnNode nd; nd.left = nd.right = -1; nd.first = b; nd.count = e - b;
+        float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int k = 0; k < 3; k++) { nd.lo[k] = 3e38f; nd.hi[k] = -3e38f; }
+        for (int i = b; i < e; i++) for (int k = 0; k < 3; k++) {
+            nd.lo[k] = std::min(nd.lo[k], t[i].lo[k]); nd.hi[k] = std::max(nd.hi[k], t[i].hi[k]);
+            clo[k] = std::min(clo[k], t[i].c[k]); chi[k] = std::max(chi[k], t[i].c[k]);
+        }
+        const int me = (int)nodes.size(); nodes.push_back(nd);
+        if (e - b <= 2) return me;
+        int axis = 0; for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+        int mid = (b + e) / 2;
+        const float ext = chi[axis] - clo[axis];
+        if (ext > 0.0f) {
+            const int NB = 16;
+            int cnt[NB] = {0}; float blo[NB][3], bhi[NB][3];
+            for (int q = 0; q < NB; q++) for (int k = 0; k < 3; k++) { blo[q][k] = 3e38f; bhi[q][k] = -3e38f; }
+            const float scale = NB * (1.0f - 1e-6f) / ext;
+            auto bin_of = [&](const OwnTri& x) { int q = (int)((x.c[axis] - clo[axis]) * scale); return q < 0 ? 0 : (q >= NB ? NB - 1 : q); };
+            for (int i = b; i < e; i++) { const int q = bin_of(t[i]); cnt[q]++; for (int k = 0; k < 3; k++) { blo[q][k] = std::min(blo[q][k], t[i].lo[k]); bhi[q][k] = std::max(bhi[q][k], t[i].hi[k]); } }
+            float rl[NB][3], rh[NB][3]; int rc[NB];
+            { float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}; int c = 0;
+              for (int q = NB - 1; q >= 0; q--) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[q][k]); hi[k] = std::max(hi[k], bhi[q][k]); } c += cnt[q]; for (int k = 0; k < 3; k++) { rl[q][k] = lo[k]; rh[q][k] = hi[k]; } rc[q] = c; } }
+            float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}; int c = 0, best = -1; float best_cost = 3e38f;
+            for (int q = 0; q < NB - 1; q++) {
+                for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], blo[q][k]); hi[k] = std::max(hi[k], bhi[q][k]); }
+                c += cnt[q];
+                if (c == 0 || rc[q + 1] == 0) continue;
+                const float cost = area(lo, hi) * c + area(rl[q + 1], rh[q + 1]) * rc[q + 1];
+                if (cost < best_cost) { best_cost = cost; best = q; }
+            }
+            if (best >= 0) {
+                mid = (int)(std::partition(t.begin() + b, t.begin() + e, [&](const OwnTri& x) { return bin_of(x) <= best; }) - t.begin());
+                if (mid == b || mid == e) mid = (b + e) / 2;
+            }
+        }
+        const int l = build(b, mid, depth + 1);
+        const int r = build(mid, e, depth + 1);
+        nodes[me].left = l; nodes[me].right = r;
+        return me;
+    }
+};
+
+// Structural checks shared by both layouts: child indices in range and breadth-first, leaves sane, every leaf linked from the root
+// (accel 1 decides reachability from the leaf boxes alone, so an orphan leaf must be an error, not silently visible).
+static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n_tris, std::string& err)
+{
+    std::vector<char> linked(n_nodes, 0);
+    linked[0] = 1;
+    for (int i = 0; i < n_nodes; i++) {
+        const yune_bvh_node& nd = nodes[i];
+        const bool is_leaf = nd.child_idx == -1 && nd.vert_len > 0;
+        const bool is_inner = !is_leaf && nd.child_idx > 0;
+        if (is_leaf) {
+            if (nd.vert_len > 10) { err = "leaf with more than 10 triangles"; return false; }
+            for (int j = 0; j < nd.vert_len; j++)
+                if (nd.vert_list[j] < 0 || nd.vert_list[j] >= n_tris) { err = "leaf references a triangle out of range"; return false; }
+            if (!linked[i]) { err = "leaf is not linked from the root"; return false; }
+        } else if (is_inner) {
+            if (nd.child_idx + 1 >= n_nodes) { err = "child index out of range"; return false; }
+            if (nd.child_idx <= i) { err = "BVH is not in breadth-first order (child index <= parent index)"; return false; }
+            if (linked[i]) linked[nd.child_idx] = linked[nd.child_idx + 1] = 1;
+        }
+    }
+    return true;
+}
+
+static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes, TravLayoutHost& out, std::string& err)
+{
+    if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    // reference leaves: id, box, visiting rank of every triangle slot
+    std::vector<OwnTri> t; t.reserve(n_tris);
+    int rank = 0, n_leaves = 0;
+    for (int i = 0; i < n_nodes; i++) {
+        const yune_bvh_node& nd = nodes[i];
+        if (!(nd.child_idx == -1 && nd.vert_len > 0)) continue;
+        if (nd.vert_len > 10) { err = "leaf with more than 10 triangles"; return false; }
+        out.leaf_boxes.push_back({nd.aabb.p_min.s[0], nd.aabb.p_min.s[1], nd.aabb.p_min.s[2], 0.0f});
+        out.leaf_boxes.push_back({nd.aabb.p_max.s[0], nd.aabb.p_max.s[1], nd.aabb.p_max.s[2], 0.0f});
+        for (int j = 0; j < nd.vert_len; j++) {
+            const int id = nd.vert_list[j];
+            if (id < 0 || id >= n_tris) { err = "leaf references a triangle out of range"; return false; }
+            OwnTri x; x.tri = id; x.rank = rank++; x.leaf = n_leaves;
+            const yune_triangle& T = tris[id];
+            float ext = 0.0f, mag = 0.0f;
+            for (int k = 0; k < 3; k++) {
+                x.lo[k] = std::min(T.v1.s[k], std::min(T.v2.s[k], T.v3.s[k]));
+                x.hi[k] = std::max(T.v1.s[k], std::max(T.v2.s[k], T.v3.s[k]));
+                x.c[k] = 0.5f * (x.lo[k] + x.hi[k]);
+                ext = std::max(ext, x.hi[k] - x.lo[k]); mag = std::max(mag, std::max(std::fabs(x.lo[k]), std::fabs(x.hi[k])));
+            }
+            const float pad = 2.0e-3f * ext + 4.0e-6f * mag + 1.0e-30f;      // same conservative margin as the leaf refinement
+            for (int k = 0; k < 3; k++) { x.lo[k] -= pad; x.hi[k] += pad; }
+            t.push_back(x);
+        }
+        n_leaves++;
+    }
+    out.n_leaf_tris = (int)t.size();
+    if (t.empty()) { out.root_ref = YUNE_REF_EMPTY; out.n_inner = out.n_inner_ref = 0; out.max_depth = 0; return true; }
+    OwnBuilder B(t);
+    const int root = B.build(0, (int)t.size(), 0);
+    if (B.depth_max + 2 > YUNE_STACK_SIZE) { err = "BVH deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
+    out.max_depth = B.depth_max;
+    for (int k = 0; k < 3; k++) { out.root_lo[k] = B.nodes[root].lo[k]; out.root_hi[k] = B.nodes[root].hi[k]; }
+    // triangles in builder order (each leaf contiguous)
+    out.tris.resize((size_t)t.size() * 3);
+    for (size_t i = 0; i < t.size(); i++) {
+        const yune_triangle& T = tris[t[i].tri];
+        V3 v1 = v3(T.v1.s[0], T.v1.s[1], T.v1.s[2]);
+        V3 e1 = vsub(v3(T.v2.s[0], T.v2.s[1], T.v2.s[2]), v1);
+        V3 e2 = vsub(v3(T.v3.s[0], T.v3.s[1], T.v3.s[2]), v1);
+        out.tris[3 * i + 0] = {v1.x, v1.y, v1.z, bits(t[i].tri)};
+        out.tris[3 * i + 1] = {e1.x, e1.y, e1.z, bits(t[i].rank)};
+        out.tris[3 * i + 2] = {e2.x, e2.y, e2.z, bits(t[i].leaf)};
+    }
+    // pair records in breadth-first order of the inner nodes
+    std::vector<int> pair_of(B.nodes.size(), -1), order;
+    auto ref_of = [&](int n) { const OwnNode& nd = B.nodes[n]; return nd.left < 0 ? ~((nd.first << 4) | nd.count) : pair_of[n]; };
+    if (B.nodes[root].left >= 0) { order.push_back(root); pair_of[root] = 0; }
+    for (size_t h = 0; h < order.size(); h++) {
+        const OwnNode& nd = B.nodes[order[h]];
+        for (int c : {nd.left, nd.right}) if (B.nodes[c].left >= 0) { pair_of[c] = (int)order.size(); order.push_back(c); }
+    }
+    out.pairs.resize(order.size() * 4);
+    for (size_t h = 0; h < order.size(); h++) {
+        const OwnNode& nd = B.nodes[order[h]];
+        const OwnNode& a = B.nodes[nd.left]; const OwnNode& b = B.nodes[nd.right];
+        F4* q = &out.pairs[h * 4];
+        q[0] = {a.lo[0], a.hi[0], a.lo[1], a.hi[1]};
+        q[1] = {b.lo[0], b.hi[0], b.lo[1], b.hi[1]};
+        q[2] = {a.lo[2], a.hi[2], b.lo[2], b.hi[2]};
+        q[3] = {bits(ref_of(nd.left)), bits(ref_of(nd.right)), 0.0f, 0.0f};
+    }
+    out.n_inner = out.n_inner_ref = (int)order.size();
+    out.root_ref = ref_of(root);
+    return true;
+}
+
 } // namespace
 
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err, int leaf_split)
+                     TravLayoutHost& out, std::string& err, int leaf_split, int accel)
 {
     out = TravLayoutHost();
     if (n_nodes <= 0 || !nodes) { err = "no BVH nodes (brute-force mode, bvh_size == 0, is not supported)"; return false; }
     if (n_tris < 0 || (n_tris > 0 && !tris)) { err = "bad triangle buffer"; return false; }
     if (n_tris >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
-    out.n_tris = n_tris;
+    out.n_tris = n_tris; out.accel = accel;
 
+    if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    if (accel == 1) {
+        if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err)) return false;
+        goto shade_records;
+    }
+    {
     // classify nodes; inner nodes get their pair index in node-index (= breadth-first) order
     std::vector<int> ref(n_nodes, YUNE_REF_EMPTY);
     std::vector<char> kind(n_nodes, 0);      // 0 empty, 1 inner, 2 leaf
@@ -167,6 +321,8 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     out.max_depth = max_depth + sub_depth;
     if (out.max_depth + 2 > YUNE_STACK_SIZE) { err = "BVH deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
 
+    }
+shade_records:
     out.shade.resize((size_t)n_tris * 4);
     for (int i = 0; i < n_tris; i++) {
         const yune_triangle& t = tris[i];

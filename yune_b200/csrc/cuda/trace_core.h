@@ -22,6 +22,7 @@ namespace yune {
 
 struct RayPre {
     V3 o, d, inv;     // inv = 1 / d, IEEE division (udpt.cl:395)
+    V3 oi;            // o * inv, for the fused slab test of our own tree (accel 1)
     bool guard;       // some 1/d is not finite -> NaNs are possible in the slab products
 };
 
@@ -31,6 +32,7 @@ YUNE_HD RayPre make_ray(V3 o, V3 d)
     r.inv = v3(YF_DIV(1.0f, d.x), YF_DIV(1.0f, d.y), YF_DIV(1.0f, d.z));
     // finite <=> |x| < inf (false for NaN too)
     r.guard = !(fabsf(r.inv.x) < INFINITY && fabsf(r.inv.y) < INFINITY && fabsf(r.inv.z) < INFINITY);
+    r.oi = v3(YF_MUL(o.x, r.inv.x), YF_MUL(o.y, r.inv.y), YF_MUL(o.z, r.inv.z));
     return r;
 }
 
@@ -65,6 +67,30 @@ YUNE_HD bool box_hit(const RayPre& r, float lox, float hix, float loy, float hiy
     }
     entry = fmaxf(t_min, 0.0f);
     return t_max > entry;
+}
+
+// Slab test for OUR boxes (accel 1): one fused multiply-add per plane, result widened by a few ulps.  It only has to be
+// CONSERVATIVE (never reject a box that holds a triangle the ray hits); which triangles the reference would have reached is
+// decided separately, with box_hit() on the reference leaf's box.  A NaN (0 * inf on an axis the ray does not move along) is
+// dropped by fminf/fmaxf, i.e. that axis does not constrain -- conservative again.
+#if defined(__CUDA_ARCH__)
+  #define YF_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+  #define YF_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
+YUNE_HD bool box_hit_own(const RayPre& r, float lox, float hix, float loy, float hiy, float loz, float hiz, float t_prune, float& entry)
+{
+    if (r.guard) {      // 1/d not finite: lo * inf - o * inf is inf - inf; use the subtract-then-multiply form with its NaN guards
+        const bool h = box_hit(r, lox, hix, loy, hiy, loz, hiz, entry);
+        return h && !(entry > t_prune);
+    }
+    const float ax = YF_FMA(lox, r.inv.x, -r.oi.x), bx = YF_FMA(hix, r.inv.x, -r.oi.x);
+    const float ay = YF_FMA(loy, r.inv.y, -r.oi.y), by = YF_FMA(hiy, r.inv.y, -r.oi.y);
+    const float az = YF_FMA(loz, r.inv.z, -r.oi.z), bz = YF_FMA(hiz, r.inv.z, -r.oi.z);
+    const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_prune));
+    entry = t_min;
+    return YF_MUL(t_max, 1.000001f) >= YF_MUL(t_min, 0.999999f);
 }
 
 // Moller-Trumbore, two-sided, no determinant epsilon, borders included (udpt.cl:326-350).  `tri` points at the
@@ -182,6 +208,73 @@ YUNE_HD void ts_tri_step(TraceState& s, const int* stack, const TriFetch& fetch_
         }
     }
     if (s.leaf_pos >= s.leaf_end) ts_pop(s, stack);
+}
+
+// ---- accel 1: the same machine over our own tree ----
+template <class PairFetch, bool ANY, bool COUNT>
+YUNE_HD void ts_inner_step_own(TraceState& s, int* stack, const PairFetch& fetch_pair, WorkCount* wc)
+{
+    F4 q0, q1, q2, q3;
+    fetch_pair(s.cur, q0, q1, q2, q3);
+    const int ref0 = YF_ASINT(q3.x), ref1 = YF_ASINT(q3.y);
+    float e0, e1;
+    if (COUNT) wc->box += 2;
+    const bool h0 = box_hit_own(s.r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, s.t_prune, e0);
+    const bool h1 = box_hit_own(s.r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, s.t_prune, e1);
+    if (h0 && h1) {
+        const bool swap = !ANY && (e1 < e0);
+        stack[s.sp++] = swap ? ref0 : ref1;
+        ts_enter(s, swap ? ref1 : ref0);
+    } else if (h0) ts_enter(s, ref0);
+    else if (h1) ts_enter(s, ref1);
+    else ts_pop(s, stack);
+}
+// fetch_leaf_box(id, lo, hi) returns the uploaded box of reference leaf `id`
+template <class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
+YUNE_HD void ts_tri_step_own(TraceState& s, const int* stack, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, WorkCount* wc)
+{
+    const int pos = s.leaf_pos++;
+    F4 a, b, c, lo, hi;
+    fetch_tri(pos, a, b, c);
+    fetch_leaf_box(YF_ASINT(c.w), lo, hi);
+    float t, u, v, entry;
+    if (COUNT) { wc->tri++; wc->box++; }
+    // would the reference have reached this triangle?  <=> the box of its leaf passes the reference's predicate (udpt.cl:392-431)
+    const bool reachable = box_hit(s.r, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
+    if (reachable && tri_test(s.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+        if (ANY) {
+            if (t > 0.0f && t < s.t_best) { s.tri = 0; s.done = true; s.leaf_pos = s.leaf_end = 0; return; }
+        } else if (t > 0.0f && (t < s.t_best || (t == s.t_best && s.best_pos >= 0 && YF_ASINT(b.w) < s.best_pos))) {
+            s.t_best = t; s.u = u; s.v = v; s.tri = YF_ASINT(a.w); s.best_pos = YF_ASINT(b.w);
+            s.t_prune = t * 1.00001f;
+        }
+    }
+    if (s.leaf_pos >= s.leaf_end) ts_pop(s, stack);
+}
+template <bool COUNT>
+YUNE_HD void ts_init_own(TraceState& s, V3 o, V3 d, float t_in, int root_ref, const float* root_lo, const float* root_hi, WorkCount* wc)
+{
+    s.r = make_ray(o, d);
+    s.t_best = t_in; s.t_prune = t_in * 1.00001f;
+    s.u = 0.0f; s.v = 0.0f; s.tri = -1; s.best_pos = -1;
+    s.cur = 0; s.leaf_pos = s.leaf_end = 0; s.sp = 0; s.done = false;
+    if (root_ref == YUNE_REF_EMPTY) { s.done = true; return; }
+    float entry;
+    if (COUNT) wc->box++;
+    if (!box_hit_own(s.r, root_lo[0], root_hi[0], root_lo[1], root_hi[1], root_lo[2], root_hi[2], s.t_prune, entry)) { s.done = true; return; }
+    ts_enter(s, root_ref);
+}
+template <class PairFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
+YUNE_HD void trace_own(const PairFetch& fetch_pair, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, int root_ref,
+                       const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)
+{
+    TraceState s; int stack[YUNE_STACK_SIZE];
+    ts_init_own<COUNT>(s, o, d, t_in, root_ref, root_lo, root_hi, wc);
+    while (!s.done) {
+        if (s.leaf_pos < s.leaf_end) ts_tri_step_own<TriFetch, LeafBoxFetch, ANY, COUNT>(s, stack, fetch_tri, fetch_leaf_box, wc);
+        else ts_inner_step_own<PairFetch, ANY, COUNT>(s, stack, fetch_pair, wc);
+    }
+    out.t = s.t_best; out.u = s.u; out.v = s.v; out.tri = s.tri;
 }
 
 // ---- whole-ray wrappers (host check, hooks): drive the machine until done ----

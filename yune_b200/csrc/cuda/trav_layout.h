@@ -37,6 +37,8 @@ struct TravLayoutHost {
     std::vector<F4> pairs;       // 4 per inner node
     std::vector<F4> tris;        // 3 per leaf-ordered triangle
     std::vector<F4> shade;       // 4 per original triangle
+    std::vector<F4> leaf_boxes;  // accel 1: 2 per REFERENCE leaf (p_min, p_max exactly as uploaded), indexed by the id in triangle record t2.w
+    int   accel = 0;
     int   n_inner = 0, n_inner_ref = 0, n_leaf_tris = 0, n_tris = 0;   // n_inner counts refinement pairs too; n_inner_ref = reference inner nodes
     int   root_ref = YUNE_REF_EMPTY;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
@@ -47,8 +49,16 @@ struct TravLayoutHost {
 // triangle index out of range, leaf with more than 10 slots, tree deeper than YUNE_STACK_SIZE).
 // leaf_split: 0 = keep the reference's leaves (up to 10 triangles); N > 0 = refine every leaf holding more than N triangles
 // with a private, padded subtree (see relayout.cpp) -- same hits, fewer triangle tests.
+//
+// accel: 0 = walk the reference tree itself (pair records = the reference's boxes, entered under the reference's predicate).
+//        1 = walk OUR OWN binned-SAH tree over the same triangles (tight boxes, conservatively padded, leaves of <= 2), and
+//            decide per candidate triangle whether the REFERENCE would have reached it by testing the box of its reference
+//            leaf with the reference's exact predicate.  Sound because every reference box contains its children's boxes
+//            exactly (getExtent / refit, src/BVH.cpp:218-278) and float subtraction / multiplication are monotone, so
+//            "the leaf's box passes" implies "every ancestor's box passes" (rays with a non-finite 1/d excepted).
+//            Same hit records, roughly half the box tests and a third of the triangle tests.
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err, int leaf_split = 0);
+                     TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0);
 
 } // namespace yune
 #endif

@@ -167,9 +167,9 @@ static int trace_config(yune_ctx* c, TraceLaunch& tl)
 {
     int n_smem = c->opt_smem_nodes < c->sc.n_inner ? c->opt_smem_nodes : c->sc.n_inner;
     if (n_smem < 0) n_smem = 0;
-    if (n_smem > 3400) n_smem = 3400;                         // 3400 * 64 B = 212.5 KB < 227 KB
+    if (n_smem > 3900) n_smem = 3900;                         // 3900 * 56 B = 213 KB < 227 KB
     c->sc.n_smem_pairs = n_smem;
-    tl.smem = (size_t)n_smem * 64;
+    tl.smem = (size_t)n_smem * 56;                            // 48 B of boxes + 8 B of child refs per staged record
     Y_CUDA(c, trace_set_smem(tl.smem > 0 ? tl.smem : 16));
     tl.block = c->opt_trace_block;
     int per_sm = trace_blocks_per_sm(tl.block, tl.smem);

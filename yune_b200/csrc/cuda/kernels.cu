@@ -97,12 +97,20 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const float4* s_pairs, WorkCount& wc)
+__device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const float4* s_box, const int2* s_ref, WorkCount& wc)
 {
     float4 q0, q1, q2, q3;
-    if (L.cur < sc.n_smem_pairs) { const float4* p = s_pairs + 4 * L.cur; q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3]; }
-    else { const float4* p = sc.pairs + 4 * (size_t)L.cur; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3); }
-    const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
+    int ref0, ref1;
+    if (L.cur < sc.n_smem_pairs) {
+        // Shared-memory copy: boxes at a 48-byte stride, child refs in a separate int2 array.  With the 64-byte records of
+        // the global layout every lane's q_k would fall into the same two 16-byte bank columns (64 * idx mod 128) and an
+        // LDS.128 of 18 scattered lanes took ~15 wavefronts (ncu); 48 * idx mod 128 visits all eight columns.
+        const float4* p = s_box + 3 * L.cur; q0 = p[0]; q1 = p[1]; q2 = p[2];
+        const int2 rr = s_ref[L.cur]; ref0 = rr.x; ref1 = rr.y;
+    } else {
+        const float4* p = sc.pairs + 4 * (size_t)L.cur; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+        ref0 = __float_as_int(q3.x); ref1 = __float_as_int(q3.y);
+    }
     float e0, e1; bool h0, h1;
     if (ACCEL == 1 && !L.guard) {
         h0 = box_own(L, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
@@ -148,14 +156,19 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
     if (ACCEL == 1) {
         // Would the reference have reached this triangle?  <=> the uploaded box of its reference leaf passes the reference's
-        // own predicate (its ancestors' boxes contain it exactly, so they pass too).
-        const float4* lb = sc.leaf_boxes + 2 * (size_t)__float_as_int(c.w);
-        const float4 lo = __ldg(lb), hi = __ldg(lb + 1);
-        float entry; bool reach;
-        if (COUNT) wc.box++;
-        if (!L.guard) reach = box_fast(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
-        else reach = box_guarded(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) >= 0.0f;
-        inside = inside && reach;
+        // own predicate (its ancestors' boxes contain it exactly, so they pass too).  Geometrically a ray that hits the
+        // triangle always crosses that box, so the test can only ever reject in last-bit grazing cases; it is evaluated just
+        // for the lanes that are about to accept a hit, which keeps its two loads off the L1 pipe almost always.
+        const bool candidate = inside && t > 0.0f && !(t > L.t_best);
+        if (candidate) {
+            const float4* lb = sc.leaf_boxes + 2 * (size_t)__float_as_int(c.w);
+            const float4 lo = __ldg(lb), hi = __ldg(lb + 1);
+            float entry; bool reach;
+            if (COUNT) wc.box++;
+            if (!L.guard) reach = box_fast(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
+            else reach = box_guarded(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) >= 0.0f;
+            inside = reach;
+        }
     }
     bool finished_leaf = L.leaf_pos >= L.leaf_end;
     if (ANY) {
@@ -180,7 +193,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 #define YUNE_FETCH_CHUNK 128
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_pairs, WorkCount& wc)
+__device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_box, const int2* s_ref, WorkCount& wc)
 {
     const DevScene& sc = A.sc;
     const int lane = threadIdx.x & 31;
@@ -232,7 +245,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
         for (int k = 0; k < YUNE_PHASE_MAX; k++) {        // bounded so that finished lanes are retired / refilled regularly
             const bool want = L.cur >= 0;
             if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
-            if (want) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_pairs, wc);
+            if (want) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
             progressed = true;
         }
         // ---- TRI phase ----
@@ -245,7 +258,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
         }
         // ---- thin warp (fewer than phase_min lanes in either mode): one step of each kind ----
         if (!progressed) {
-            if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_pairs, wc);
+            if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
             __syncwarp();
             if (L.leaf_pos < L.leaf_end) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc);
             __syncwarp();
@@ -256,14 +269,20 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
 template <bool COUNT, int ACCEL>
 __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
 {
-    extern __shared__ float4 s_pairs[];
+    extern __shared__ float4 s_box[];                    // [3 * n_smem_pairs] boxes, then [n_smem_pairs] int2 child refs
     const DevScene& sc = A.sc;
-    for (int i = threadIdx.x; i < sc.n_smem_pairs * 4; i += blockDim.x) s_pairs[i] = __ldg(sc.pairs + i);
+    int2* s_ref = reinterpret_cast<int2*>(s_box + 3 * sc.n_smem_pairs);
+    for (int i = threadIdx.x; i < sc.n_smem_pairs * 4; i += blockDim.x) {
+        const float4 v = __ldg(sc.pairs + i);
+        const int node = i >> 2, k = i & 3;
+        if (k < 3) s_box[3 * node + k] = v;
+        else s_ref[node] = make_int2(__float_as_int(v.x), __float_as_int(v.y));
+    }
     __syncthreads();
 
     WorkCount wc; wc.box = 0; wc.tri = 0;
-    trace_queue<true, COUNT, ACCEL>(A, s_pairs, wc);      // shadow rays: any hit
-    trace_queue<false, COUNT, ACCEL>(A, s_pairs, wc);     // extension rays: closest hit
+    trace_queue<true, COUNT, ACCEL>(A, s_box, s_ref, wc);      // shadow rays: any hit
+    trace_queue<false, COUNT, ACCEL>(A, s_box, s_ref, wc);     // extension rays: closest hit
     if (COUNT) {
         const int lane = threadIdx.x & 31;
         unsigned long long b = wc.box, t = wc.tri;

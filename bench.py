@@ -288,7 +288,7 @@ def run_ours(args):
         "data": "synthetic (reference scene buffers from tests/golden, default camera, counter-based RNG seed 12345)",
         "config": {"workload": WORKLOAD, "spp_per_rank": SPP, "sample_range_of_rank_r": "[r*1024, (r+1)*1024)",
                    "pool_slots": int(m.getOption("pool_slots")),
-                   "l2": "per-step working set (path pool + queues ~340 MB, 16.8 MB accumulation) exceeds the 126 MB L2; "
+                   "l2": "per-step working set (path pool + queues ~1.4 GB at 4M slots, 16.8 MB accumulation) exceeds the 126 MB L2; "
                          "the 0.9 MB scene is cache-resident by nature of the workload"},
         "mrays_per_s": rays * world / (dev_ms * 1e-3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays / (WIDTH * HEIGHT * SPP * args.steps),

@@ -76,7 +76,7 @@ struct yune_ctx {
     int cap_iteration = -1, cap_max = 0; int cap_counts[4] = {0, 0, 0, 0};
 
     // options
-    int opt_pool_slots = 1 << 21, opt_smem_nodes = 2048, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_pool_slots = 1 << 22, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
     int opt_leaf_split = 2, opt_fused_shade = 1, opt_accel = 1;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;

@@ -93,8 +93,8 @@ struct OwnTri { float lo[3], hi[3], c[3]; int tri, rank, leaf; };
 struct OwnNode { float lo[3], hi[3]; int left, right, first, count; };   // left < 0: leaf [first, first + count)
 
 struct OwnBuilder {
-    std::vector<OwnTri>& t; std::vector<OwnNode> nodes; int depth_max = 0;
-    explicit OwnBuilder(std::vector<OwnTri>& tt) : t(tt) {}
+    std::vector<OwnTri>& t; std::vector<OwnNode> nodes; int depth_max = 0, leaf_max = 2;
+    OwnBuilder(std::vector<OwnTri>& tt, int lm) : t(tt), leaf_max(lm) {}
     static float area(const float* lo, const float* hi) { float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx * dy + dx * dz + dy * dz; }
     int build(int b, int e, int depth)
     {
@@ -107,7 +107,7 @@ struct OwnBuilder {
             clo[k] = std::min(clo[k], t[i].c[k]); chi[k] = std::max(chi[k], t[i].c[k]);
         }
         const int me = (int)nodes.size(); nodes.push_back(nd);
-        if (e - b <= 2) return me;
+        if (e - b <= leaf_max) return me;
         int axis = 0; for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
         int mid = (b + e) / 2;
         const float ext = chi[axis] - clo[axis];
@@ -165,7 +165,7 @@ static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n
     return true;
 }
 
-static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes, TravLayoutHost& out, std::string& err)
+static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes, TravLayoutHost& out, std::string& err, int leaf_max)
 {
     if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
     // reference leaves: id, box, visiting rank of every triangle slot
@@ -197,7 +197,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     }
     out.n_leaf_tris = (int)t.size();
     if (t.empty()) { out.root_ref = YUNE_REF_EMPTY; out.n_inner = out.n_inner_ref = 0; out.max_depth = 0; return true; }
-    OwnBuilder B(t);
+    OwnBuilder B(t, leaf_max < 1 ? 2 : (leaf_max > 8 ? 8 : leaf_max));
     const int root = B.build(0, (int)t.size(), 0);
     if (B.depth_max + 2 > YUNE_STACK_SIZE) { err = "BVH deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
     out.max_depth = B.depth_max;
@@ -249,7 +249,7 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
 
     if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
     if (accel == 1) {
-        if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err)) return false;
+        if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err, leaf_split)) return false;
         goto shade_records;
     }
     {

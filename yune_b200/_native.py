@@ -77,10 +77,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("YUNE_B200_LIB", LIB_PATH)        # development: A/B a differently-compiled build of the SAME sources
+    if not os.path.exists(path):
         raise RuntimeError("%s is missing: run `python -m yune_b200.build` (nvcc, sm_100a). "
-                           "There is no CPU implementation of the render path." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                           "There is no CPU implementation of the render path." % path)
+    lib = C.CDLL(path)
     for table in (CUDA_API, HOST_API):
         for name, (res, args) in table.items():
             fn = getattr(lib, name)

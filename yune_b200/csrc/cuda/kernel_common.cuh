@@ -109,8 +109,12 @@ struct NeeOut {
 
 // BDPT = the variants bdpt.cl uses inside the same function: un-flipped reflection (bdpt.cl:723, 814), padded lobe
 // probabilities (bdpt.cl:1089-1104).
+//
+// `act` = the lanes of the warp that call this together.  ptxas threads jumps through the early-outs of this function and
+// lets the two sides of an earlier branch run the REST of the code as separate groups (ncu: every SASS line executed twice
+// per warp at half the lanes); the __syncwarp()s on explicit masks pin the reconvergence points.
 template <bool MIS, bool BDPT>
-__device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights, const MatDev& mat, V3 hp, V3 n, V3 w_o,
+__device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* lights, int n_lights, const MatDev& mat, V3 hp, V3 n, V3 w_o,
                                            U4 u_nee, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t vertex, bool use_on, NeeOut& R)
 {
     R.S.has = R.MV.has = R.MO.has = false; R.mo_is_mv = false;
@@ -124,7 +128,9 @@ __device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights,
     }
     float light_pdf = 0.0f; V3 w_i = v3(0, 0, 0);
     const int j = sample_lights(lights, n_lights, hp, n, u_l, u_pick, light_pdf, w_i);
-    if (j == -1 || light_pdf <= 0.0f) return;
+    const bool lit = !(j == -1 || light_pdf <= 0.0f);
+    const unsigned m_lit = __ballot_sync(act, lit);
+    if (!lit) return;
     float len = vlength(w_i);
     len = YF_SUB(len, YF_MUL(YUNE_EPS, 1.5f));
     w_i = vnormalize(w_i);
@@ -141,6 +147,7 @@ __device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights,
         R.Lv = vscale(R.Lv, YF_DIV(1.0f, light_pdf));
     }
     if (!MIS) return;
+    __syncwarp(m_lit);
     const float r1 = u01(u_nee.z), r2 = u01(u_nee.w);
     float pdfV = 0.0f, pdfO = 0.0f;
     V3 dv = v3(0, 0, 1), dq;
@@ -162,6 +169,7 @@ __device__ __forceinline__ void nee_sample(const LightDev* lights, int n_lights,
     // (inf, inf, inf, inf) * light ke (.., .., .., 0): the W LANE is inf*0 = NaN, the kernel's any(isnan(color)) fires (:193)
     // and the WHOLE SAMPLE becomes PINK.  We carry that outcome as a NaN contribution (finalisation turns a NaN sample into
     // PINK), not as the infinities of the xyz lanes.
+    __syncwarp(m_lit);
     const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
     if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
     if (pdfO > 0.0f) {

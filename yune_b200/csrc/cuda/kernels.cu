@@ -304,6 +304,13 @@ __global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
     ctr[parity ^ 1] = z;
 }
 
+__device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
+{
+    if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (udpt.cl:193-194)
+    float* dst = reinterpret_cast<float*>(A.sum + pixel);
+    atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // shade kernel (unidirectional path tracing, with or without MIS)
 // ------------------------------------------------------------------------------------------------------------
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
                 if (!mat.is_specular) {
                     col = vadd(col, vmul(T, mat.ke));                           // the 'emission' term of every return path
                     NeeOut N;
-                    nee_sample<MIS, false>(lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
+                    nee_sample<MIS, false>(__activemask(), lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
                     S = N.S; MV = N.MV; MO = N.MO; mo_is_mv = N.mo_is_mv; Lv = N.Lv; BV = N.BV; BO = N.BO;
                     nee_pending = S.has || MV.has || MO.has;
                 }
@@ -520,6 +527,321 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Shade stage with IN-BLOCK SORTING (default).  ncu on the kernel above: 14.8 of 32 threads active per instruction, because
+// the lanes of a warp are in different situations (diffuse surface 53 %, specular surface 19 %, miss / drain / free 28 %)
+// and take turns through ~10 K SASS instructions.  Here a persistent block walks chunks of YUNE_SHADE_BLOCK slots:
+//   A  classify   every lane, cheap: settle last iteration's NEE answers, retire misses and drained paths into the
+//                 accumulation buffer, and append the slot to one of three shared-memory lists
+//   D  diffuse    runs only when the list holds a full block of diffuse surface hits: NEE (+ MIS rays), lobe sampling,
+//                 roulette -- every lane of every warp on the same code
+//   S  specular   likewise for mirror / glass hits (no NEE)
+//   R  regenerate likewise for slots that need the next (pixel, sample): camera ray in fp64
+// Leftovers stay in the lists for the next chunk; the last pass flushes them.  Per-slot results are the same as the
+// fused kernel's (same arithmetic, same random-number addressing); only the order of queue entries differs.
+// ------------------------------------------------------------------------------------------------------------
+#define YUNE_NW (YUNE_SHADE_BLOCK / 32)
+enum { YL_DIFFUSE = 0, YL_SPECULAR = 1 };
+
+__device__ __forceinline__ void list_push(int* list, int* count, bool want, int value)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+struct DenseShared {
+    int surf[2][2 * YUNE_SHADE_BLOCK];      // diffuse / specular surface hits waiting for a full round
+    int regen[4 * YUNE_SHADE_BLOCK];        // slots waiting for a fresh sample (fed by A, D and S)
+    int n_surf[2], n_regen;
+    int cnt[3 * (YUNE_NW + 1)];             // block_alloc scratch
+    unsigned long long sample_base; int ext_base;
+};
+
+// phase A for one slot
+__device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
+{
+    const PathPool& P = A.pool;
+    const bool valid = s < P.n_slots;
+    const uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
+    const unsigned state = meta.w & YS_STATE_MASK;
+    bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
+    if (state == YS_TRACE || state == YS_DRAIN) {
+        const int tri = state == YS_TRACE ? __float_as_int(P.hit[s].w) : -1;
+        const bool pend = (meta.w & (YF_PEND_EVT | YF_PEND_L)) != 0;
+        if (pend || tri < 0) {
+            V3 col = xyz(P.col[s]);
+            bool dirty = false;
+            // resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
+            if (meta.w & YF_PEND_EVT) {
+                const V3 T = xyz(P.thr[s]);
+                const int e = P.evt_idx[s];
+                const float4 e0 = P.evt[3 * (size_t)e], e1 = P.evt[3 * (size_t)e + 1], e2 = P.evt[3 * (size_t)e + 2];
+                const int ef = __float_as_int(e0.w);
+                const bool visS = (ef & YE_HAS_S) && P.evt_vis[4 * (size_t)e + 0];
+                const bool visMV = (ef & YE_HAS_MV) && P.evt_vis[4 * (size_t)e + 1];
+                const bool visMO = (ef & YE_MO_IS_MV) ? visMV : ((ef & YE_HAS_MO) && P.evt_vis[4 * (size_t)e + 2]);
+                V3 nee;
+                if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
+                else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
+                col = vadd(col, vmul(T, nee)); dirty = true;
+            } else if ((meta.w & YF_PEND_L) && P.vis_l[s]) { col = vadd(col, vmul(xyz(P.thr[s]), xyz(P.pend_l[s]))); dirty = true; }
+            if (tri < 0) {
+                if (state == YS_TRACE) {                                            // nothing hit, or a light
+                    const float4 rd = P.ray_d[s];
+                    const int lid = __float_as_int(rd.w);
+                    if (meta.z == 0) {                                              // udpt.cl:437-446
+                        if (lid >= 0) col = (vdot(xyz(rd), A.lights.l[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
+                        else col = v3(0.4f, 0.4f, 0.4f);
+                    } else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(P.thr[s]), A.lights.l[lid].ke));   // :490-493
+                }
+                finish_sample(A, meta.x, col);                                      // udpt.cl:193-210
+                to_regen = true;
+            } else if (dirty) P.col[s] = f4(col, 0.0f);
+        }
+        if (tri >= 0) {
+            const int mat_id = __float_as_int(__ldg(A.sc.shade + 4 * (size_t)tri).w);
+            to_s = __float_as_int(__ldg(A.sc.mats + 5 * (size_t)mat_id + 4).z) != 0;
+            to_d = !to_s;
+        }
+    }
+    list_push(sh.surf[YL_DIFFUSE], &sh.n_surf[YL_DIFFUSE], to_d, s);
+    list_push(sh.surf[YL_SPECULAR], &sh.n_surf[YL_SPECULAR], to_s, s);
+    list_push(sh.regen, &sh.n_regen, to_regen, s);
+}
+
+// phases D / S for one list entry per thread (s < 0: idle lane of a flush round); every thread of the block calls it
+template <bool MIS, bool SPEC>
+__device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, DenseShared& sh, int& live)
+{
+    const PathPool& P = A.pool;
+    IterCounters* C = A.ctr + A.parity;
+    const LightDev* lights = A.lights.l;
+    const int n_lights = A.lights.n;
+    bool has_ext = false, finished = false;
+    V3 ext_o = v3(0, 0, 0), ext_d = v3(0, 0, 1); float ext_t = INFINITY; int ext_lid = -1;
+    NeeOut N; N.S.has = N.MV.has = N.MO.has = false; N.mo_is_mv = false; N.Lv = N.BV = N.BO = v3(0, 0, 0);
+    uint4 meta = make_uint4(0, 0, 0, 0);
+    V3 col = v3(0, 0, 0), T = v3(1, 1, 1), Tn = v3(1, 1, 1);
+    unsigned new_flags = 0;
+    const unsigned act = __ballot_sync(0xffffffffu, s >= 0);
+
+    if (s >= 0) {
+        meta = P.meta[s];
+        const float4 hit = P.hit[s], ro = P.ray_o[s], rd = P.ray_d[s];
+        col = xyz(P.col[s]); T = xyz(P.thr[s]);
+        const int tri = __float_as_int(hit.w);
+        const V3 o = xyz(ro), d = xyz(rd);
+        const unsigned vtx = meta.z;
+        bool terminate = false;
+        // ---- the surface point (udpt.cl:375-385)
+        const float4 s0 = __ldg(A.sc.shade + 4 * (size_t)tri), s1 = __ldg(A.sc.shade + 4 * (size_t)tri + 1), s2 = __ldg(A.sc.shade + 4 * (size_t)tri + 2);
+        const MatDev mat = load_material(A.sc.mats, __float_as_int(s0.w));
+        const float bw = YF_SUB(YF_SUB(1.0f, hit.y), hit.z);
+        const V3 hp = vadd(o, vscale(d, hit.x));
+        const V3 n = vnormalize(vmadd3(xyz(s0), bw, xyz(s1), hit.y, xyz(s2), hit.z));
+        const V3 w_o = vneg(d);
+        U4 u_nee; u_nee.x = u_nee.y = u_nee.z = u_nee.w = 0u;
+        if (!SPEC || (vtx > 0 && (int)vtx - 1 > A.rr_threshold)) u_nee = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_NEE);
+        if (vtx > 0) {                                                          // arrival of bounce i = vtx - 1
+            Tn = xyz(P.thr_next[s]);
+            col = vadd(col, vmul(T, mat.ke));                                   // :498
+            T = Tn;                                                             // :504-507 (product was formed at sampling time)
+            if ((int)vtx - 1 > A.rr_threshold) {                                // :514-523
+                const float p = cl_min(luminance(T), 0.95f);
+                const float r = u01(u_nee.x);
+                if (r >= p) terminate = true;
+                else T = vscale(T, YF_DIV(1.0f, p));
+            }
+        }
+        bool nee_pending = false;
+        __syncwarp(act);                                                        // see nee_sample: keep the warp together
+        const unsigned alive = __ballot_sync(act, !terminate);
+        if (!terminate) {
+            // ---- next-event estimation at this vertex (evaluateDirectLighting, :535-609)
+            if (!SPEC) {
+                col = vadd(col, vmul(T, mat.ke));                               // the 'emission' term of every return path
+                nee_sample<MIS, false>(alive, lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
+                nee_pending = N.S.has || N.MV.has || N.MO.has;
+            }
+            __syncwarp(alive);
+            // ---- continue the path (udpt.cl:463-530)
+            if (!A.gi_check) terminate = true;
+            else {
+                const U4 u_b = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_BOUNCE);
+                V3 dir = v3(0, 0, 1);
+                if (SPEC) {
+                    float ior = 1.0f;
+                    dir = sample_specular(mat, w_o, n, u01(u_b.w), ior);
+                    Tn = vscale(T, ior);
+                } else {
+                    float prob = 0.0f, pdf = 1.0f;
+                    const bool glossy = select_lobe(mat, u01(u_b.x), false, prob);
+                    if (prob == 0.0f) terminate = true;                         // absorbed (:475-476)
+                    else {
+                        dir = glossy ? sample_phong(w_o, n, mat.px, mat.py, u01(u_b.y), u01(u_b.z), true, pdf)
+                                     : sample_cosine(n, u01(u_b.y), u01(u_b.z), pdf);
+                        if (pdf <= 0.0f) terminate = true;                      // :488
+                        else Tn = vdivs(vscale(vmul(T, eval_brdf(mat, dir, w_o, n, glossy, prob, true, A.oren_nayar != 0)), fmaxf(vdot(dir, n), 0.0f)), pdf);
+                    }
+                }
+                if (!terminate) {
+                    has_ext = true;
+                    ext_d = dir; ext_o = vadd(hp, vscale(dir, YUNE_EPS)); ext_t = INFINITY;
+                    ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
+                    new_flags = YS_TRACE | (SPEC ? YF_PREV_SPEC : 0u);
+                    meta.z = vtx + 1;
+                }
+            }
+        }
+        __syncwarp(act);
+        if (!has_ext) {
+            if (nee_pending) new_flags = YS_DRAIN;
+            else { finished = true; new_flags = YS_FREE; finish_sample(A, meta.x, col); }
+        }
+    }
+    list_push(sh.regen, &sh.n_regen, finished, s);
+    if (s >= 0 && !finished) live++;
+
+    // ---- queue pushes (block-wide compaction: one atomic per counter per round) and state write-back
+    if (SPEC) {
+        int* const counters[1] = { &C->n_extend };
+        const int cnt[1] = { has_ext ? 1 : 0 };
+        int first[1];
+        block_alloc<1, YUNE_NW>(counters, cnt, first, sh.cnt);
+        if (has_ext) P.eq[first[0]] = s;
+    } else {
+        const bool is_event = N.MV.has || N.MO.has;
+        int* const counters[3] = { &C->n_extend, &C->n_shadow, &C->n_events };
+        const int cnt[3] = { has_ext ? 1 : 0, (N.S.has ? 1 : 0) + (N.MV.has ? 1 : 0) + (N.MO.has ? 1 : 0), is_event ? 1 : 0 };
+        int first[3];
+        block_alloc<3, YUNE_NW>(counters, cnt, first, sh.cnt);
+        if (has_ext) P.eq[first[0]] = s;
+        const int ev = A.parity * P.n_slots + first[2];
+        if (is_event) {
+            const int ef = (N.S.has ? YE_HAS_S : 0) | (N.MV.has ? YE_HAS_MV : 0) | (N.MO.has ? YE_HAS_MO : 0) | (N.mo_is_mv ? YE_MO_IS_MV : 0);
+            P.evt[3 * (size_t)ev] = f4(N.Lv, __int_as_float(ef));
+            P.evt[3 * (size_t)ev + 1] = f4(N.BV, 0.0f);
+            P.evt[3 * (size_t)ev + 2] = f4(N.BO, 0.0f);
+            P.evt_idx[s] = ev;
+            new_flags |= YF_PEND_EVT;
+        } else if (N.S.has) new_flags |= YF_PEND_L;
+        int qs = first[1];
+        if (N.S.has) {
+            P.sq_o[qs] = f4(N.S.o, N.S.tmax);
+            P.sq_d[qs] = f4(N.S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
+            if (!is_event) P.pend_l[s] = f4(N.Lv, 0.0f);
+            qs++;
+        }
+        if (MIS) {
+            if (N.MV.has) { P.sq_o[qs] = f4(N.MV.o, N.MV.tmax); P.sq_d[qs] = f4(N.MV.d, __int_as_float(~(4 * ev + 1))); qs++; }
+            if (N.MO.has) { P.sq_o[qs] = f4(N.MO.o, N.MO.tmax); P.sq_d[qs] = f4(N.MO.d, __int_as_float(~(4 * ev + 2))); qs++; }
+        }
+    }
+    if (s >= 0 && !finished) {
+        meta.w = new_flags;
+        P.meta[s] = meta;
+        P.col[s] = f4(col, 0.0f);
+        P.thr[s] = f4(T, 0.0f);
+        if (has_ext) {
+            P.ray_o[s] = f4(ext_o, ext_t);
+            P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
+            P.thr_next[s] = f4(Tn, 0.0f);
+        }
+    }
+}
+
+// phase R: `take` list entries [from, from + take), thread t serves entry from + t
+__device__ __forceinline__ void regen_round(const RenderArgs& A, const int from, const int take, DenseShared& sh, int& live)
+{
+    const PathPool& P = A.pool;
+    IterCounters* C = A.ctr + A.parity;
+    if (threadIdx.x == 0) {
+        const unsigned long long base = atomicAdd(&A.tot->next_sample, (unsigned long long)take);     // next (pixel, sample) in global order
+        const unsigned long long total = A.tot->n_samples;
+        const int n_fresh = base >= total ? 0 : (int)((total - base) < (unsigned long long)take ? (total - base) : (unsigned long long)take);
+        sh.sample_base = base;
+        sh.ext_base = n_fresh > 0 ? atomicAdd(&C->n_extend, n_fresh) : 0;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < take) {
+        const int s = sh.regen[from + threadIdx.x];
+        const unsigned long long g = sh.sample_base + threadIdx.x;
+        if (g < A.tot->n_samples) {
+            // udpt.cl:164-189
+            const unsigned long long n_pix = (unsigned long long)A.width * A.height;
+            const unsigned pixel = (unsigned)(g % n_pix);
+            const unsigned sample = (unsigned)(A.spp_begin + (int)(g / n_pix));
+            const int px = pixel % A.width, py = pixel / A.width;
+            const U4 uj = draw4(A.seed, pixel, sample, YUNE_VERTEX_CAMERA, 0u);
+            V3 ro, rd;
+            create_ray(A.cam, A.width, A.height, (float)px + u01(uj.x), (float)py + u01(uj.y), ro, rd);
+            float rt = INFINITY;
+            const int rl = light_loop(A.lights.l, A.lights.n, ro, rd, rt);
+            P.eq[sh.ext_base + threadIdx.x] = s;
+            P.ray_o[s] = f4(ro, rt);
+            P.ray_d[s] = f4(rd, __int_as_float(rl));
+            P.meta[s] = make_uint4(pixel, sample, 0u, YS_TRACE);
+            P.col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            P.thr[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            live++;
+        } else P.meta[s] = make_uint4(0u, 0u, 0u, YS_DONE);
+    }
+    __syncthreads();
+}
+
+template <bool MIS>
+__global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_shade_dense(RenderArgs A)
+{
+    __shared__ DenseShared sh;
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh.n_surf[0] = sh.n_surf[1] = 0; sh.n_regen = 0; }
+    __syncthreads();
+    const int n_chunks = (A.pool.n_slots + YUNE_SHADE_BLOCK - 1) / YUNE_SHADE_BLOCK;
+    int live = 0;                                   // slots this thread left in flight (TRACE or DRAIN)
+    for (int chunk = blockIdx.x; ; chunk += gridDim.x) {
+        const bool flush = chunk >= n_chunks;       // block-uniform: the pass after the last chunk empties the lists
+        if (!flush) classify_slot(A, chunk * YUNE_SHADE_BLOCK + tid, sh);
+        __syncthreads();
+        YUNE_NO_UNROLL
+        for (int k = 0; k < 2; k++) {
+            const int n = sh.n_surf[k];
+            if (n >= YUNE_SHADE_BLOCK || (flush && n > 0)) {
+                const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
+                const int s = tid < take ? sh.surf[k][n - take + tid] : -1;
+                __syncthreads();
+                if (tid == 0) sh.n_surf[k] = n - take;
+                if (k == YL_DIFFUSE) surface_round<MIS, false>(A, s, sh, live);
+                else                 surface_round<MIS, true>(A, s, sh, live);
+                __syncthreads();
+            }
+        }
+        for (;;) {
+            const int n = sh.n_regen;
+            if (!(n >= YUNE_SHADE_BLOCK || (flush && n > 0))) break;
+            const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
+            __syncthreads();
+            if (tid == 0) sh.n_regen = n - take;
+            regen_round(A, n - take, take, sh, live);
+        }
+        if (flush) break;
+    }
+    // one atomic per block: how many slots are still in flight
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+    if ((tid & 31) == 0) sh.cnt[tid >> 5] = live;
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int w = 0; w < YUNE_NW; w++) total += sh.cnt[w];
+        if (total > 0) atomicAdd(&A.ctr[A.parity].live, total);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // The same stage split into three kernels with typed queues (default; the fused kernel above stays selectable with
 // option "fused_shade" for A/B measurements).  ncu on the fused kernel showed 11.9 of 32 threads active per instruction
 // and 112 registers: lanes that regenerate (fp64 camera ray), lanes that miss, and lanes on a surface took turns.
@@ -528,12 +850,6 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
 //   k_surface  SURFACE queue: every lane has a surface hit -> material evaluation, NEE + MIS rays, next direction, roulette
 //   k_regen    REGENERATION queue: next (pixel, sample) + camera ray, every lane active
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
-{
-    if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (udpt.cl:193-194)
-    float* dst = reinterpret_cast<float*>(A.sum + pixel);
-    atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
-}
 
 __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_logic(RenderArgs A)
 {
@@ -637,7 +953,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_surface(RenderArgs A)
             // ---- next-event estimation at this vertex (evaluateDirectLighting, :535-609)
             if (!mat.is_specular) {
                 col = vadd(col, vmul(T, mat.ke));                               // the 'emission' term of every return path
-                nee_sample<MIS, false>(lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
+                nee_sample<MIS, false>(__activemask(), lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
                 nee_pending = N.S.has || N.MV.has || N.MO.has;
             }
             // ---- continue the path (udpt.cl:463-530)
@@ -896,6 +1212,24 @@ cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st)
     const int grid = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
     if (a.mis) k_shade_udpt<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
     else       k_shade_udpt<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st)
+{
+    static int occ[2] = { 0, 0 };                   // resident blocks per SM of the two instantiations (asked once)
+    const int v = a.mis ? 1 : 0;
+    if (occ[v] == 0) {
+        cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_dense<true>, YUNE_SHADE_BLOCK, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_dense<false>, YUNE_SHADE_BLOCK, 0);
+        if (e != cudaSuccess) return e;
+        if (occ[v] < 1) occ[v] = 1;
+    }
+    int grid = sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ[v]);
+    const int n_chunks = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
+    if (grid > n_chunks) grid = n_chunks;
+    if (grid < 1) grid = 1;
+    if (a.mis) k_shade_dense<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
+    else       k_shade_dense<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_shade_split(const RenderArgs& a, cudaStream_t st)

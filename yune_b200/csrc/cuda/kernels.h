@@ -5,7 +5,9 @@
 #include "wavefront_types.h"
 
 #define YUNE_TRACE_MAX_BLOCK  1024     /* k_trace is compiled for <= 64 registers so any block size up to this fits */
+#ifndef YUNE_SHADE_BLOCK
 #define YUNE_SHADE_BLOCK      256
+#endif
 #ifndef YUNE_SHADE_MIN_BLOCKS
 #define YUNE_SHADE_MIN_BLOCKS 3
 #endif
@@ -32,6 +34,7 @@ cudaError_t trace_set_smem(size_t smem_bytes);
 int         trace_blocks_per_sm(int block, size_t smem_bytes);
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
 cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st);      // fused logic+material+regen kernel
+cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st);   // persistent, in-block sorted (default)
 cudaError_t launch_shade_split(const RenderArgs& a, cudaStream_t st);     // k_logic + k_surface + k_regen
 cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, cudaStream_t st);
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);

@@ -54,6 +54,8 @@ struct yune_ctx {
     bool layout_dirty = true, have_tris = false, have_nodes = false, have_mats = false, have_cam = false;
     TravLayoutHost lay;
     float4 *d_pairs = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_mats = nullptr, *d_leaf_boxes = nullptr;
+    unsigned char* d_tri_class = nullptr;      // per original triangle: 1 = its material is specular (shade-stage sorting key)
+    bool class_dirty = true;
     DevScene sc{};
     yune_cam cam{};
 
@@ -137,12 +139,22 @@ static int ensure_scene(yune_ctx* c)
 {
     if (!c->have_tris || !c->have_nodes || !c->have_mats)
         Y_FAIL(c, YUNE_ERR_STATE, "scene incomplete: vertex, material and BVH buffers must all be set up before rendering");
+    if (c->class_dirty || c->layout_dirty) {
+        for (const yune_triangle& t : c->h_tris)
+            if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
+        std::vector<unsigned char> cls(std::max<size_t>(c->h_tris.size(), 1), 0);
+        for (size_t i = 0; i < c->h_tris.size(); i++) cls[i] = c->h_mats[c->h_tris[i].matID].is_specular != 0 ? 1 : 0;
+        dfree(c->d_tri_class);
+        Y_CUDA(c, cudaMalloc(&c->d_tri_class, cls.size()));
+        Y_CUDA(c, cudaMemcpyAsync(c->d_tri_class, cls.data(), cls.size(), cudaMemcpyHostToDevice, c->stream));
+        Y_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->sc.tri_class = c->d_tri_class;
+        c->class_dirty = false;
+    }
     if (!c->layout_dirty) return YUNE_OK;
     std::string err;
     if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
-    for (const yune_triangle& t : c->h_tris)
-        if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
     const TravLayoutHost& L = c->lay;
     Y_CUDA(c, cudaMalloc(&c->d_leaf_boxes, std::max<size_t>(L.leaf_boxes.size(), 2) * 16));
@@ -231,7 +243,7 @@ void yune_destroy(yune_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_pool(c);
-    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes);
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
     dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_ctr); dfree(c->d_tot);
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
     dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
@@ -294,7 +306,7 @@ int yune_setup_mat_buffer(yune_ctx* c, const yune_material* mats, int n)
     Y_CUDA(c, cudaMemcpyAsync(c->d_mats, mats, (size_t)n * 80, cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
     c->sc.mats = c->d_mats; c->sc.n_mats = n;
-    c->have_mats = true;
+    c->have_mats = true; c->class_dirty = true;
     return YUNE_OK;
 }
 

@@ -567,10 +567,12 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
     const PathPool& P = A.pool;
     const bool valid = s < P.n_slots;
     const uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
+    const float hit_w = valid ? P.hit[s].w : 0.0f;                             // unconditional: in flight together with meta
     const unsigned state = meta.w & YS_STATE_MASK;
     bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
     if (state == YS_TRACE || state == YS_DRAIN) {
-        const int tri = state == YS_TRACE ? __float_as_int(P.hit[s].w) : -1;
+        const int tri = state == YS_TRACE ? __float_as_int(hit_w) : -1;
+        if (tri >= 0) { to_s = A.sc.tri_class[tri] != 0; to_d = !to_s; }
         const bool pend = (meta.w & (YF_PEND_EVT | YF_PEND_L)) != 0;
         if (pend || tri < 0) {
             V3 col = xyz(P.col[s]);
@@ -601,11 +603,6 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
                 finish_sample(A, meta.x, col);                                      // udpt.cl:193-210
                 to_regen = true;
             } else if (dirty) P.col[s] = f4(col, 0.0f);
-        }
-        if (tri >= 0) {
-            const int mat_id = __float_as_int(__ldg(A.sc.shade + 4 * (size_t)tri).w);
-            to_s = __float_as_int(__ldg(A.sc.mats + 5 * (size_t)mat_id + 4).z) != 0;
-            to_d = !to_s;
         }
     }
     list_push(sh.surf[YL_DIFFUSE], &sh.n_surf[YL_DIFFUSE], to_d, s);
@@ -828,6 +825,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
             regen_round(A, n - take, take, sh, live);
         }
         if (flush) break;
+        __syncthreads();                            // every warp has read the list counts before the next chunk's classify bumps them
     }
     // one atomic per block: how many slots are still in flight
     #pragma unroll

@@ -14,6 +14,7 @@ struct DevScene {
     const float4* tris;      // 3 x float4 per leaf-ordered triangle
     const float4* shade;     // 4 x float4 per original triangle (normalised normals, matID)
     const float4* mats;      // 5 x float4 per material (the 80-byte reference record, untouched)
+    const unsigned char* tri_class; // 1 byte per original triangle: 1 = specular material
     const float4* leaf_boxes;// accel 1: 2 x float4 per REFERENCE leaf (its uploaded box), indexed by triangle record t2.w
     int   accel;             // 0 = walk the reference tree, 1 = walk our own tree + exact leaf-box filter (trav_layout.h)
     int   n_inner, n_tris, n_mats, root_ref;

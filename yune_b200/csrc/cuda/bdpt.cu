@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_shade_bdpt(RenderArgs A, B
         pend_c[0] = f4(e_mat.ke, 0.0f);
         bm.w = __float_as_int(ks);
         const U4 u_nee = draw4(A.seed, meta.x, meta.y, 0x20000000u + e_vtx, YUNE_BLK_NEE);
-        nee_sample<MIS, true>(__activemask(), lights, n_lights, e_mat, e_hp, e_n, e_wo, u_nee, A.seed, meta.x, meta.y, 0x20000000u + e_vtx, use_on, N);
+        const LobePrep e_lobes = lobe_prepare(e_mat, true);
+        V3 e_nx, e_ny; onb(e_n, e_nx, e_ny);
+        nee_sample<MIS, true>(__activemask(), lights, n_lights, e_mat, e_lobes, e_hp, e_n, e_nx, e_ny, e_wo, u_nee, A.seed, meta.x, meta.y, 0x20000000u + e_vtx, use_on, N);
     }
     {
         const int j_top = __reduce_max_sync(0xffffffffu, shade_eye ? bm.x : 0);

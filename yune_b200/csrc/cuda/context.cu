@@ -80,7 +80,7 @@ struct yune_ctx {
     // options
     int opt_pool_slots = 1 << 22, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
-    int opt_leaf_split = 2, opt_fused_shade = 1, opt_accel = 1, opt_shade_blocks_per_sm = 0;
+    int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
     yune_stats stats{};
@@ -365,7 +365,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split}, {"fused_shade", &c->opt_fused_shade}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -448,9 +448,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
             if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->stream));
-            else if (c->opt_fused_shade == 1) Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->stream));
-            else if (c->opt_fused_shade == 2) Y_CUDA(c, launch_shade_udpt(a, c->stream));
-            else { Y_CUDA(c, launch_shade_split(a, c->stream)); st.kernel_launches += 2; }
+            else Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->stream));
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));

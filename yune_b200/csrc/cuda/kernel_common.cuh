@@ -114,7 +114,8 @@ struct NeeOut {
 // lets the two sides of an earlier branch run the REST of the code as separate groups (ncu: every SASS line executed twice
 // per warp at half the lanes); the __syncwarp()s on explicit masks pin the reconvergence points.
 template <bool MIS, bool BDPT>
-__device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* lights, int n_lights, const MatDev& mat, V3 hp, V3 n, V3 w_o,
+__device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* lights, int n_lights, const MatDev& mat, const LobePrep& lobes,
+                                           V3 hp, V3 n, V3 Nx, V3 Ny, V3 w_o,
                                            U4 u_nee, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t vertex, bool use_on, NeeOut& R)
 {
     R.S.has = R.MV.has = R.MO.has = false; R.mo_is_mv = false;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* l
     R.S.has = !(light_loop(lights, n_lights, R.S.o, R.S.d, tl) >= 0);        // traceRay's light loop (:244-276) can already block it
     // branch "light sample visible": lobe selection happens only then (:559-561)
     float prob = 0.0f;
-    const bool glossy = select_lobe(mat, u01(u_nee.y), BDPT, prob);
+    const bool glossy = select_lobe_r(lobes, u01(u_nee.y), BDPT, prob);
     const bool v_alive = prob != 0.0f;
     const V3 Lke = lights[j].ke;
     if (v_alive) {
@@ -154,7 +155,7 @@ __device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* l
     if (v_alive) {
         const float brdf_pdf = glossy ? phong_pdf(mat, w_i, w_o, n) : cos_pdf(w_i, n);
         R.Lv = vscale(R.Lv, power_heuristic(light_pdf, light_pdf, brdf_pdf));                       // :570-577
-        dv = glossy ? sample_phong(w_o, n, mat.px, mat.py, r1, r2, !BDPT, pdfV) : sample_cosine(n, r1, r2, pdfV);
+        dv = glossy ? sample_phong(w_o, n, mat.px, mat.py, r1, r2, !BDPT, pdfV) : sample_cosine_onb(n, Nx, Ny, r1, r2, pdfV);
         if (pdfV > 0.0f) {                                                                          // :587-588
             R.MV.o = vadd(hp, vscale(dv, YUNE_EPS)); R.MV.d = dv; R.MV.tmax = INFINITY;
             if (light_loop(lights, n_lights, R.MV.o, R.MV.d, R.MV.tmax) == j) {                     // closest light must be j (:594)
@@ -171,7 +172,7 @@ __device__ __forceinline__ void nee_sample(const unsigned act, const LightDev* l
     // PINK), not as the infinities of the xyz lanes.
     __syncwarp(m_lit);
     const bool same_dir = v_alive && !glossy;      // both branches then draw the same cosine direction
-    if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine(n, r1, r2, pdfO);
+    if (same_dir) { dq = dv; pdfO = pdfV; } else dq = sample_cosine_onb(n, Nx, Ny, r1, r2, pdfO);
     if (pdfO > 0.0f) {
         bool reaches = false;
         if (same_dir) { reaches = R.MV.has; R.mo_is_mv = R.MV.has; }

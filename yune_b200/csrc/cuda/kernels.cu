@@ -312,221 +312,6 @@ __device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixe
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// shade kernel (unidirectional path tracing, with or without MIS)
-// ------------------------------------------------------------------------------------------------------------
-template <bool MIS>
-__global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_shade_udpt(RenderArgs A)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = s < A.pool.n_slots;
-    const PathPool& P = A.pool;
-    IterCounters* C = A.ctr + A.parity;
-    const LightDev* lights = A.lights.l;
-    const int n_lights = A.lights.n;
-
-    uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
-    unsigned state = meta.w & YS_STATE_MASK;
-    V3 col = v3(0, 0, 0), T = v3(1, 1, 1), Tn = v3(1, 1, 1);
-    unsigned new_flags = 0;
-    bool has_ext = false; V3 ext_o = v3(0, 0, 0), ext_d = v3(0, 0, 1); float ext_t = INFINITY; int ext_lid = -1;
-    ShadowOut S, MV, MO; S.has = MV.has = MO.has = false;
-    bool mo_is_mv = false;
-    V3 Lv = v3(0, 0, 0), BV = v3(0, 0, 0), BO = v3(0, 0, 0);
-    bool nee_pending = false;       // the NEE of THIS visit left something to resolve next visit
-    bool need_new = false;
-
-    if (state == YS_TRACE || state == YS_DRAIN) {
-        col = xyz(P.col[s]);
-        T = xyz(P.thr[s]);
-        // ---- 1. resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
-        if (meta.w & YF_PEND_EVT) {
-            const int e = P.evt_idx[s];
-            const float4 e0 = P.evt[3 * (size_t)e], e1 = P.evt[3 * (size_t)e + 1], e2 = P.evt[3 * (size_t)e + 2];
-            const int ef = __float_as_int(e0.w);
-            const bool visS = (ef & YE_HAS_S) && P.evt_vis[4 * (size_t)e + 0];
-            const bool visMV = (ef & YE_HAS_MV) && P.evt_vis[4 * (size_t)e + 1];
-            const bool visMO = (ef & YE_MO_IS_MV) ? visMV : ((ef & YE_HAS_MO) && P.evt_vis[4 * (size_t)e + 2]);
-            V3 nee;
-            if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
-            else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
-            col = vadd(col, vmul(T, nee));
-        } else if (meta.w & YF_PEND_L) {
-            if (P.vis_l[s]) col = vadd(col, vmul(T, xyz(P.pend_l[s])));
-        }
-    }
-
-    bool finished = false;          // the sample's radiance is final
-    if (state == YS_DRAIN) finished = true;
-    else if (state == YS_TRACE) {
-        const float4 hit = P.hit[s], ro = P.ray_o[s], rd = P.ray_d[s];
-        const int tri = __float_as_int(hit.w);
-        const V3 o = xyz(ro), d = xyz(rd);
-        const unsigned vtx = meta.z;
-        bool terminate = false;
-        if (tri < 0) {
-            const int lid = __float_as_int(rd.w);
-            if (vtx == 0) {                                                     // udpt.cl:437-446
-                if (lid >= 0) col = (vdot(d, lights[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
-                else col = v3(0.4f, 0.4f, 0.4f);
-            } else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(T, lights[lid].ke));   // :490-493
-            terminate = true;
-        } else {
-            // ---- 2. the surface point (udpt.cl:375-385)
-            const float4 s0 = __ldg(A.sc.shade + 4 * (size_t)tri), s1 = __ldg(A.sc.shade + 4 * (size_t)tri + 1), s2 = __ldg(A.sc.shade + 4 * (size_t)tri + 2);
-            const MatDev mat = load_material(A.sc.mats, __float_as_int(s0.w));
-            const float bw = YF_SUB(YF_SUB(1.0f, hit.y), hit.z);
-            const V3 hp = vadd(o, vscale(d, hit.x));
-            const V3 n = vnormalize(vmadd3(xyz(s0), bw, xyz(s1), hit.y, xyz(s2), hit.z));
-            const V3 w_o = vneg(d);
-            const U4 u_nee = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_NEE);
-
-            if (vtx > 0) {                                                      // arrival of bounce i = vtx - 1
-                Tn = xyz(P.thr_next[s]);
-                col = vadd(col, vmul(T, mat.ke));                               // :498
-                T = Tn;                                                         // :504-507 (product was formed at sampling time)
-                if ((int)vtx - 1 > A.rr_threshold) {                            // :514-523
-                    const float p = cl_min(luminance(T), 0.95f);
-                    const float r = u01(u_nee.x);
-                    if (r >= p) terminate = true;
-                    else T = vscale(T, YF_DIV(1.0f, p));
-                }
-            }
-            if (!terminate) {
-                // ---- 3. next-event estimation at this vertex (evaluateDirectLighting, :535-609)
-                if (!mat.is_specular) {
-                    col = vadd(col, vmul(T, mat.ke));                           // the 'emission' term of every return path
-                    NeeOut N;
-                    nee_sample<MIS, false>(__activemask(), lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
-                    S = N.S; MV = N.MV; MO = N.MO; mo_is_mv = N.mo_is_mv; Lv = N.Lv; BV = N.BV; BO = N.BO;
-                    nee_pending = S.has || MV.has || MO.has;
-                }
-                // ---- 4. continue the path (udpt.cl:463-530)
-                if (!A.gi_check) terminate = true;
-                else {
-                    const U4 u_b = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_BOUNCE);
-                    V3 dir;
-                    if (mat.is_specular) {
-                        float ior = 1.0f;
-                        dir = sample_specular(mat, w_o, n, u01(u_b.w), ior);
-                        Tn = vscale(T, ior);
-                    } else {
-                        float prob = 0.0f, pdf = 1.0f;
-                        const bool glossy = select_lobe(mat, u01(u_b.x), false, prob);
-                        if (prob == 0.0f) terminate = true;                     // absorbed (:475-476)
-                        else {
-                            dir = glossy ? sample_phong(w_o, n, mat.px, mat.py, u01(u_b.y), u01(u_b.z), true, pdf)
-                                         : sample_cosine(n, u01(u_b.y), u01(u_b.z), pdf);
-                            if (pdf <= 0.0f) terminate = true;                  // :488
-                            else Tn = vdivs(vscale(vmul(T, eval_brdf(mat, dir, w_o, n, glossy, prob, true, A.oren_nayar != 0)), fmaxf(vdot(dir, n), 0.0f)), pdf);
-                        }
-                    }
-                    if (!terminate) {
-                        has_ext = true;
-                        ext_d = dir; ext_o = vadd(hp, vscale(dir, YUNE_EPS)); ext_t = INFINITY;
-                        ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
-                        new_flags = YS_TRACE | (mat.is_specular ? YF_PREV_SPEC : 0u);
-                        meta.z = vtx + 1;
-                    }
-                }
-            }
-        }
-        if (terminate && !has_ext) {
-            if (nee_pending) new_flags = YS_DRAIN;
-            else finished = true;
-        }
-    }
-
-    // ---- 5. a finished sample goes to the accumulation buffer (udpt.cl:193-210; sum instead of running mean)
-    if (finished) {
-        if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (:193-194)
-        float* dst = reinterpret_cast<float*>(A.sum + meta.x);
-        atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
-        state = YS_FREE;
-    }
-    need_new = valid && (finished || state == YS_FREE) && !has_ext && new_flags == 0;
-
-    // ---- 6. regenerate: next (pixel, sample) in global order + camera ray (udpt.cl:164-189)
-    __shared__ int s_cnt[4 * (YUNE_SHADE_BLOCK / 32 + 1)];
-    __shared__ unsigned long long s_sample_base;
-    {
-        // one 64-bit atomic per block: block-wide rank of the lanes that need a sample
-        int* const c1[1] = { &s_cnt[3 * (YUNE_SHADE_BLOCK / 32 + 1)] };       // dummy smem counter: only the ranks are used
-        (void)c1;
-        const unsigned m = __ballot_sync(0xffffffffu, need_new);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) s_cnt[warp] = __popc(m);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int total = 0;
-            for (int w = 0; w < YUNE_SHADE_BLOCK / 32; w++) { const int v = s_cnt[w]; s_cnt[w] = total; total += v; }
-            s_sample_base = total > 0 ? atomicAdd(&A.tot->next_sample, (unsigned long long)total) : 0ull;
-        }
-        __syncthreads();
-        const unsigned long long g = s_sample_base + (unsigned long long)(s_cnt[warp] + __popc(m & ((1u << lane) - 1u)));
-        __syncthreads();
-        if (need_new) {
-            if (g >= A.tot->n_samples) new_flags = YS_DONE;
-            else {
-                const unsigned long long n_pix = (unsigned long long)A.width * A.height;
-                const unsigned pixel = (unsigned)(g % n_pix);
-                const unsigned sample = (unsigned)(A.spp_begin + (int)(g / n_pix));
-                const int px = pixel % A.width, py = pixel / A.width;
-                const U4 uj = draw4(A.seed, pixel, sample, YUNE_VERTEX_CAMERA, 0u);
-                create_ray(A.cam, A.width, A.height, (float)px + u01(uj.x), (float)py + u01(uj.y), ext_o, ext_d);
-                ext_t = INFINITY;
-                ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
-                has_ext = true;
-                meta.x = pixel; meta.y = sample; meta.z = 0;
-                col = v3(0, 0, 0); T = v3(1, 1, 1); Tn = v3(1, 1, 1);
-                new_flags = YS_TRACE;
-            }
-        }
-    }
-
-    // ---- 7. queue pushes (block-wide compaction: warp scans + one atomic per counter per block) and state write-back
-    const bool is_event = MV.has || MO.has;
-    const bool live_now = valid && (new_flags & YS_STATE_MASK) != YS_DONE && (meta.w & YS_STATE_MASK) != YS_DONE;
-    int* const counters[4] = { &C->n_extend, &C->n_shadow, &C->n_events, &C->live };
-    const int cnt[4] = { has_ext ? 1 : 0, (S.has ? 1 : 0) + (MV.has ? 1 : 0) + (MO.has ? 1 : 0), is_event ? 1 : 0, live_now ? 1 : 0 };
-    int first[4];
-    block_alloc<4, YUNE_SHADE_BLOCK / 32>(counters, cnt, first, s_cnt);
-    if (has_ext) {
-        P.eq[first[0]] = s;
-        P.ray_o[s] = f4(ext_o, ext_t);
-        P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
-    }
-    const int ev = A.parity * P.n_slots + first[2];
-    if (is_event) {
-        int ef = (S.has ? YE_HAS_S : 0) | (MV.has ? YE_HAS_MV : 0) | (MO.has ? YE_HAS_MO : 0) | (mo_is_mv ? YE_MO_IS_MV : 0);
-        P.evt[3 * (size_t)ev] = f4(Lv, __int_as_float(ef));
-        P.evt[3 * (size_t)ev + 1] = f4(BV, 0.0f);
-        P.evt[3 * (size_t)ev + 2] = f4(BO, 0.0f);
-        P.evt_idx[s] = ev;
-        new_flags |= YF_PEND_EVT;
-    } else if (S.has) new_flags |= YF_PEND_L;
-    int qs = first[1];
-    if (S.has) {
-        P.sq_o[qs] = f4(S.o, S.tmax);
-        P.sq_d[qs] = f4(S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
-        if (!is_event) P.pend_l[s] = f4(Lv, 0.0f);
-        qs++;
-    }
-    if (MIS) {
-        if (MV.has) { P.sq_o[qs] = f4(MV.o, MV.tmax); P.sq_d[qs] = f4(MV.d, __int_as_float(~(4 * ev + 1))); qs++; }
-        if (MO.has) { P.sq_o[qs] = f4(MO.o, MO.tmax); P.sq_d[qs] = f4(MO.d, __int_as_float(~(4 * ev + 2))); qs++; }
-    }
-    if (valid && (meta.w & YS_STATE_MASK) != YS_DONE) {
-        meta.w = new_flags;
-        P.meta[s] = meta;
-        if ((new_flags & YS_STATE_MASK) != YS_DONE) {
-            P.col[s] = f4(col, 0.0f);
-            P.thr[s] = f4(T, 0.0f);
-            if (has_ext) P.thr_next[s] = f4(Tn, 0.0f);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // Shade stage with IN-BLOCK SORTING (default).  ncu on the kernel above: 14.8 of 32 threads active per instruction, because
 // the lanes of a warp are in different situations (diffuse surface 53 %, specular surface 19 %, miss / drain / free 28 %)
 // and take turns through ~10 K SASS instructions.  Here a persistent block walks chunks of YUNE_SHADE_BLOCK slots:
@@ -659,9 +444,13 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
         const unsigned alive = __ballot_sync(act, !terminate);
         if (!terminate) {
             // ---- next-event estimation at this vertex (evaluateDirectLighting, :535-609)
+            LobePrep lobes; lobes.mode = 0; lobes.pd = lobes.ps = 0.0f;
+            V3 Nx = v3(1, 0, 0), Ny = v3(0, 1, 0);
             if (!SPEC) {
+                lobes = lobe_prepare(mat, false);                               // shared by the NEE and the bounce below
+                onb(n, Nx, Ny);
                 col = vadd(col, vmul(T, mat.ke));                               // the 'emission' term of every return path
-                nee_sample<MIS, false>(alive, lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
+                nee_sample<MIS, false>(alive, lights, n_lights, mat, lobes, hp, n, Nx, Ny, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
                 nee_pending = N.S.has || N.MV.has || N.MO.has;
             }
             __syncwarp(alive);
@@ -676,11 +465,11 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
                     Tn = vscale(T, ior);
                 } else {
                     float prob = 0.0f, pdf = 1.0f;
-                    const bool glossy = select_lobe(mat, u01(u_b.x), false, prob);
+                    const bool glossy = select_lobe_r(lobes, u01(u_b.x), false, prob);
                     if (prob == 0.0f) terminate = true;                         // absorbed (:475-476)
                     else {
                         dir = glossy ? sample_phong(w_o, n, mat.px, mat.py, u01(u_b.y), u01(u_b.z), true, pdf)
-                                     : sample_cosine(n, u01(u_b.y), u01(u_b.z), pdf);
+                                     : sample_cosine_onb(n, Nx, Ny, u01(u_b.y), u01(u_b.z), pdf);
                         if (pdf <= 0.0f) terminate = true;                      // :488
                         else Tn = vdivs(vscale(vmul(T, eval_brdf(mat, dir, w_o, n, glossy, prob, true, A.oren_nayar != 0)), fmaxf(vdot(dir, n), 0.0f)), pdf);
                     }
@@ -840,234 +629,6 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// The same stage split into three kernels with typed queues (default; the fused kernel above stays selectable with
-// option "fused_shade" for A/B measurements).  ncu on the fused kernel showed 11.9 of 32 threads active per instruction
-// and 112 registers: lanes that regenerate (fp64 camera ray), lanes that miss, and lanes on a surface took turns.
-//   k_logic    dense over slots, cheap: resolve last iteration's NEE answers, retire misses / finished paths into the
-//              accumulation buffer, and sort the survivors into the SURFACE queue and the REGENERATION queue
-//   k_surface  SURFACE queue: every lane has a surface hit -> material evaluation, NEE + MIS rays, next direction, roulette
-//   k_regen    REGENERATION queue: next (pixel, sample) + camera ray, every lane active
-// ------------------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_logic(RenderArgs A)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const PathPool& P = A.pool;
-    const bool valid = s < P.n_slots;
-    IterCounters* C = A.ctr + A.parity;
-    uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
-    const unsigned state = meta.w & YS_STATE_MASK;
-    bool to_surface = false, to_regen = valid && state == YS_FREE;
-
-    if (state == YS_TRACE || state == YS_DRAIN) {
-        V3 col = xyz(P.col[s]);
-        bool col_dirty = false;
-        // resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
-        if (meta.w & (YF_PEND_EVT | YF_PEND_L)) {
-            const V3 T = xyz(P.thr[s]);
-            if (meta.w & YF_PEND_EVT) {
-                const int e = P.evt_idx[s];
-                const float4 e0 = P.evt[3 * (size_t)e], e1 = P.evt[3 * (size_t)e + 1], e2 = P.evt[3 * (size_t)e + 2];
-                const int ef = __float_as_int(e0.w);
-                const bool visS = (ef & YE_HAS_S) && P.evt_vis[4 * (size_t)e + 0];
-                const bool visMV = (ef & YE_HAS_MV) && P.evt_vis[4 * (size_t)e + 1];
-                const bool visMO = (ef & YE_MO_IS_MV) ? visMV : ((ef & YE_HAS_MO) && P.evt_vis[4 * (size_t)e + 2]);
-                V3 nee;
-                if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
-                else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
-                col = vadd(col, vmul(T, nee)); col_dirty = true;
-            } else if (P.vis_l[s]) { col = vadd(col, vmul(T, xyz(P.pend_l[s]))); col_dirty = true; }
-        }
-        bool finished = state == YS_DRAIN;
-        if (!finished) {
-            const int tri = __float_as_int(P.hit[s].w);
-            if (tri < 0) {                                                          // nothing hit, or a light
-                const float4 rd = P.ray_d[s];
-                const int lid = __float_as_int(rd.w);
-                if (meta.z == 0) {                                                  // udpt.cl:437-446
-                    if (lid >= 0) col = (vdot(xyz(rd), A.lights.l[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
-                    else col = v3(0.4f, 0.4f, 0.4f);
-                } else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(P.thr[s]), A.lights.l[lid].ke));   // :490-493
-                finished = true;
-            } else to_surface = true;
-        }
-        if (finished) { finish_sample(A, meta.x, col); to_regen = true; }
-        else if (col_dirty) P.col[s] = f4(col, 0.0f);
-    }
-    const int qs = warp_alloc(&C->n_shade, to_surface);
-    if (to_surface) P.shade_q[qs] = s;
-    const int qr = warp_alloc(&C->n_regen, to_regen);
-    if (to_regen) P.regen_q[qr] = s;
-    const unsigned lm = __ballot_sync(0xffffffffu, valid && state != YS_DONE);
-    if ((threadIdx.x & 31) == 0 && lm) atomicAdd(&C->live, __popc(lm));
-}
-
-template <bool MIS>
-__global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_surface(RenderArgs A)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const PathPool& P = A.pool;
-    IterCounters* C = A.ctr + A.parity;
-    const bool active = i < C->n_shade;
-    const int s = active ? P.shade_q[i] : 0;
-    const LightDev* lights = A.lights.l;
-    const int n_lights = A.lights.n;
-
-    bool has_ext = false, finished = false, nee_pending = false;
-    V3 ext_o = v3(0, 0, 0), ext_d = v3(0, 0, 1); float ext_t = INFINITY; int ext_lid = -1;
-    NeeOut N; N.S.has = N.MV.has = N.MO.has = false; N.mo_is_mv = false; N.Lv = N.BV = N.BO = v3(0, 0, 0);
-    uint4 meta = make_uint4(0, 0, 0, 0);
-    V3 col = v3(0, 0, 0), T = v3(1, 1, 1), Tn = v3(1, 1, 1);
-    unsigned new_flags = 0;
-
-    if (active) {
-        meta = P.meta[s];
-        const float4 hit = P.hit[s], ro = P.ray_o[s], rd = P.ray_d[s];
-        col = xyz(P.col[s]); T = xyz(P.thr[s]);
-        const int tri = __float_as_int(hit.w);
-        const V3 o = xyz(ro), d = xyz(rd);
-        const unsigned vtx = meta.z;
-        bool terminate = false;
-        // ---- the surface point (udpt.cl:375-385)
-        const float4 s0 = __ldg(A.sc.shade + 4 * (size_t)tri), s1 = __ldg(A.sc.shade + 4 * (size_t)tri + 1), s2 = __ldg(A.sc.shade + 4 * (size_t)tri + 2);
-        const MatDev mat = load_material(A.sc.mats, __float_as_int(s0.w));
-        const float bw = YF_SUB(YF_SUB(1.0f, hit.y), hit.z);
-        const V3 hp = vadd(o, vscale(d, hit.x));
-        const V3 n = vnormalize(vmadd3(xyz(s0), bw, xyz(s1), hit.y, xyz(s2), hit.z));
-        const V3 w_o = vneg(d);
-        const U4 u_nee = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_NEE);
-        if (vtx > 0) {                                                          // arrival of bounce i = vtx - 1
-            Tn = xyz(P.thr_next[s]);
-            col = vadd(col, vmul(T, mat.ke));                                   // :498
-            T = Tn;                                                             // :504-507 (product was formed at sampling time)
-            if ((int)vtx - 1 > A.rr_threshold) {                                // :514-523
-                const float p = cl_min(luminance(T), 0.95f);
-                const float r = u01(u_nee.x);
-                if (r >= p) terminate = true;
-                else T = vscale(T, YF_DIV(1.0f, p));
-            }
-        }
-        if (!terminate) {
-            // ---- next-event estimation at this vertex (evaluateDirectLighting, :535-609)
-            if (!mat.is_specular) {
-                col = vadd(col, vmul(T, mat.ke));                               // the 'emission' term of every return path
-                nee_sample<MIS, false>(__activemask(), lights, n_lights, mat, hp, n, w_o, u_nee, A.seed, meta.x, meta.y, vtx, A.oren_nayar != 0, N);
-                nee_pending = N.S.has || N.MV.has || N.MO.has;
-            }
-            // ---- continue the path (udpt.cl:463-530)
-            if (!A.gi_check) terminate = true;
-            else {
-                const U4 u_b = draw4(A.seed, meta.x, meta.y, vtx, YUNE_BLK_BOUNCE);
-                V3 dir;
-                if (mat.is_specular) {
-                    float ior = 1.0f;
-                    dir = sample_specular(mat, w_o, n, u01(u_b.w), ior);
-                    Tn = vscale(T, ior);
-                } else {
-                    float prob = 0.0f, pdf = 1.0f;
-                    const bool glossy = select_lobe(mat, u01(u_b.x), false, prob);
-                    if (prob == 0.0f) terminate = true;                         // absorbed (:475-476)
-                    else {
-                        dir = glossy ? sample_phong(w_o, n, mat.px, mat.py, u01(u_b.y), u01(u_b.z), true, pdf)
-                                     : sample_cosine(n, u01(u_b.y), u01(u_b.z), pdf);
-                        if (pdf <= 0.0f) terminate = true;                      // :488
-                        else Tn = vdivs(vscale(vmul(T, eval_brdf(mat, dir, w_o, n, glossy, prob, true, A.oren_nayar != 0)), fmaxf(vdot(dir, n), 0.0f)), pdf);
-                    }
-                }
-                if (!terminate) {
-                    has_ext = true;
-                    ext_d = dir; ext_o = vadd(hp, vscale(dir, YUNE_EPS)); ext_t = INFINITY;
-                    ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
-                    new_flags = YS_TRACE | (mat.is_specular ? YF_PREV_SPEC : 0u);
-                    meta.z = vtx + 1;
-                }
-            }
-        }
-        if (!has_ext) {
-            if (nee_pending) new_flags = YS_DRAIN;
-            else { finished = true; new_flags = YS_FREE; finish_sample(A, meta.x, col); }
-        }
-    }
-
-    // ---- queue pushes (ballot/popc compaction) and state write-back
-    const int qe = warp_alloc(&C->n_extend, has_ext);
-    if (has_ext) {
-        P.eq[qe] = s;
-        P.ray_o[s] = f4(ext_o, ext_t);
-        P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
-    }
-    const int qr = warp_alloc(&C->n_regen, finished);
-    if (finished) P.regen_q[qr] = s;
-    const bool is_event = N.MV.has || N.MO.has;
-    const int ev = A.parity * P.n_slots + warp_alloc(&C->n_events, is_event);
-    if (is_event) {
-        const int ef = (N.S.has ? YE_HAS_S : 0) | (N.MV.has ? YE_HAS_MV : 0) | (N.MO.has ? YE_HAS_MO : 0) | (N.mo_is_mv ? YE_MO_IS_MV : 0);
-        P.evt[3 * (size_t)ev] = f4(N.Lv, __int_as_float(ef));
-        P.evt[3 * (size_t)ev + 1] = f4(N.BV, 0.0f);
-        P.evt[3 * (size_t)ev + 2] = f4(N.BO, 0.0f);
-        P.evt_idx[s] = ev;
-        new_flags |= YF_PEND_EVT;
-    } else if (N.S.has) new_flags |= YF_PEND_L;
-    const int qs = warp_alloc(&C->n_shadow, N.S.has);
-    if (N.S.has) {
-        P.sq_o[qs] = f4(N.S.o, N.S.tmax);
-        P.sq_d[qs] = f4(N.S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
-        if (!is_event) P.pend_l[s] = f4(N.Lv, 0.0f);
-    }
-    if (MIS) {
-        const int qv = warp_alloc(&C->n_shadow, N.MV.has);
-        if (N.MV.has) { P.sq_o[qv] = f4(N.MV.o, N.MV.tmax); P.sq_d[qv] = f4(N.MV.d, __int_as_float(~(4 * ev + 1))); }
-        const int qo = warp_alloc(&C->n_shadow, N.MO.has);
-        if (N.MO.has) { P.sq_o[qo] = f4(N.MO.o, N.MO.tmax); P.sq_d[qo] = f4(N.MO.d, __int_as_float(~(4 * ev + 2))); }
-    }
-    if (active) {
-        meta.w = new_flags;
-        P.meta[s] = meta;
-        if (!finished) {
-            P.col[s] = f4(col, 0.0f);
-            P.thr[s] = f4(T, 0.0f);
-            if (has_ext) P.thr_next[s] = f4(Tn, 0.0f);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(YUNE_SHADE_BLOCK) k_regen(RenderArgs A)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const PathPool& P = A.pool;
-    IterCounters* C = A.ctr + A.parity;
-    const bool active = i < C->n_regen;
-    const int s = active ? P.regen_q[i] : 0;
-    // next (pixel, sample) in global order + camera ray (udpt.cl:164-189)
-    const long long g = warp_alloc64(&A.tot->next_sample, active);
-    bool has_ext = false;
-    V3 ext_o = v3(0, 0, 0), ext_d = v3(0, 0, 1); float ext_t = INFINITY; int ext_lid = -1;
-    uint4 meta = make_uint4(0, 0, 0, YS_DONE);
-    if (active && (unsigned long long)g < A.tot->n_samples) {
-        const unsigned long long n_pix = (unsigned long long)A.width * A.height;
-        const unsigned pixel = (unsigned)((unsigned long long)g % n_pix);
-        const unsigned sample = (unsigned)(A.spp_begin + (int)((unsigned long long)g / n_pix));
-        const int px = pixel % A.width, py = pixel / A.width;
-        const U4 uj = draw4(A.seed, pixel, sample, YUNE_VERTEX_CAMERA, 0u);
-        create_ray(A.cam, A.width, A.height, (float)px + u01(uj.x), (float)py + u01(uj.y), ext_o, ext_d);
-        ext_lid = light_loop(A.lights.l, A.lights.n, ext_o, ext_d, ext_t);
-        has_ext = true;
-        meta = make_uint4(pixel, sample, 0, YS_TRACE);
-    }
-    const int qe = warp_alloc(&C->n_extend, has_ext);
-    if (active) {
-        P.meta[s] = meta;
-        if (has_ext) {
-            P.eq[qe] = s;
-            P.ray_o[s] = f4(ext_o, ext_t);
-            P.ray_d[s] = f4(ext_d, __int_as_float(ext_lid));
-            P.col[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            P.thr[s] = make_float4(1.f, 1.f, 1.f, 0.f);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // pool / buffer initialisation, tonemap, hooks
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_pool_reset(PathPool P)
@@ -1205,13 +766,6 @@ cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStre
     k_iter_end<<<1, 1, 0, st>>>(ctr, tot, parity);
     return cudaGetLastError();
 }
-cudaError_t launch_shade_udpt(const RenderArgs& a, cudaStream_t st)
-{
-    const int grid = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
-    if (a.mis) k_shade_udpt<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    else       k_shade_udpt<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    return cudaGetLastError();
-}
 cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st)
 {
     static int occ[2] = { 0, 0 };                   // resident blocks per SM of the two instantiations (asked once)
@@ -1228,15 +782,6 @@ cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per
     if (grid < 1) grid = 1;
     if (a.mis) k_shade_dense<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
     else       k_shade_dense<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    return cudaGetLastError();
-}
-cudaError_t launch_shade_split(const RenderArgs& a, cudaStream_t st)
-{
-    const int grid = ceil_div(a.pool.n_slots, YUNE_SHADE_BLOCK);
-    k_logic<<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    if (a.mis) k_surface<true><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    else       k_surface<false><<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
-    k_regen<<<grid, YUNE_SHADE_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st)

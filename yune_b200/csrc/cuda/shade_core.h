@@ -62,6 +62,15 @@ YUNE_HD V3 onb_to_world(V3 Nx, V3 Ny, V3 Nz, float x, float y, float z)
 }
 
 // cosineWeightedHemisphere (udpt.cl:843-910): direction about the shading normal, pdf = cos/pi.
+// (Nx, Ny) = onb(n): a surface point samples up to three directions about the same normal, the frame is built once.
+YUNE_HD_CALL V3 sample_cosine_onb(V3 n, V3 Nx, V3 Ny, float r1, float r2, float& pdf)
+{
+    const float phi = YF_MUL(YF_MUL(2.0f, YUNE_PI), r2);
+    const float sinTheta = YF_SQRT(r1);
+    const float x = YF_MUL(sinTheta, cosf(phi)), y = YF_MUL(sinTheta, sinf(phi)), z = YF_SQRT(YF_SUB(1.0f, r1));
+    pdf = YF_MUL(z, YUNE_INV_PI);
+    return onb_to_world(Nx, Ny, n, x, y, z);
+}
 YUNE_HD_CALL V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
 {
     V3 Nx, Ny; onb(n, Nx, Ny);
@@ -93,25 +102,41 @@ YUNE_HD_CALL V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2,
 
 // sampleGlossyPdf (udpt.cl:1062-1119; bdpt variant bdpt.cl:1048-1105): choose diffuse or glossy lobe with the
 // uniform r; returns true for glossy and the selection probability (0 = absorbed, udpt only).
-YUNE_HD_CALL bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float& prob)
+// The part that does not depend on r is computed once per surface point (lobe_prepare) and used by the NEE and the bounce.
+struct LobePrep { int mode; float pd, ps; };       // mode 0: diffuse only, 1: glossy only, 2: both with probabilities pd / ps
+YUNE_HD_CALL LobePrep lobe_prepare(const MatDev& m, bool bdpt_variant)
 {
+    LobePrep L; L.pd = L.ps = 0.0f;
     const V3 ks = m.ks, kd = m.kd;
-    if (vlength(ks) == 0.0f) { prob = 1.0f; return false; }
-    if (vlength(kd) == 0.0f || YF_ADD(YF_ADD(kd.x, kd.y), kd.z) == 0.0f) { prob = 1.0f; return true; }
+    if (vlength(ks) == 0.0f) { L.mode = 0; return L; }
+    if (vlength(kd) == 0.0f || YF_ADD(YF_ADD(kd.x, kd.y), kd.z) == 0.0f) { L.mode = 1; return L; }
     const V3 sum = vadd(ks, kd);
     const float max_val = cl_max(sum.x, cl_max(sum.y, sum.z));
     float pd, ps;
     if (max_val == sum.x) { pd = kd.x; ps = ks.x; }
     else if (max_val == sum.y) { pd = kd.y; ps = ks.y; }
     else { pd = kd.z; ps = ks.z; }
+    if (bdpt_variant && max_val < 1.0f) { const float pad = YF_DIV(YF_SUB(1.0f, max_val), 2.0f); pd = YF_ADD(pd, pad); ps = YF_ADD(ps, pad); }
+    L.mode = 2; L.pd = pd; L.ps = ps;
+    return L;
+}
+YUNE_HD bool select_lobe_r(const LobePrep& L, float r, bool bdpt_variant, float& prob)
+{
+    if (L.mode == 0) { prob = 1.0f; return false; }
+    if (L.mode == 1) { prob = 1.0f; return true; }
+    const float pd = L.pd, ps = L.ps;
     if (bdpt_variant) {
-        if (max_val < 1.0f) { const float pad = YF_DIV(YF_SUB(1.0f, max_val), 2.0f); pd = YF_ADD(pd, pad); ps = YF_ADD(ps, pad); }
         if (r < pd) { prob = pd; return false; }
         prob = ps; return true;
     }
     if (r < pd) { prob = pd; return false; }
     if (r < YF_ADD(pd, ps) && r >= pd) { prob = ps; return true; }
     prob = 0.0f; return false;
+}
+YUNE_HD_CALL bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float& prob)
+{
+    const LobePrep L = lobe_prepare(m, bdpt_variant);
+    return select_lobe_r(L, r, bdpt_variant, prob);
 }
 
 // toShadingSpace + trig helpers + OrenNayarBRDF (udpt-primitives.cl:696-725, 1147-1210); sigma^2 = alpha_x.
@@ -142,7 +167,8 @@ YUNE_HD_CALL V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, fl
 {
     if (!glossy) {
         if (use_oren_nayar && rr_prob == 1.0f) return oren_nayar(m, w_i, w_o, n);       // udpt-primitives.cl:681-686
-        return vdivs(vscale(m.kd, YUNE_INV_PI), rr_prob);
+        const V3 c = vscale(m.kd, YUNE_INV_PI);
+        return rr_prob == 1.0f ? c : vdivs(c, rr_prob);                                 // x / 1 is x, bit for bit
     }
     V3 refl = flip_normal ? reflect_flip(w_i, n) : reflect_noflip(w_i, n);
     refl = vnormalize(refl);
@@ -152,7 +178,7 @@ YUNE_HD_CALL V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, fl
     c = vscale(c, (float)(phong_exp + 2));
     c = vscale(c, YUNE_INV_PI);
     c = vscale(c, 0.5f);
-    return vdivs(c, rr_prob);
+    return rr_prob == 1.0f ? c : vdivs(c, rr_prob);
 }
 
 // calcPhongPDF (udpt.cl:1033-1045, including the cos() of the dot product) and calcCosPDF (:1047-1050)

@@ -14,7 +14,7 @@ r = subprocess.run(cmd, capture_output=True, text=True)
 open(out + ".ptxas.log", "w").write(r.stdout + r.stderr)
 if r.returncode: sys.exit(r.stderr[-3000:])
 for l in (r.stdout + r.stderr).splitlines():
-    if "k_shade_udptILb1" in l or "k_traceILb0ELi1" in l: show = 2
+    if "k_shade_denseILb1" in l or "k_traceILb0ELi1" in l: show = 2
     elif "show" in dir() and show > 0:
         print(l.strip()); show -= 1
 print(out)

@@ -217,13 +217,14 @@ def run_ours(args):
         sampler.start()
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
-    agg = dict(ext=0, sh=0, launches=0, trace_ms=0.0, shade_ms=0.0, timed=0, trace_launches=0, iters=0)
+    agg = dict(ext=0, sh=0, launches=0, trace_ms=0.0, shade_ms=0.0, timed=0, trace_launches=0, iters=0, vd=0, vs=0, vr=0, visits=0)
     for _ in range(args.steps):
         st, extra = step(True)
         dev_ms += st.render_ms + extra
         agg["ext"] += st.extend_rays; agg["sh"] += st.shadow_rays; agg["launches"] += st.kernel_launches + 1 + (1 if rank == 0 else 0)
         agg["trace_ms"] += st.trace_ms; agg["shade_ms"] += st.shade_ms; agg["timed"] += st.timed_iterations
         agg["trace_launches"] += st.trace_launches; agg["iters"] += st.iterations
+        agg["vd"] += st.diffuse_visits; agg["vs"] += st.specular_visits; agg["vr"] += st.regenerations; agg["visits"] += st.slot_visits
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -276,11 +277,30 @@ def run_ours(args):
                 "work_model": work, "trace_share_of_step": agg["trace_ms"] / max(agg["trace_ms"] + agg["shade_ms"], 1e-9),
                 "note": "scene is 0.9 MB and cache resident: this is effective bandwidth of the work model vs HBM peak (SURVEY.md 8d)"}
 
-    # ---- CPU baseline: the reference's kernel on this box's cores, bounded sample of the same workload ----
+    # ---- second kernel of the step: k_shade_dense streams the path pool (DESIGN.md "Kernels"): algorithmic bytes per slot visit
+    # = the state a visit of that kind must read and write (16-byte fields), counted by the kernel itself per kind ----
+    B_CLASSIFY, B_DIFFUSE, B_SPECULAR, B_REGEN = 20.0, 330.0, 260.0, 100.0
+    n_l = max(agg["trace_launches"], 1)
+    shade_bytes = (agg["visits"] * B_CLASSIFY + agg["vd"] * B_DIFFUSE + agg["vs"] * B_SPECULAR + agg["vr"] * B_REGEN) / n_l
+    shade_ms = agg["shade_ms"] / max(agg["timed"], 1)
+    shade_traffic = None
+    sp = os.path.join(ROOT, "profiles", "shade_traffic.json")
+    if os.path.exists(sp):
+        try:
+            shade_traffic = json.load(open(sp)).get("dram_bytes_per_launch")
+        except Exception:
+            shade_traffic = None
+    shade_ach = shade_bytes / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
+    roofline_shade = {"bound": "hbm", "kernel": "k_shade_dense", "achieved": shade_ach, "peak": peak, "unit": "GB/s", "frac": shade_ach / peak,
+                      "traffic": shade_traffic, "avg_launch_ms": shade_ms, "bytes_per_launch": shade_bytes,
+                      "visits_per_launch": {"slots": agg["visits"] / n_l, "diffuse": agg["vd"] / n_l, "specular": agg["vs"] / n_l, "regenerate": agg["vr"] / n_l},
+                      "bytes_per_visit": {"classify": B_CLASSIFY, "diffuse": B_DIFFUSE, "specular": B_SPECULAR, "regenerate": B_REGEN}}
+
+    # ---- CPU baseline: the reference's kernel on this box's cores, bounded sample of the same workload (N = 1 only) ----
     from tests.refbind import ncores
     cores = ncores()
     cw, cspp = 256, 32
-    cpu_v, kind = cpu_reference_run(tris, mats, nodes, cw, cspp, cores)
+    cpu_v, kind = cpu_reference_run(tris, mats, nodes, cw, cspp, cores) if world == 1 else (None, "reference")
     rays = agg["ext"] + agg["sh"]
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,7 +317,8 @@ def run_ours(args):
         "gpu_launches": int(agg["launches"]),
         "clocks": clocks,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": kind,
+        "roofline_shade": roofline_shade,
+        "cpu_baseline": None if world > 1 else {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": kind,
                          "sample": "%dx%dx%dspp of the C2 workload, reference RNG" % (cw, cw, cspp)},
     }
     print(json.dumps(line))

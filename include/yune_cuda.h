@@ -130,6 +130,10 @@ typedef struct yune_stats {
     uint32_t kernel_launches;  /* kernels launched by the last yune_render                                */
     uint32_t trace_launches;   /* ... of which trace kernels                                              */
     uint32_t timed_iterations; /* iterations that trace_ms / shade_ms were summed over                    */
+    uint64_t diffuse_visits;   /* slot visits shaded as a diffuse/glossy surface hit (NEE + bounce)       */
+    uint64_t specular_visits;  /* slot visits shaded as a mirror/glass surface hit                         */
+    uint64_t regenerations;    /* slot visits that started a fresh sample                                  */
+    uint64_t slot_visits;      /* pool slots x shade launches (every launch classifies every slot)        */
 } yune_stats;
 int yune_get_stats(yune_ctx* ctx, yune_stats* out);
 

@@ -16,7 +16,8 @@ class Stats(C.Structure):
     _fields_ = [("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("tonemap_ms", C.c_double),
                 ("samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
-                ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("timed_iterations", C.c_uint32)]
+                ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("timed_iterations", C.c_uint32),
+                ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/*.h declares is listed here (tests check the export table against it)

@@ -447,7 +447,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
             const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
-            if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->stream));
+            if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->sm_count, c->stream));
             else Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->stream));
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
@@ -475,6 +475,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     st.render_ms = ms; st.shade_ms = shade_ms; st.trace_ms = trace_ms;
     st.samples = c->h_tot->n_samples; st.extend_rays = c->h_tot->extend_rays; st.shadow_rays = c->h_tot->shadow_rays;
+    st.diffuse_visits = c->h_tot->visits_d; st.specular_visits = c->h_tot->visits_s; st.regenerations = c->h_tot->visits_r;
+    st.slot_visits = (uint64_t)c->pool.n_slots * (uint64_t)it;
     st.box_tests = c->h_tot->box_tests; st.tri_tests = c->h_tot->tri_tests; st.iterations = (uint32_t)it;
     st.tonemap_ms = c->stats.tonemap_ms;
     c->stats = st;

@@ -68,6 +68,28 @@ __device__ __forceinline__ void block_alloc(int* const (&counters)[K], const int
     for (int k = 0; k < K; k++) first[k] = s_cnt[k * (NWARPS + 1) + warp] + excl[k];
 }
 
+#define YUNE_NW (YUNE_SHADE_BLOCK / 32)
+
+// append to a shared-memory list (persistent shade kernels): one shared atomic per warp
+__device__ __forceinline__ void list_push(int* list, int* count, bool want, int value)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// a finished sample goes to the fp32 accumulation buffer (udpt.cl:193-210; sum instead of running mean)
+__device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
+{
+    if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (udpt.cl:193-194)
+    float* dst = reinterpret_cast<float*>(A.sum + pixel);
+    atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
+}
+
 // camera ray (createRay, udpt.cl:213-238); fp64 where the kernel's literals make it fp64
 __device__ __forceinline__ void create_ray(const float* cam, int W, int H, float pixel_x, float pixel_y, V3& o, V3& d)
 {

@@ -304,12 +304,6 @@ __global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
     ctr[parity ^ 1] = z;
 }
 
-__device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
-{
-    if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (udpt.cl:193-194)
-    float* dst = reinterpret_cast<float*>(A.sum + pixel);
-    atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Shade stage with IN-BLOCK SORTING (default).  ncu on the kernel above: 14.8 of 32 threads active per instruction, because
@@ -324,19 +318,8 @@ __device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixe
 // Leftovers stay in the lists for the next chunk; the last pass flushes them.  Per-slot results are the same as the
 // fused kernel's (same arithmetic, same random-number addressing); only the order of queue entries differs.
 // ------------------------------------------------------------------------------------------------------------
-#define YUNE_NW (YUNE_SHADE_BLOCK / 32)
 enum { YL_DIFFUSE = 0, YL_SPECULAR = 1 };
 
-__device__ __forceinline__ void list_push(int* list, int* count, bool want, int value)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
-}
 
 struct DenseShared {
     int surf[2][2 * YUNE_SHADE_BLOCK];      // diffuse / specular surface hits waiting for a full round
@@ -344,6 +327,7 @@ struct DenseShared {
     int n_surf[2], n_regen;
     int cnt[3 * (YUNE_NW + 1)];             // block_alloc scratch
     unsigned long long sample_base; int ext_base;
+    int visits[3];                          // rounds' entries by kind (statistics)
 };
 
 // phase A for one slot
@@ -584,7 +568,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
 {
     __shared__ DenseShared sh;
     const int tid = threadIdx.x;
-    if (tid == 0) { sh.n_surf[0] = sh.n_surf[1] = 0; sh.n_regen = 0; }
+    if (tid == 0) { sh.n_surf[0] = sh.n_surf[1] = 0; sh.n_regen = 0; sh.visits[0] = sh.visits[1] = sh.visits[2] = 0; }
     __syncthreads();
     const int n_chunks = (A.pool.n_slots + YUNE_SHADE_BLOCK - 1) / YUNE_SHADE_BLOCK;
     int live = 0;                                   // slots this thread left in flight (TRACE or DRAIN)
@@ -599,7 +583,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
                 const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
                 const int s = tid < take ? sh.surf[k][n - take + tid] : -1;
                 __syncthreads();
-                if (tid == 0) sh.n_surf[k] = n - take;
+                if (tid == 0) { sh.n_surf[k] = n - take; sh.visits[k] += take; }
                 if (k == YL_DIFFUSE) surface_round<MIS, false>(A, s, sh, live);
                 else                 surface_round<MIS, true>(A, s, sh, live);
                 __syncthreads();
@@ -610,7 +594,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
             if (!(n >= YUNE_SHADE_BLOCK || (flush && n > 0))) break;
             const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
             __syncthreads();
-            if (tid == 0) sh.n_regen = n - take;
+            if (tid == 0) { sh.n_regen = n - take; sh.visits[2] += take; }
             regen_round(A, n - take, take, sh, live);
         }
         if (flush) break;
@@ -625,6 +609,9 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
         int total = 0;
         for (int w = 0; w < YUNE_NW; w++) total += sh.cnt[w];
         if (total > 0) atomicAdd(&A.ctr[A.parity].live, total);
+        if (sh.visits[0]) atomicAdd(&A.tot->visits_d, (unsigned long long)sh.visits[0]);
+        if (sh.visits[1]) atomicAdd(&A.tot->visits_s, (unsigned long long)sh.visits[1]);
+        if (sh.visits[2]) atomicAdd(&A.tot->visits_r, (unsigned long long)sh.visits[2]);
     }
 }
 

@@ -42,6 +42,7 @@ struct Totals {
     alignas(128) unsigned long long n_samples;       // samples to render in this call
     unsigned long long samples_done;
     unsigned long long extend_rays, shadow_rays, box_tests, tri_tests;
+    unsigned long long visits_d, visits_s, visits_r;   // shade-stage rounds by kind (one atomic per block per launch)
     int live_last;                      // slots still busy after the last completed iteration
     int iterations;
 };

@@ -7,10 +7,12 @@ import yune_b200 as yb
 from tests.refbind import load_golden_scene
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-tris, mats, nodes = load_golden_scene("cornellbox")
+tris, mats, nodes = load_golden_scene("teapot")
+mats = mats.copy(); mats["alpha_x"] = 0.25                  # C3: Oren-Nayar walls
 m = yb.CUDAManager().setup(0)
 for kv in sys.argv[3:]:
     k, v = kv.split("="); m.setOption(k, float(v))
+m.setOption("oren_nayar", 1)
 r = yb.RendererCore(m, size, size)
 assert m.createRenderProgram("bdpt.cl", compiler_opts="-DMIS")
 second = yb.quad_light((0.6, 0.0, -3.6), (-1, 0, 0), (8, 8, 8), (0, 0.3, 0), (0, 0, 0.3))

@@ -6,9 +6,12 @@ sys.path.insert(0, ROOT)
 import yune_b200 as yb
 from tests.refbind import load_golden_scene
 
-def run(name, scene, prog, opts, W, H, spp, lights=None):
+def run(name, scene, prog, opts, W, H, spp, lights=None, oren_nayar=False):
     tris, mats, nodes = load_golden_scene(scene)
     m = yb.CUDAManager().setup(0)
+    if oren_nayar:
+        mats = mats.copy(); mats["alpha_x"] = 0.25            # sigma^2 of the diffuse walls
+        m.setOption("oren_nayar", 1)
     r = yb.RendererCore(m, W, H)
     assert m.createRenderProgram(prog, compiler_opts=opts), m.last_message
     if lights is not None: m.setLightSources(lights)
@@ -32,5 +35,5 @@ out = []
 out.append(run("C1", "cornellbox", "udpt.cl", "", 512, 512, 64))
 out.append(run("C1 x16 spp (steady state)", "cornellbox", "udpt.cl", "", 512, 512, 1024))
 second = yb.quad_light((0.6, 0.0, -3.6), (-1, 0, 0), (8, 8, 8), (0, 0.3, 0), (0, 0, 0.3))       # same second light as tests/test_gpu_parity.py
-out.append(run("C3", "cornellbox", "bdpt.cl", "-DMIS", 1024, 1024, 64, lights=np.concatenate([yb.LIGHT_BDPT, second])))
+out.append(run("C3", "teapot", "bdpt.cl", "-DMIS", 1024, 1024, 512, lights=np.concatenate([yb.LIGHT_BDPT, second]), oren_nayar=True))
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_c1_c3.json"), "w"), indent=1)

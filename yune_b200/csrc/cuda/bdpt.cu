@@ -12,6 +12,7 @@
 // Random numbers are addressed per purpose (rng.h), with the vertex codes of oracle/yune_oracle.cpp:
 //     eye vertex i: i | NEE at eye vertex i: 0x20000000+i | light vertex k: 0x40000000+k | connection (i,j): 0x10000000+32*i+j.
 // Extension: with several lights the emitter of the light path is drawn proportionally to |ke| * area.
+#define YUNE_LEAF_NOINLINE 1       // see strict_math.h (YUNE_HD_LEAF)
 #include "kernel_common.cuh"
 
 namespace yune {
@@ -32,12 +33,21 @@ __device__ __forceinline__ float u01_via_double(uint32_t w) { return (float)((do
 // ------------------------------------------------------------------------------------------------------------
 enum { BL_LIGHT = 0, BL_EYE = 1, BL_REGEN = 2, BL_CAMERA = 3 };
 
+#define YB_MAX_TASKS (YUNE_SHADE_BLOCK * (YB_MAXV - 1))
 struct BdptShared {
-    int list[4][4 * YUNE_SHADE_BLOCK];
+    int list_l[2 * YUNE_SHADE_BLOCK], list_v[2 * YUNE_SHADE_BLOCK], list_r[4 * YUNE_SHADE_BLOCK], list_e[4 * YUNE_SHADE_BLOCK];
     int n[4];
     int cnt[3 * (YUNE_NW + 1)];
     unsigned long long sample_base;
     int visits[4];
+    // eye round: the (eye vertex, light vertex) connections of the round are flattened into one task list so that every
+    // lane evaluates a connection, whatever the light-path lengths of the slots that met in the round
+    float4 eye[YUNE_SHADE_BLOCK][4];            // (hit point, matID) (normal, vertex) (w_o, pixel) (throughput, sample)
+    int eye_slot[YUNE_SHADE_BLOCK];
+    unsigned eye_mask[YUNE_SHADE_BLOCK];        // connection rays launched by the entry (bit j = light vertex j)
+    unsigned short task[YB_MAX_TASKS];          // (entry << 5) | j
+    int n_tasks, n_conn, conn_base;
+    __device__ __forceinline__ int* list(int k) { return k == 0 ? list_l : k == 1 ? list_v : k == 2 ? list_r : list_e; }
 };
 
 // ---- phase A: fold in the answers of the previous eye vertex (bdpt.cl:593-636), retire finished samples, classify ----
@@ -164,7 +174,7 @@ __device__ __forceinline__ void bdpt_light_round(const RenderArgs& A, const Bdpt
         B.bmeta[s] = bm;
         to_camera = !has_ext;
     }
-    list_push(sh.list[BL_CAMERA], &sh.n[BL_CAMERA], to_camera, s);
+    list_push(sh.list_e, &sh.n[BL_CAMERA], to_camera, s);
     int* const counters[1] = { &C->n_extend };
     const int cnt[1] = { has_ext ? 1 : 0 };
     int first[1];
@@ -198,7 +208,7 @@ __device__ __forceinline__ void bdpt_eye_round(const RenderArgs& A, const BdptPo
     int4 bm = make_int4(1, 0, 0, 0);
     V3 e_hp = v3(0, 0, 0), e_n = v3(0, 0, 1), e_wo = v3(0, 0, 1); MatDev e_mat; unsigned e_vtx = 0; bool e_last = false;
     e_mat.ke = e_mat.kd = e_mat.ks = v3(0, 0, 0); e_mat.n = e_mat.px = e_mat.py = e_mat.alpha_x = 1.0f; e_mat.is_specular = e_mat.is_transmissive = 0;
-    float epw = 1.0f;
+    float epw = 1.0f; int e_mat_id = 0;
     unsigned conn_mask = 0;
     const unsigned act = __ballot_sync(0xffffffffu, s >= 0);
     float4* lp = B.lp + (size_t)(s >= 0 ? s : 0) * YB_MAXV * 4;
@@ -212,7 +222,8 @@ __device__ __forceinline__ void bdpt_eye_round(const RenderArgs& A, const BdptPo
         const V3 o = xyz(ro), d = xyz(rd);
         e_vtx = meta.z;
         const float4 s0 = __ldg(A.sc.shade + 4 * (size_t)tri), s1 = __ldg(A.sc.shade + 4 * (size_t)tri + 1), s2 = __ldg(A.sc.shade + 4 * (size_t)tri + 2);
-        e_mat = load_material(A.sc.mats, __float_as_int(s0.w));
+        e_mat_id = __float_as_int(s0.w);
+        e_mat = load_material(A.sc.mats, e_mat_id);
         const float bw = YF_SUB(YF_SUB(1.0f, hit.y), hit.z);
         e_hp = vadd(o, vscale(d, hit.x));
         e_n = vnormalize(vmadd3(xyz(s0), bw, xyz(s1), hit.y, xyz(s2), hit.z));
@@ -239,26 +250,6 @@ __device__ __forceinline__ void bdpt_eye_round(const RenderArgs& A, const BdptPo
         nee_sample<MIS, true>(act, lights, n_lights, e_mat, e_lobes, e_hp, e_n, e_nx, e_ny, e_wo, u_nee, A.seed, meta.x, meta.y, 0x20000000u + e_vtx, use_on, N);
         __syncwarp(act);
     }
-    // ---- connections, pass 1: which light vertices does this eye vertex see geometrically (:604-613)? ----
-    const int lpn = s >= 0 ? bm.x : 0;
-    {
-        const int j_top = __reduce_max_sync(0xffffffffu, lpn);
-        for (int j = j_top - 1; j > 0; j--) {
-            if (j < lpn) {
-                const float4 l0 = lp[4 * j + 0], l1 = lp[4 * j + 1];
-                const V3 lpnt = xyz(l0), ln = xyz(l1);
-                const V3 cd = vnormalize(vsub(lpnt, e_hp));
-                bool want = !(vdot(cd, e_n) <= 0.0f || vdot(vneg(cd), ln) <= 0.0f);                   // :612-613
-                if (want) {
-                    const V3 co = vadd(e_hp, vscale(cd, YUNE_EPS));
-                    float tl = vlength(vsub(lpnt, co));
-                    if (light_loop(lights, n_lights, co, cd, tl) >= 0) want = false;                 // a light inside the segment occludes (traceRay, :244-276)
-                }
-                if (want) conn_mask |= 1u << j;
-            }
-            __syncwarp();
-        }
-    }
     // ---- continue the eye path (:525-537) ----
     if (s >= 0 && !e_last) {
         const U4 u = draw4(A.seed, meta.x, meta.y, e_vtx, YUNE_BLK_BOUNCE);
@@ -278,7 +269,7 @@ __device__ __forceinline__ void bdpt_eye_round(const RenderArgs& A, const BdptPo
     const bool is_event = N.MV.has || N.MO.has;
     const int n_nee = (N.S.has ? 1 : 0) + (N.MV.has ? 1 : 0) + (N.MO.has ? 1 : 0);
     int* const counters[3] = { &C->n_extend, &C->n_shadow, &C->n_events };
-    const int cnt[3] = { has_ext ? 1 : 0, n_nee + __popc(conn_mask), is_event ? 1 : 0 };
+    const int cnt[3] = { has_ext ? 1 : 0, n_nee, is_event ? 1 : 0 };
     int first[3];
     block_alloc<3, YUNE_NW>(counters, cnt, first, sh.cnt);
     unsigned new_flags = (has_ext ? YS_TRACE : YS_DRAIN) | YB_PENDING;  // without a next ray: wait for this vertex's answers, then finish
@@ -302,41 +293,94 @@ __device__ __forceinline__ void bdpt_eye_round(const RenderArgs& A, const BdptPo
         if (N.MV.has) { P.sq_o[qs] = f4(N.MV.o, N.MV.tmax); P.sq_d[qs] = f4(N.MV.d, __int_as_float(~(4 * ev + 1))); qs++; }
         if (N.MO.has) { P.sq_o[qs] = f4(N.MO.o, N.MO.tmax); P.sq_d[qs] = f4(N.MO.d, __int_as_float(~(4 * ev + 2))); qs++; }
     }
-    // ---- connections, pass 2: throughput of every connection found (:614-635) and its shadow ray; lane k-th set bit per trip ----
+    // ---- connections (:594-635), flattened over the round.  Tasks = (entry, j) for every stored light vertex j >= 1. ----
+    const int tid = threadIdx.x;
+    const int lpn = s >= 0 ? bm.x : 0;
+    sh.eye[tid][0] = f4(e_hp, __int_as_float(e_mat_id));
+    sh.eye[tid][1] = f4(e_n, __int_as_float((int)e_vtx));
+    sh.eye[tid][2] = f4(e_wo, __int_as_float((int)meta.x));
+    sh.eye[tid][3] = f4(T, __int_as_float((int)meta.y));
+    sh.eye_slot[tid] = s;
+    sh.eye_mask[tid] = 0u;
+    if (tid == 0) { sh.n_tasks = 0; sh.n_conn = 0; }
+    __syncthreads();
     {
-        unsigned rest = conn_mask;
-        const int trips = __reduce_max_sync(0xffffffffu, __popc(conn_mask));
-        for (int k = 0; k < trips; k++) {
-            if (rest) {
-                const int j = 31 - __clz(rest);
-                rest &= ~(1u << j);
-                const float4 l0 = lp[4 * j + 0], l1 = lp[4 * j + 1], l2 = lp[4 * j + 2], l3 = lp[4 * j + 3];
-                const V3 lpnt = xyz(l0), ln = xyz(l1);
-                const V3 delta = vsub(lpnt, e_hp);
-                const V3 cd = vnormalize(delta);
-                const V3 co = vadd(e_hp, vscale(cd, YUNE_EPS));
-                float dist = vlength(delta);
-                dist = YF_MUL(dist, dist);
-                const float clen = vlength(vsub(lpnt, co));
-                const float gf = YF_DIV(YF_MUL(cl_max(vdot(cd, e_n), 0.0f), cl_max(vdot(vneg(cd), ln), 0.0f)), dist);
-                const U4 uc = draw4(A.seed, meta.x, meta.y, 0x10000000u + 32u * e_vtx + (unsigned)j, YUNE_BLK_BOUNCE);
-                const U4 uc2 = draw4(A.seed, meta.x, meta.y, 0x10000000u + 32u * e_vtx + (unsigned)j, YUNE_BLK_NEE);
-                float prob = 0.0f;
-                bool g = select_lobe(e_mat, u01(uc.x), true, prob);
-                const V3 e2l = eval_brdf(e_mat, cd, e_wo, e_n, g, prob, false, use_on);
-                const MatDev lmat = load_material(A.sc.mats, __float_as_int(__ldg(A.sc.shade + 4 * (size_t)__float_as_int(l0.w)).w));
-                g = select_lobe(lmat, u01(uc2.y), true, prob);
-                const V3 l2e = eval_brdf(lmat, vneg(xyz(l2)), vneg(cd), ln, g, prob, false, use_on);
-                V3 tl3 = vmul(xyz(l3), vmul(vscale(e2l, gf), l2e));                                   // throughput_lp *= gf * e2l * l2e   (:631)
-                tl3 = vmul(tl3, T);                                                                   // *= throughput                       (:632)
-                pend_c[j] = f4(tl3, 0.0f);
-                P.sq_o[qs] = f4(co, clen);
-                P.sq_d[qs] = f4(cd, __int_as_float(P.n_slots + s * YB_MAXV + j));
-                qs++;
-            }
-            __syncwarp();
-        }
+        const int lane = tid & 31;
+        const int mine = lpn > 1 ? lpn - 1 : 0;
+        int incl = mine;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&sh.n_tasks, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+        for (int j = 1; j <= mine; j++) sh.task[base + j - 1] = (unsigned short)((tid << 5) | j);
+        __syncwarp();
     }
+    __syncthreads();
+    // pass 1: which connections exist geometrically (:604-613)?  Survivors are compacted to the front of the task list.
+    const int n_tasks = sh.n_tasks;
+    for (int t0 = 0; t0 < n_tasks; t0 += YUNE_SHADE_BLOCK) {
+        const int t = t0 + tid;
+        bool want = false; unsigned short tk = 0;
+        if (t < n_tasks) {
+            tk = sh.task[t];
+            const int e = tk >> 5, j = tk & 31;
+            const float4* lpe = B.lp + (size_t)sh.eye_slot[e] * YB_MAXV * 4;
+            const float4 l0 = lpe[4 * j + 0], l1 = lpe[4 * j + 1];
+            const V3 hp = xyz(sh.eye[e][0]), en = xyz(sh.eye[e][1]);
+            const V3 lpnt = xyz(l0), ln = xyz(l1);
+            const V3 cd = vnormalize(vsub(lpnt, hp));
+            want = !(vdot(cd, en) <= 0.0f || vdot(vneg(cd), ln) <= 0.0f);                           // :612-613
+            if (want) {
+                const V3 co = vadd(hp, vscale(cd, YUNE_EPS));
+                float tl = vlength(vsub(lpnt, co));
+                if (light_loop(lights, n_lights, co, cd, tl) >= 0) want = false;                     // a light inside the segment occludes (traceRay, :244-276)
+            }
+            if (want) atomicOr(&sh.eye_mask[e], 1u << j);
+        }
+        __syncthreads();                                                                             // batch read before its survivors are written
+        list_push_u16(sh.task, &sh.n_conn, want, tk);
+        __syncthreads();
+    }
+    const int n_conn = sh.n_conn;
+    if (tid == 0) sh.conn_base = n_conn > 0 ? atomicAdd(&C->n_shadow, n_conn) : 0;
+    __syncthreads();
+    // pass 2: throughput of every connection found (:614-635) and its shadow ray
+    for (int t = tid; t < n_conn; t += YUNE_SHADE_BLOCK) {
+        const unsigned short tk = sh.task[t];
+        const int e = tk >> 5, j = tk & 31;
+        const int es = sh.eye_slot[e];
+        const float4 r0 = sh.eye[e][0], r1 = sh.eye[e][1], r2 = sh.eye[e][2], r3 = sh.eye[e][3];
+        const V3 hp = xyz(r0), en = xyz(r1), wo = xyz(r2), Te = xyz(r3);
+        const unsigned pvtx = (unsigned)__float_as_int(r1.w), pix = (unsigned)__float_as_int(r2.w), smp = (unsigned)__float_as_int(r3.w);
+        const MatDev emat = load_material(A.sc.mats, __float_as_int(r0.w));
+        const float4* lpe = B.lp + (size_t)es * YB_MAXV * 4;
+        const float4 l0 = lpe[4 * j + 0], l1 = lpe[4 * j + 1], l2 = lpe[4 * j + 2], l3 = lpe[4 * j + 3];
+        const V3 lpnt = xyz(l0), ln = xyz(l1);
+        const V3 delta = vsub(lpnt, hp);
+        const V3 cd = vnormalize(delta);
+        const V3 co = vadd(hp, vscale(cd, YUNE_EPS));
+        float dist = vlength(delta);
+        dist = YF_MUL(dist, dist);
+        const float clen = vlength(vsub(lpnt, co));
+        const float gf = YF_DIV(YF_MUL(cl_max(vdot(cd, en), 0.0f), cl_max(vdot(vneg(cd), ln), 0.0f)), dist);
+        const U4 uc = draw4(A.seed, pix, smp, 0x10000000u + 32u * pvtx + (unsigned)j, YUNE_BLK_BOUNCE);
+        const U4 uc2 = draw4(A.seed, pix, smp, 0x10000000u + 32u * pvtx + (unsigned)j, YUNE_BLK_NEE);
+        float prob = 0.0f;
+        bool g = select_lobe(emat, u01(uc.x), true, prob);
+        const V3 e2l = eval_brdf(emat, cd, wo, en, g, prob, false, use_on);
+        const MatDev lmat = load_material(A.sc.mats, __float_as_int(__ldg(A.sc.shade + 4 * (size_t)__float_as_int(l0.w)).w));
+        g = select_lobe(lmat, u01(uc2.y), true, prob);
+        const V3 l2e = eval_brdf(lmat, vneg(xyz(l2)), vneg(cd), ln, g, prob, false, use_on);
+        V3 tl3 = vmul(xyz(l3), vmul(vscale(e2l, gf), l2e));                                           // throughput_lp *= gf * e2l * l2e   (:631)
+        tl3 = vmul(tl3, Te);                                                                          // *= throughput                       (:632)
+        B.pend_c[(size_t)es * YB_MAXV + j] = f4(tl3, 0.0f);
+        const int q = sh.conn_base + t;
+        P.sq_o[q] = f4(co, clen);
+        P.sq_d[q] = f4(cd, __int_as_float(P.n_slots + es * YB_MAXV + j));
+    }
+    __syncthreads();
+    conn_mask = sh.eye_mask[tid];
     if (s >= 0) {
         if (has_ext) {
             P.eq[first[0]] = s;
@@ -406,7 +450,7 @@ __device__ __forceinline__ void bdpt_regen_round(const RenderArgs& A, const Bdpt
         } else to_camera = true;
     }
     __syncwarp();
-    list_push(sh.list[BL_CAMERA], &sh.n[BL_CAMERA], to_camera, s);
+    list_push(sh.list_e, &sh.n[BL_CAMERA], to_camera, s);
     int* const counters[1] = { &C->n_extend };
     const int cnt[1] = { has_ext ? 1 : 0 };
     int first[1];
@@ -472,7 +516,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, 2) k_shade_bdpt(RenderArgs A
             const int cls = bdpt_classify(A, B, s);
             __syncwarp();
             #pragma unroll
-            for (int k = 0; k < 4; k++) list_push(sh.list[k], &sh.n[k], cls == k, s);
+            for (int k = 0; k < 4; k++) list_push(sh.list(k), &sh.n[k], cls == k, s);
         }
         __syncthreads();
         // order: L feeds E, V feeds nothing, R feeds E; E last
@@ -482,7 +526,7 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, 2) k_shade_bdpt(RenderArgs A
                 const int n = sh.n[k];
                 if (!(n >= YUNE_SHADE_BLOCK || (flush && n > 0))) break;
                 const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
-                const int s = tid < take ? sh.list[k][n - take + tid] : -1;
+                const int s = tid < take ? sh.list(k)[n - take + tid] : -1;
                 __syncthreads();
                 if (tid == 0) { sh.n[k] = n - take; sh.visits[k] += take; }
                 if (k == BL_LIGHT) bdpt_light_round(A, B, s, sh, live);

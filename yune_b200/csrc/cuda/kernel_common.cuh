@@ -82,6 +82,17 @@ __device__ __forceinline__ void list_push(int* list, int* count, bool want, int 
     if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
+__device__ __forceinline__ void list_push_u16(unsigned short* list, int* count, bool want, unsigned short value)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
 // a finished sample goes to the fp32 accumulation buffer (udpt.cl:193-210; sum instead of running mean)
 __device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
 {

@@ -42,7 +42,7 @@ YUNE_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 struct U4 { uint32_t x, y, z, w; };
 
 // Philox4x32-10 (Salmon et al., SC'11), constants as published.
-YUNE_HD_CALL U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
+YUNE_HD_LEAF U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1)
 {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #if defined(__CUDA_ARCH__)

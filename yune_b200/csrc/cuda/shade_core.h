@@ -83,8 +83,10 @@ YUNE_HD_CALL V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
 
 // phongSampleHemisphere (udpt.cl:700-771): lobe about the mirror direction of w (w = direction back along the
 // arriving ray).  flip_normal = udpt behaviour (reflect()), false = bdpt.cl:814.  pdf = 0 below the surface.
-YUNE_HD_CALL V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal, float& pdf)
+struct DirPdf { V3 d; float pdf; };
+YUNE_HD_LEAF DirPdf sample_phong_v(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal)
 {
+    float pdf;
     V3 Nz = flip_normal ? reflect_flip(w, n) : reflect_noflip(w, n);
     Nz = vnormalize(Nz);
     V3 Nx, Ny; onb(Nz, Nx, Ny);
@@ -97,7 +99,13 @@ YUNE_HD_CALL V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2,
     V3 dir = onb_to_world(Nx, Ny, Nz, x, y, z);
     if (vdot(dir, n) < 0.0f) pdf = 0.0f;
     else pdf = (float)((phong_exponent + 1) * 0.5 * (double)YUNE_INV_PI * (double)powf(costheta, (float)phong_exponent));   // :770, double
-    return dir;
+    DirPdf r; r.d = dir; r.pdf = pdf; return r;
+}
+YUNE_HD V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal, float& pdf)
+{
+    const DirPdf r = sample_phong_v(w, n, px, py, r1, r2, flip_normal);
+    pdf = r.pdf;
+    return r.d;
 }
 
 // sampleGlossyPdf (udpt.cl:1062-1119; bdpt variant bdpt.cl:1048-1105): choose diffuse or glossy lobe with the
@@ -143,7 +151,7 @@ YUNE_HD_CALL bool select_lobe(const MatDev& m, float r, bool bdpt_variant, float
 YUNE_HD float on_sin_theta(V3 w) { return YF_SQRT(YF_SUB(1.0f, YF_MUL(w.z, w.z))); }
 YUNE_HD float on_cos_phi(V3 w) { const float s = on_sin_theta(w); if (s <= YUNE_EPS && s >= -YUNE_EPS) return 0.0f; return fminf(fmaxf(YF_DIV(w.x, s), -1.0f), 1.0f); }
 YUNE_HD float on_sin_phi(V3 w) { const float s = on_sin_theta(w); if (s <= YUNE_EPS && s >= -YUNE_EPS) return 0.0f; return fminf(fmaxf(YF_DIV(w.y, s), -1.0f), 1.0f); }
-YUNE_HD_CALL V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
+YUNE_HD_LEAF V3 oren_nayar(V3 kd, float sigma_sq, V3 w_i, V3 w_o, V3 n)
 {
     V3 Nx, Ny; onb(n, Nx, Ny);
     const V3 wi = v3(vdot(Nx, w_i), vdot(Ny, w_i), vdot(n, w_i));
@@ -154,11 +162,10 @@ YUNE_HD_CALL V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
     float sin_alpha, tan_beta;
     if (fabsf(wi.z) < fabsf(wo.z)) { sin_alpha = on_sin_theta(wi); tan_beta = YF_DIV(on_sin_theta(wo), fabsf(wo.z)); }
     else                           { sin_alpha = on_sin_theta(wo); tan_beta = YF_DIV(on_sin_theta(wi), fabsf(wi.z)); }
-    const float sigma_sq = m.alpha_x;
     const float A = (float)(1 - ((double)sigma_sq / (2 * ((double)sigma_sq + 0.33))));
     const float B = (float)(0.45 * (double)sigma_sq / ((double)sigma_sq + 0.09));
     const float f = YF_ADD(A, YF_MUL(B, YF_MUL(YF_MUL(costerm, sin_alpha), tan_beta)));
-    return vscale(vscale(m.kd, YUNE_INV_PI), f);
+    return vscale(vscale(kd, YUNE_INV_PI), f);
 }
 
 // evaluateBRDF (udpt.cl:611-630; bdpt.cl:718-737 does not flip the normal).  rr_prob = lobe-selection probability.
@@ -166,7 +173,7 @@ YUNE_HD_CALL V3 oren_nayar(const MatDev& m, V3 w_i, V3 w_o, V3 n)
 YUNE_HD_CALL V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, float rr_prob, bool flip_normal, bool use_oren_nayar)
 {
     if (!glossy) {
-        if (use_oren_nayar && rr_prob == 1.0f) return oren_nayar(m, w_i, w_o, n);       // udpt-primitives.cl:681-686
+        if (use_oren_nayar && rr_prob == 1.0f) return oren_nayar(m.kd, m.alpha_x, w_i, w_o, n);       // udpt-primitives.cl:681-686
         const V3 c = vscale(m.kd, YUNE_INV_PI);
         return rr_prob == 1.0f ? c : vdivs(c, rr_prob);                                 // x / 1 is x, bit for bit
     }

@@ -14,9 +14,18 @@
 #if defined(__CUDACC__)
   #define YUNE_HD __host__ __device__ __forceinline__
   #define YUNE_HD_CALL __host__ __device__ __forceinline__   /* big leaf functions; real calls were measured 30 % slower (stack traffic) */
+  /* Leaf functions whose arguments and results are plain values (registers only across the call).  bdpt.cu compiles them as
+     real calls: its shade kernel inlined them ~10 times each (250 KB of code) and ncu showed warps waiting for instruction
+     fetch 7 cycles per issued instruction. */
+  #ifdef YUNE_LEAF_NOINLINE
+    #define YUNE_HD_LEAF __host__ __device__ __noinline__ inline
+  #else
+    #define YUNE_HD_LEAF __host__ __device__ __forceinline__
+  #endif
 #else
   #define YUNE_HD inline
   #define YUNE_HD_CALL inline
+  #define YUNE_HD_LEAF inline
 #endif
 
 #if defined(__CUDA_ARCH__)

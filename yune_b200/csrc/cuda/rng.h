@@ -28,7 +28,8 @@ YUNE_HD uint32_t xor_shift(uint32_t seed)
     seed ^= seed << 13; seed ^= seed >> 17; seed ^= seed << 5;
     return seed;
 }
-YUNE_HD float u01(uint32_t w) { return YF_DIV((float)w, 4294967296.0f); }
+// udpt.cl:185 divides by (float)UINT_MAX = 2^32; x / 2^32 == x * 2^-32 bit for bit (power of two, no underflow for integer-valued x)
+YUNE_HD float u01(uint32_t w) { return YF_MUL((float)w, 2.3283064365386963e-10f); }
 
 YUNE_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {

@@ -88,7 +88,7 @@ YUNE_HD float div_pos(float x, float s)
     return z ? x : q;
 }
 
-YUNE_HD V3 vdivs(V3 a, float s) { return v3(div_pos(a.x, s), div_pos(a.y, s), div_pos(a.z, s)); }
+YUNE_HD_LEAF V3 vdivs(V3 a, float s) { return v3(div_pos(a.x, s), div_pos(a.y, s), div_pos(a.z, s)); }
 YUNE_HD V3 vnormalize(V3 a) { float l = YF_SQRT(vdot(a, a)); return vdivs(a, l); }
 
 // OpenCL min/max per the specification text (clc_shim.inc): only used where a NaN may reach them.

@@ -61,13 +61,19 @@ YUNE_HD V3 onb_to_world(V3 Nx, V3 Ny, V3 Nz, float x, float y, float z)
     return vnormalize(d);
 }
 
+// libm calls behind one definition each: real calls in the BDPT translation unit (code size), inlined elsewhere
+struct CosSin { float c, s; };
+YUNE_HD_LEAF CosSin cos_sin(float phi) { CosSin r; r.c = cosf(phi); r.s = sinf(phi); return r; }
+YUNE_HD_LEAF float pow_leaf(float x, float y) { return powf(x, y); }
+
 // cosineWeightedHemisphere (udpt.cl:843-910): direction about the shading normal, pdf = cos/pi.
 // (Nx, Ny) = onb(n): a surface point samples up to three directions about the same normal, the frame is built once.
 YUNE_HD_CALL V3 sample_cosine_onb(V3 n, V3 Nx, V3 Ny, float r1, float r2, float& pdf)
 {
     const float phi = YF_MUL(YF_MUL(2.0f, YUNE_PI), r2);
     const float sinTheta = YF_SQRT(r1);
-    const float x = YF_MUL(sinTheta, cosf(phi)), y = YF_MUL(sinTheta, sinf(phi)), z = YF_SQRT(YF_SUB(1.0f, r1));
+    const CosSin cs = cos_sin(phi);
+    const float x = YF_MUL(sinTheta, cs.c), y = YF_MUL(sinTheta, cs.s), z = YF_SQRT(YF_SUB(1.0f, r1));
     pdf = YF_MUL(z, YUNE_INV_PI);
     return onb_to_world(Nx, Ny, n, x, y, z);
 }
@@ -76,7 +82,8 @@ YUNE_HD_CALL V3 sample_cosine(V3 n, float r1, float r2, float& pdf)
     V3 Nx, Ny; onb(n, Nx, Ny);
     const float phi = YF_MUL(YF_MUL(2.0f, YUNE_PI), r2);
     const float sinTheta = YF_SQRT(r1);
-    const float x = YF_MUL(sinTheta, cosf(phi)), y = YF_MUL(sinTheta, sinf(phi)), z = YF_SQRT(YF_SUB(1.0f, r1));
+    const CosSin cs = cos_sin(phi);
+    const float x = YF_MUL(sinTheta, cs.c), y = YF_MUL(sinTheta, cs.s), z = YF_SQRT(YF_SUB(1.0f, r1));
     pdf = YF_MUL(z, YUNE_INV_PI);
     return onb_to_world(Nx, Ny, n, x, y, z);
 }
@@ -92,13 +99,14 @@ YUNE_HD_LEAF DirPdf sample_phong_v(V3 w, V3 n, float px, float py, float r1, flo
     V3 Nx, Ny; onb(Nz, Nx, Ny);
     const int phong_exponent = (int)YF_ADD(px, py);
     const float phi = YF_MUL(YF_MUL(2.0f, YUNE_PI), r2);
-    const float costheta = powf(r1, YF_DIV(1.0f, (float)(phong_exponent + 1)));
-    float sintheta = YF_SUB(1.0f, powf(r1, YF_DIV(2.0f, (float)(phong_exponent + 1))));
+    const float costheta = pow_leaf(r1, YF_DIV(1.0f, (float)(phong_exponent + 1)));
+    float sintheta = YF_SUB(1.0f, pow_leaf(r1, YF_DIV(2.0f, (float)(phong_exponent + 1))));
     sintheta = YF_SQRT(sintheta);
-    const float x = YF_MUL(sintheta, cosf(phi)), y = YF_MUL(sintheta, sinf(phi)), z = costheta;
+    const CosSin cs = cos_sin(phi);
+    const float x = YF_MUL(sintheta, cs.c), y = YF_MUL(sintheta, cs.s), z = costheta;
     V3 dir = onb_to_world(Nx, Ny, Nz, x, y, z);
     if (vdot(dir, n) < 0.0f) pdf = 0.0f;
-    else pdf = (float)((phong_exponent + 1) * 0.5 * (double)YUNE_INV_PI * (double)powf(costheta, (float)phong_exponent));   // :770, double
+    else pdf = (float)((phong_exponent + 1) * 0.5 * (double)YUNE_INV_PI * (double)pow_leaf(costheta, (float)phong_exponent));   // :770, double
     DirPdf r; r.d = dir; r.pdf = pdf; return r;
 }
 YUNE_HD V3 sample_phong(V3 w, V3 n, float px, float py, float r1, float r2, bool flip_normal, float& pdf)
@@ -179,7 +187,7 @@ YUNE_HD_CALL V3 eval_brdf(const MatDev& m, V3 w_i, V3 w_o, V3 n, bool glossy, fl
     }
     V3 refl = flip_normal ? reflect_flip(w_i, n) : reflect_noflip(w_i, n);
     refl = vnormalize(refl);
-    const float cos_alpha = powf(fmaxf(vdot(w_o, refl), 0.0f), YF_ADD(m.px, m.py));
+    const float cos_alpha = pow_leaf(fmaxf(vdot(w_o, refl), 0.0f), YF_ADD(m.px, m.py));
     const int phong_exp = (int)YF_ADD(m.px, m.py);
     V3 c = vscale(m.ks, cos_alpha);
     c = vscale(c, (float)(phong_exp + 2));
@@ -195,7 +203,7 @@ YUNE_HD_CALL float phong_pdf(const MatDev& m, V3 w_i, V3 w_o, V3 n)
     refl = vnormalize(refl);
     const float costheta = fmaxf(0.0f, cosf(vdot(refl, w_i)));
     const float e = YF_ADD(m.px, m.py);
-    return (float)(((double)YF_ADD(e, 1.0f)) * 0.5 * (double)YUNE_INV_PI * (double)powf(costheta, e));
+    return (float)(((double)YF_ADD(e, 1.0f)) * 0.5 * (double)YUNE_INV_PI * (double)pow_leaf(costheta, e));
 }
 YUNE_HD float cos_pdf(V3 w_i, V3 n) { return YF_MUL(fmaxf(vdot(w_i, n), 0.0f), YUNE_INV_PI); }
 // powerHeuristic with beta = 2 (udpt.cl:1149-1152): w^2 / (a^2 + b^2)
@@ -216,7 +224,7 @@ YUNE_HD_CALL float fresnel_reflectance(const MatDev& m, V3 w_i, V3 n, float& ior
     r0 = YF_DIV(r0, 3.0f);
     ior_factor = YF_DIV(YF_MUL(n2, n2), YF_MUL(n1, n1));
     const float c = (n1 > n2) ? cosThetaI : cosThetaT;
-    return YF_ADD(r0, YF_MUL(YF_SUB(1.0f, r0), YF_SUB(1.0f, powf(c, 5.0f))));
+    return YF_ADD(r0, YF_MUL(YF_SUB(1.0f, r0), YF_SUB(1.0f, pow_leaf(c, 5.0f))));
 }
 // refract (udpt.cl:963-990)
 YUNE_HD_CALL V3 refract_dir(const MatDev& m, V3 w_i, V3 n)

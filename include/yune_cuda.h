@@ -68,6 +68,7 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
  *   0 = walk the reference tree itself), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
  *   "trace_block", "trace_blocks_per_sm", "refill_idle", "phase_min" (trace-kernel launch shape / warp scheduling),
+ *   "shade_blocks_per_sm" (persistent shade grid; 0 = what the occupancy query returns),
  *   "isect" (0 = reference Moller-Trumbore), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);

@@ -45,6 +45,18 @@ void yune_camera_default(float y_fov_degrees, yune_cam* out);
 void yune_camera_set(const float side[4], const float up[4], const float look_at[4], const float eye[4],
                      float y_fov_degrees, yune_cam* out);
 
+/* Interactive pose updates (Camera::setOrientation, src/Camera.cpp:119-166): a stateful camera object.
+ * dir = key direction (one axis per call, priority z, x, y; moves by move_speed = 0.1), pitch / yaw = mouse deltas
+ * (multiplied by rotation_speed = 0.25 rad); pitch is ignored once it would turn the up vector below the horizon.
+ * After a change render with reset = 1 (src/RendererCore.cpp:531-574). */
+typedef struct yune_camera yune_camera;
+yune_camera* yune_camera_create(float y_fov_degrees);
+void yune_camera_destroy(yune_camera* cam);
+void yune_camera_set_orientation(yune_camera* cam, const float dir[4], float pitch, float yaw);
+void yune_camera_reset(yune_camera* cam);
+int  yune_camera_is_changed(const yune_camera* cam);
+void yune_camera_set_buffer(yune_camera* cam, yune_cam* out);       /* Camera::setBuffer: writes the record, clears is_changed */
+
 #ifdef __cplusplus
 }
 #endif

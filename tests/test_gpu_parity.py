@@ -312,6 +312,26 @@ def test_shade_result_independent_of_scheduling(gpu_manager):
         m.setOption("pool_slots", old_pool); m.setOption("shade_blocks_per_sm", 0)
 
 
+def test_bdpt_result_independent_of_scheduling(gpu_manager):
+    """Same property for the bidirectional kernel: its rounds (light vertex / eye vertex / regenerate / camera) and the
+    flattened connection task list regroup with the pool size; every sample must come out the same."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 64, 64, kernel="bdpt.cl", opts="-DMIS")
+    r.seed = 23
+    old_pool = m.getOption("pool_slots")
+    ref = None
+    try:
+        for pool in (1 << 22, 4096, 1025, 1 << 15, 4096):
+            m.setOption("pool_slots", pool)
+            m.check(r._lib.yune_render(r._ctx, 0, 3, 1, r.seed, 1))
+            a = r.readSum()
+            assert (a[..., 3] == 3).all()
+            if ref is None: ref = a
+            else: np.testing.assert_allclose(a, ref, rtol=2e-5, atol=1e-5)
+    finally:
+        m.setOption("pool_slots", old_pool)
+
+
 def test_headless_cli(gpu_manager, tmp_path):
     """C++ front end (csrc/app/yune_headless.cpp over csrc/host/RendererCore.cpp): OBJ in, .pfm out, same image as the
     Python harness renders through the same C ABI."""

@@ -126,6 +126,58 @@ def test_camera_record():
     assert yb.default_camera(90.0)["view_plane_dist"][0] == np.float32(1 / math.tan(90.0 * 3.14 / 360))
 
 
+def _glm_rotate(angle, axis):
+    """glm::rotate(mat4(1), angle, axis) (GLM's matrix_transform.inl), column-major -> returned as a numpy matrix M with M @ v."""
+    a = np.asarray(axis, np.float64); a = a / np.linalg.norm(a)
+    c, s = np.cos(angle), np.sin(angle)
+    t = (1 - c) * a
+    R = np.eye(4)
+    R[0, 0] = c + t[0] * a[0]; R[1, 0] = t[0] * a[1] + s * a[2]; R[2, 0] = t[0] * a[2] - s * a[1]
+    R[0, 1] = t[1] * a[0] - s * a[2]; R[1, 1] = c + t[1] * a[1]; R[2, 1] = t[1] * a[2] + s * a[0]
+    R[0, 2] = t[2] * a[0] + s * a[1]; R[1, 2] = t[2] * a[1] - s * a[0]; R[2, 2] = c + t[2] * a[2]
+    return R
+
+
+def test_camera_set_orientation_follows_reference():
+    """Camera::setOrientation (src/Camera.cpp:119-166) restated with numpy in double: key moves (one axis per call, priority
+    z, x, y, step 0.1), yaw about world +Y, pitch about the local side axis and refused once up.y would turn negative."""
+    import yune_b200 as yb
+    cam = yb.Camera(60.0)
+    side = np.array([1.0, 0, 0, 0]); up = np.array([0, 1.0, 0, 0]); look = np.array([0, 0, -1.0, 0]); eye = np.array([0, 0, 0, 1.0])
+    M = np.stack([side, up, -look, eye], axis=1)               # columns
+    assert not cam.is_changed or cam.setBuffer() is not None
+    rng = np.random.default_rng(5)
+    moves = [((0, 0, 1, 0), 0, 0), ((1, 0, 0, 0), 0, 0), ((0, -1, 0, 0), 0, 0), ((1, 1, -1, 0), 0, 0),
+             ((0, 0, 0, 0), 0.0, 2.0), ((0, 0, 0, 0), 1.5, 0.0), ((0, 0, 1, 0), -0.7, 0.9), ((0, 0, 0, 0), 40.0, 0.0)]
+    moves += [(tuple(rng.integers(-1, 2, 3)) + (0,), float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2))) for _ in range(12)]
+    for d, pitch, yaw in moves:
+        cam.setOrientation(d, pitch, yaw)
+        assert cam.is_changed
+        # --- restatement ---
+        if d[2] > 0: eye = eye + look * 0.1
+        elif d[2] < 0: eye = eye - look * 0.1
+        elif d[0] > 0: eye = eye + side * 0.1
+        elif d[0] < 0: eye = eye - side * 0.1
+        elif d[1] > 0: eye = eye + up * 0.1
+        elif d[1] < 0: eye = eye - up * 0.1
+        if pitch == 0 and yaw == 0:
+            M[:, 3] = eye
+        else:
+            rotx = _glm_rotate(pitch * 0.25, side[:3]); roty = _glm_rotate(yaw * 0.25, (0, 1, 0))
+            M[:, 3] = (0, 0, 0, 1)
+            if (rotx @ up)[1] >= 0: M = rotx @ M
+            M = roty @ M
+            M[:, 3] = eye
+            side = M[:, 0] / np.linalg.norm(M[:, 0]); up = M[:, 1] / np.linalg.norm(M[:, 1]); look = -M[:, 2] / np.linalg.norm(M[:, 2])
+        rec = cam.setBuffer()
+        assert not cam.is_changed
+        ours = np.stack([rec["r1"][0], rec["r2"][0], rec["r3"][0], rec["r4"][0]])      # rows of view2world (Cam.r1..r4)
+        np.testing.assert_allclose(ours, M, atol=2e-5)
+    assert up[1] >= -1e-6                                        # the pitch limit held through the 40-unit pitch
+    cam.resetCamera()
+    np.testing.assert_array_equal(cam.setBuffer().view(np.uint8), yb.default_camera(60.0).view(np.uint8))
+
+
 def test_synthetic_c4_scene_and_in_memory_geometry(tmp_path):
     """configs[3] generator at a small subdivision: 40 wall triangles + 2 icospheres; setGeometry (no OBJ text) must build
     exactly what loadModel builds from the equivalent OBJ, and -- when the reference is present -- what the reference builds."""

@@ -68,6 +68,12 @@ HOST_API = {
     "yune_scene_root_aabb": (None, [C.c_void_p, C.c_void_p]),
     "yune_camera_default": (None, [C.c_float, C.c_void_p]),
     "yune_camera_set": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "yune_camera_create": (C.c_void_p, [C.c_float]),
+    "yune_camera_destroy": (None, [C.c_void_p]),
+    "yune_camera_set_orientation": (None, [C.c_void_p, C.c_void_p, C.c_float, C.c_float]),
+    "yune_camera_reset": (None, [C.c_void_p]),
+    "yune_camera_is_changed": (C.c_int, [C.c_void_p]),
+    "yune_camera_set_buffer": (None, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -42,6 +42,37 @@ def default_camera(y_fov=60.0):
     return cam
 
 
+class Camera:
+    """yune::Camera (src/Camera.cpp): pose state + setOrientation + setBuffer, computed by the native host library."""
+
+    def __init__(self, y_fov=60.0):
+        self._lib = _native.load()
+        self._h = self._lib.yune_camera_create(C.c_float(y_fov))
+        if not self._h:
+            raise MemoryError("yune_camera_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.yune_camera_destroy(self._h); self._h = None
+
+    def setOrientation(self, direction=(0, 0, 0, 0), pitch=0.0, yaw=0.0):
+        d = np.asarray(direction, np.float32)
+        self._lib.yune_camera_set_orientation(self._h, _ptr(d), C.c_float(pitch), C.c_float(yaw))
+        return self
+
+    def resetCamera(self):
+        self._lib.yune_camera_reset(self._h); return self
+
+    @property
+    def is_changed(self):
+        return bool(self._lib.yune_camera_is_changed(self._h))
+
+    def setBuffer(self):
+        cam = np.zeros(1, CAM_DTYPE)
+        self._lib.yune_camera_set_buffer(self._h, _ptr(cam))
+        return cam
+
+
 def quad_light(pos, normal, ke, edge_l, edge_w):
     q = np.zeros(1, QUAD_DTYPE)
     q["pos"][0] = list(pos) + [1.0]

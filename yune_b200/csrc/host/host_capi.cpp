@@ -2,6 +2,7 @@
 #include "yune_host.h"
 #include "Scene.h"
 
+#include <new>
 #include <string>
 #include <exception>
 
@@ -70,5 +71,17 @@ void yune_camera_set(const float side[4], const float up[4], const float look_at
                       yune::Vec4{look_at[0], look_at[1], look_at[2], look_at[3]}, yune::Vec4{eye[0], eye[1], eye[2], eye[3]});
     cam.setBuffer(out);
 }
+
+
+struct yune_camera { yune::Camera cam; explicit yune_camera(float fov) : cam(fov) {} };
+yune_camera* yune_camera_create(float fov) { return new (std::nothrow) yune_camera(fov); }
+void yune_camera_destroy(yune_camera* c) { delete c; }
+void yune_camera_set_orientation(yune_camera* c, const float dir[4], float pitch, float yaw)
+{
+    c->cam.setOrientation(yune::Vec4{dir[0], dir[1], dir[2], dir[3]}, pitch, yaw);
+}
+void yune_camera_reset(yune_camera* c) { c->cam.resetCamera(); }
+int  yune_camera_is_changed(const yune_camera* c) { return c->cam.is_changed ? 1 : 0; }
+void yune_camera_set_buffer(yune_camera* c, yune_cam* out) { c->cam.setBuffer(out); }
 
 }

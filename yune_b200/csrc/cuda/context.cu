@@ -98,7 +98,7 @@ static void free_pool(yune_ctx* c)
 {
     PathPool& P = c->pool;
     dfree(P.ray_o); dfree(P.ray_d); dfree(P.hit); dfree(P.thr); dfree(P.thr_next); dfree(P.col); dfree(P.pend_l);
-    dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.shade_q); dfree(P.regen_q); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
+    dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
     dfree(c->bdpt.lp); dfree(c->bdpt.pend_c); dfree(c->bdpt.bmeta);
     P.n_slots = 0; c->pool_alloc = 0;
 }
@@ -118,7 +118,6 @@ static int ensure_pool(yune_ctx* c)
     Y_CUDA(c, cudaMalloc(&P.pend_l, N * 16)); Y_CUDA(c, cudaMalloc(&P.meta, N * 16));
     Y_CUDA(c, cudaMalloc(&P.evt_idx, N * 4)); Y_CUDA(c, cudaMalloc(&P.vis_l, bd ? N * (1 + V) : N)); Y_CUDA(c, cudaMalloc(&P.eq, N * 4));
     Y_CUDA(c, cudaMalloc(&P.sq_o, rays_per_slot * N * 16)); Y_CUDA(c, cudaMalloc(&P.sq_d, rays_per_slot * N * 16));
-    Y_CUDA(c, cudaMalloc(&P.shade_q, N * 4)); Y_CUDA(c, cudaMalloc(&P.regen_q, N * 4));
     if (bd) {
         Y_CUDA(c, cudaMalloc(&c->bdpt.lp, N * V * 4 * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.pend_c, N * V * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.bmeta, N * 16));
     }

@@ -22,16 +22,6 @@ __device__ __forceinline__ int warp_alloc(int* counter, bool want)
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     return want ? base + __popc(m & ((1u << lane) - 1)) : -1;
 }
-__device__ __forceinline__ long long warp_alloc64(unsigned long long* counter, bool want)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (m == 0) return -1;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == (__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
-}
 
 // Block-wide queue allocation: every thread of the block calls it with up to K request counts (0..3 each); ONE global
 // atomic per counter per block.  s_cnt is shared memory of K * (warps + 1) ints.  Returns, per counter, the first index this

@@ -300,7 +300,7 @@ __global__ void k_iter_end(IterCounters* ctr, Totals* tot, int parity)
     tot->shadow_rays += (unsigned long long)c.n_shadow;
     tot->live_last = c.live;
     tot->iterations += 1;
-    IterCounters z; z.n_extend = z.n_shadow = z.n_events = z.live = 0; z.fetch_extend = z.fetch_shadow = z.n_shade = z.n_regen = 0;
+    IterCounters z; z.n_extend = z.n_shadow = z.n_events = z.live = 0; z.fetch_extend = z.fetch_shadow = 0;
     ctr[parity ^ 1] = z;
 }
 

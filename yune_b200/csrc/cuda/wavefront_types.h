@@ -34,8 +34,6 @@ struct IterCounters {
     alignas(128) int live;
     alignas(128) int fetch_extend;
     alignas(128) int fetch_shadow;
-    alignas(128) int n_shade;
-    alignas(128) int n_regen;
 };
 struct Totals {
     alignas(128) unsigned long long next_sample;     // next global sample index to hand out (own line: atomics)
@@ -71,8 +69,6 @@ struct PathPool {
     int*     evt_idx;    // valid with YF_PEND_EVT
     unsigned char* vis_l;   // 1 = NEE shadow ray reached the light (written by the trace kernel)
     // queues
-    int*     shade_q;    // slots with a surface hit to shade this iteration (k_logic -> k_surface)
-    int*     regen_q;    // slots to regenerate this iteration (k_logic, k_surface -> k_regen)
     int*     eq;         // extension queue: slot indices
     float4*  sq_o;       // shadow queue: xyz origin, w = tmax
     float4*  sq_d;       // xyz direction, w = int bits: target (>= 0 slot -> vis_l ; < 0 -> ~target = event*4 + which)

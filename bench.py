@@ -226,6 +226,7 @@ def run_ours(args):
         agg["trace_launches"] += st.trace_launches; agg["iters"] += st.iterations
         agg["vd"] += st.diffuse_visits; agg["vs"] += st.specular_visits; agg["vr"] += st.regenerations; agg["visits"] += st.slot_visits
     barrier()
+    pool_in_use = int(m.getOption("pool_slots_in_use"))
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     m.setOption("time_stages", 0)
@@ -307,8 +308,8 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (reference scene buffers from tests/golden, default camera, counter-based RNG seed 12345)",
         "config": {"workload": WORKLOAD, "spp_per_rank": SPP, "sample_range_of_rank_r": "[r*1024, (r+1)*1024)",
-                   "pool_slots": int(m.getOption("pool_slots")),
-                   "l2": "per-step working set (path pool + queues ~1.4 GB at 4M slots, 16.8 MB accumulation) exceeds the 126 MB L2; "
+                   "pool_slots": pool_in_use,
+                   "l2": "per-step working set (path pool + queues ~350 B/slot = 5.6 GB at 16M slots, 16.8 MB accumulation) exceeds the 126 MB L2; "
                          "the 0.9 MB scene is cache-resident by nature of the workload"},
         "mrays_per_s": rays * world / (dev_ms * 1e-3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays / (WIDTH * HEIGHT * SPP * args.steps),

@@ -301,7 +301,7 @@ def test_shade_result_independent_of_scheduling(gpu_manager):
     old_pool = m.getOption("pool_slots")
     ref = None
     try:
-        for pool, per_sm in ((1 << 22, 0), (4096, 1), (5000, 3), (1025, 2), (1 << 16, 0), (4096, 1)):
+        for pool, per_sm in ((0, 0), (1 << 22, 0), (4096, 1), (5000, 3), (1025, 2), (1 << 16, 0), (4096, 1)):
             m.setOption("pool_slots", pool); m.setOption("shade_blocks_per_sm", per_sm)
             m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1))
             a = r.readSum()
@@ -321,7 +321,7 @@ def test_bdpt_result_independent_of_scheduling(gpu_manager):
     old_pool = m.getOption("pool_slots")
     ref = None
     try:
-        for pool in (1 << 22, 4096, 1025, 1 << 15, 4096):
+        for pool in (0, 1 << 22, 4096, 1025, 1 << 15, 4096):
             m.setOption("pool_slots", pool)
             m.check(r._lib.yune_render(r._ctx, 0, 3, 1, r.seed, 1))
             a = r.readSum()

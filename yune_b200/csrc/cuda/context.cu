@@ -78,7 +78,7 @@ struct yune_ctx {
     int cap_iteration = -1, cap_max = 0; int cap_counts[4] = {0, 0, 0, 0};
 
     // options
-    int opt_pool_slots = 1 << 22, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_pool_slots = 0, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
@@ -103,14 +103,25 @@ static void free_pool(yune_ctx* c)
     P.n_slots = 0; c->pool_alloc = 0;
 }
 
-static int ensure_pool(yune_ctx* c)
+// Pool size.  "pool_slots" = 0 (default) sizes the pool for the job: measured on C1 / C2 at 16.8 M ... 1.07 G samples the best
+// pool doubles when the job quadruples (2 M, 4 M, 8 M, 16 M slots): a bigger pool amortises the per-iteration costs (launches,
+// kernel tails), a smaller one shortens the ramp at both ends of the job.  Hence 512 * sqrt(samples), as a power of two.
+static int ensure_pool(yune_ctx* c, unsigned long long n_samples)
 {
-    const int n = c->opt_pool_slots;
-    if (c->pool_alloc == n && c->pool_integrator == c->integrator) return YUNE_OK;
-    free_pool(c);
-    PathPool& P = c->pool;
-    const size_t N = (size_t)n;
     const bool bd = c->integrator == INTEGRATOR_BDPT;
+    int n = c->opt_pool_slots;
+    if (n <= 0) {
+        const double want = 512.0 * std::sqrt((double)n_samples);
+        int e = (int)std::lround(std::log2(want > 1.0 ? want : 1.0));
+        const int e_max = bd ? 22 : 24;                      // a BDPT slot carries 4 KB of path vertices
+        if (e < 16) e = 16;
+        if (e > e_max) e = e_max;
+        n = 1 << e;
+    }
+    PathPool& P = c->pool;
+    if (c->pool_integrator == c->integrator && c->pool_alloc >= n) { P.n_slots = n; return YUNE_OK; }   // capacity is kept
+    free_pool(c);
+    const size_t N = (size_t)n;
     const size_t V = 32;                         // YB_MAXV of bdpt.cu: vertices stored per slot
     const size_t rays_per_slot = bd ? 3 + V : 3; // shadow rays one slot can emit per iteration
     Y_CUDA(c, cudaMalloc(&P.ray_o, N * 16)); Y_CUDA(c, cudaMalloc(&P.ray_d, N * 16)); Y_CUDA(c, cudaMalloc(&P.hit, N * 16));
@@ -360,7 +371,7 @@ static int* option_slot(yune_ctx* c, const char* key)
 {
     if (!key) return nullptr;
     struct { const char* k; int* p; } tab[] = {
-        {"pool_slots", &c->opt_pool_slots}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
+        {"pool_slots", &c->opt_pool_slots}, {"pool_slots_in_use", &c->pool.n_slots}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
@@ -375,7 +386,8 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     int* p = option_slot(c, key);
     if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
     const int v = (int)value;
-    if (p == &c->opt_pool_slots && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be in [1024, 2^26]");
+    if (p == &c->opt_pool_slots && v != 0 && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be 0 (sized per job) or in [1024, 2^26]");
+    if (p == &c->pool.n_slots) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots_in_use is read-only");
     if (p == &c->opt_trace_block && (v < 32 || v > YUNE_TRACE_MAX_BLOCK || (v & 31))) Y_FAIL(c, YUNE_ERR_INVALID, "trace_block must be a multiple of 32 in [32, 1024]");
     if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
@@ -405,7 +417,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     Y_CUDA(c, cudaSetDevice(c->device));
     int rc;
     if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
-    if ((rc = ensure_pool(c)) != YUNE_OK) return rc;
+    if ((rc = ensure_pool(c, (unsigned long long)c->W * c->H * (unsigned long long)spp_count)) != YUNE_OK) return rc;
     TraceLaunch tl;
     if ((rc = trace_config(c, tl)) != YUNE_OK) return rc;
 

@@ -79,7 +79,7 @@ struct yune_ctx {
 
     // options
     int opt_pool_slots = 0, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
-    int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 6, opt_phase_min = 8;
+    int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 12, opt_phase_min = 24, opt_inner_min = 16, opt_inner_chain = 1;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
@@ -97,7 +97,7 @@ template <class T> static void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr;
 static void free_pool(yune_ctx* c)
 {
     PathPool& P = c->pool;
-    dfree(P.ray_o); dfree(P.ray_d); dfree(P.hit); dfree(P.thr); dfree(P.thr_next); dfree(P.col); dfree(P.pend_l);
+    dfree(P.ray_o.p); P.ray_d.p = nullptr; dfree(P.hit); dfree(P.thr.p); P.thr_next.p = nullptr; dfree(P.col.p); P.pend_l.p = nullptr;
     dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
     dfree(c->bdpt.lp); dfree(c->bdpt.pend_c); dfree(c->bdpt.bmeta);
     P.n_slots = 0; c->pool_alloc = 0;
@@ -124,9 +124,9 @@ static int ensure_pool(yune_ctx* c, unsigned long long n_samples)
     const size_t N = (size_t)n;
     const size_t V = 32;                         // YB_MAXV of bdpt.cu: vertices stored per slot
     const size_t rays_per_slot = bd ? 3 + V : 3; // shadow rays one slot can emit per iteration
-    Y_CUDA(c, cudaMalloc(&P.ray_o, N * 16)); Y_CUDA(c, cudaMalloc(&P.ray_d, N * 16)); Y_CUDA(c, cudaMalloc(&P.hit, N * 16));
-    Y_CUDA(c, cudaMalloc(&P.thr, N * 16)); Y_CUDA(c, cudaMalloc(&P.thr_next, N * 16)); Y_CUDA(c, cudaMalloc(&P.col, N * 16));
-    Y_CUDA(c, cudaMalloc(&P.pend_l, N * 16)); Y_CUDA(c, cudaMalloc(&P.meta, N * 16));
+    Y_CUDA(c, cudaMalloc(&P.ray_o.p, N * 32)); P.ray_d.p = P.ray_o.p + 1; Y_CUDA(c, cudaMalloc(&P.hit, N * 16));
+    Y_CUDA(c, cudaMalloc(&P.thr.p, N * 32)); P.thr_next.p = P.thr.p + 1; Y_CUDA(c, cudaMalloc(&P.col.p, N * 32)); P.pend_l.p = P.col.p + 1;
+    Y_CUDA(c, cudaMalloc(&P.meta, N * 16));
     Y_CUDA(c, cudaMalloc(&P.evt_idx, N * 4)); Y_CUDA(c, cudaMalloc(&P.vis_l, bd ? N * (1 + V) : N)); Y_CUDA(c, cudaMalloc(&P.eq, N * 4));
     Y_CUDA(c, cudaMalloc(&P.sq_o, rays_per_slot * N * 16)); Y_CUDA(c, cudaMalloc(&P.sq_d, rays_per_slot * N * 16));
     if (bd) {
@@ -375,7 +375,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -389,7 +389,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_pool_slots && v != 0 && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be 0 (sized per job) or in [1024, 2^26]");
     if (p == &c->pool.n_slots) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots_in_use is read-only");
     if (p == &c->opt_trace_block && (v < 32 || v > YUNE_TRACE_MAX_BLOCK || (v & 31))) Y_FAIL(c, YUNE_ERR_INVALID, "trace_block must be a multiple of 32 in [32, 1024]");
-    if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
+    if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32) || (p == &c->opt_inner_min && (v < 1 || v > 33)) || (p == &c->opt_inner_chain && (v < 0 || v > 64))) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
@@ -434,9 +434,9 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
     c->bdpt.bounces = c->opt_bdpt_bounces;
     TraceArgs t{};
-    t.sc = c->sc; t.eq = c->pool.eq; t.ray_o = c->pool.ray_o; t.ray_d = c->pool.ray_d; t.hit = c->pool.hit;
+    t.sc = c->sc; t.eq = c->pool.eq; t.ray_o = c->pool.ray_o.p; t.ray_d = c->pool.ray_d.p; t.ray_stride = 2; t.hit = c->pool.hit;
     t.sq_o = c->pool.sq_o; t.sq_d = c->pool.sq_d; t.vis_a = c->pool.vis_l; t.vis_b = c->pool.evt_vis; t.tot = c->d_tot;
-    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min;
+    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min; t.inner_min = c->opt_inner_min; t.inner_chain = c->opt_inner_chain;
 
     yune_stats st{};
     // Stage timing: every `time_stages`-th iteration is bracketed by CUDA events on the launching stream (no host
@@ -609,10 +609,10 @@ static int hook_trace(yune_ctx* c, int n, int any)
     int h_cnt[4] = {any ? 0 : n, 0, any ? n : 0, 0};       // n_extend, fetch_extend, n_shadow, fetch_shadow
     Y_CUDA(c, cudaMemcpyAsync(c->hk_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, c->stream));
     TraceArgs t{};
-    t.sc = c->sc; t.eq = nullptr; t.ray_o = c->hk_o; t.ray_d = c->hk_d; t.hit = c->hk_hit;
+    t.sc = c->sc; t.eq = nullptr; t.ray_o = c->hk_o; t.ray_d = c->hk_d; t.ray_stride = 1; t.hit = c->hk_hit;
     t.n_extend = c->hk_cnt + 0; t.fetch_extend = c->hk_cnt + 1; t.n_shadow = c->hk_cnt + 2; t.fetch_shadow = c->hk_cnt + 3;
     t.sq_o = c->hk_o; t.sq_d = c->hk_d; t.vis_a = c->hk_vis; t.vis_b = c->hk_vis; t.tot = nullptr;
-    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min;
+    t.refill_idle = c->opt_refill_idle; t.phase_min = c->opt_phase_min; t.inner_min = c->opt_inner_min; t.inner_chain = c->opt_inner_chain;
     Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, false, c->stream));
     return YUNE_OK;
 }

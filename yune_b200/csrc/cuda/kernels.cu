@@ -20,24 +20,43 @@ namespace yune {
 // ---- device-side walk: the same state machine as trace_core.h (tests/hostcheck validates that one against the oracle;
 // tests/test_gpu_parity.py validates this one), written branch-free so that a warp's lanes stay converged. ----
 //
-// Per-lane state: `cur` >= 0 = pair index to visit (INNER); cur < 0 with leaf_pos < leaf_end = triangles pending (TRI);
-// cur = YUNE_REF_DONE (-1, "a leaf with no triangles") = finished.
+// Per-lane state:
+//   cur            what the walk visits next: >= 0 pair index (an INNER step can run); < 0 a leaf reference that waits because
+//                  the lane already holds postponed triangles; YUNE_REF_DONE (-1, "a leaf with no triangles") = stack exhausted.
+//   [pend_pos, pend_end)  POSTPONED triangles: a leaf the walk reached is not tested on the spot.  Its range is parked here and
+//                  the walk goes on with the next stack entry, so a lane keeps taking part in INNER steps until it reaches a
+//                  second leaf.  TRI steps run when enough lanes hold parked triangles.  (Aila & Laine's speculative traversal;
+//                  the ncu capture of the phase-alternating version showed 18 of ~29 ray-holding lanes active in the inner body:
+//                  the others sat on a leaf waiting for the phase to turn.)  Testing a leaf later than the reference order
+//                  cannot change the result: the closest hit is order-independent (exact ties in t go by reference rank) and a
+//                  late t_best only costs a few box tests that earlier pruning would have saved.
+//   a ray is finished when cur == DONE and nothing is parked.
 #define YUNE_REF_DONE (-1)
 
 struct Lane {
     V3 o, d, inv, oi;       // oi = o * inv: fused slab test of our own tree (ACCEL 1)
     float t_best, t_prune, u, v;
-    int tri, best_pos, cur, leaf_pos, leaf_end, sp;
+    int tri, best_pos, cur, pend_pos, pend_end, sp;
     bool guard;
 };
 
-__device__ __forceinline__ void lane_enter(Lane& L, int ref)
+// The stack lives in local memory above TWO sentinel entries (stack[0] = stack[1] = DONE, sp starts at 2).  Every step loads the
+// top entries it MIGHT need up front, unconditionally and next to the node / triangle fetch; what the walk does next is then
+// a chain of selects.  (ncu, per-SASS-line view of the previous version: `if (miss) next = stack[--sp]` and the parking code
+// compiled to branches that 3 of 32 lanes took -- 15 issue slots per inner step for one pop.)
+#define YUNE_STACK_BASE 2
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
 {
-    const int x = ~ref;
-    const bool leaf = ref < 0;
-    L.cur = ref;
-    L.leaf_pos = leaf ? (x >> 4) : 0;
-    L.leaf_end = leaf ? (x >> 4) + (x & 15) : 0;
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds64(uint32_t addr)
+{
+    int2 v;
+    asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 
 __device__ __forceinline__ bool box_fast(V3 o, V3 inv, float lox, float hix, float loy, float hiy, float loz, float hiz, float& entry)
@@ -69,7 +88,7 @@ __device__ __forceinline__ bool box_own(const Lane& L, float lox, float hix, flo
     const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.t_prune));
     entry = t_min;
-    return YF_MUL(t_max, 1.000001f) >= YF_MUL(t_min, 0.999999f);
+    return YF_MUL(t_max, 1.0000021f) >= t_min;        // (t_min >= 0) at least as wide as t_max (1 + 1e-6) >= t_min (1 - 1e-6)
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
@@ -79,34 +98,37 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
     L.inv = v3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));       // correctly rounded 1/x == '1 / ray->dir' (udpt.cl:395)
     L.guard = !(fabsf(L.inv.x) < INFINITY && fabsf(L.inv.y) < INFINITY && fabsf(L.inv.z) < INFINITY);
     L.t_best = o.w; L.t_prune = o.w * 1.00001f;
-    L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = 0;
+    L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = YUNE_STACK_BASE;
     L.oi = v3(YF_MUL(L.o.x, L.inv.x), YF_MUL(L.o.y, L.inv.y), YF_MUL(L.o.z, L.inv.z));
-    float entry; bool hit = false;
-    if (ACCEL == 1) {
-        if (sc.root_ref != YUNE_REF_EMPTY) {
-            if (COUNT) wc.box++;
-            if (!L.guard) hit = box_own(L, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
-            else hit = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]) >= 0.0f;
-        }
-    } else if (sc.root_ref != YUNE_REF_EMPTY) {
+    bool hit = sc.root_ref != YUNE_REF_EMPTY;
+    if (ACCEL == 0 && hit) {
+        // the reference tests the root box first (udpt.cl:295-296).  With ACCEL 1 the boxes of our own tree only prune -- what the
+        // reference would have reached is decided per triangle by the leaf-box filter -- so the root test is skipped there.
+        float entry;
         if (COUNT) wc.box++;
         if (L.guard) { entry = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]); hit = entry >= 0.0f; }
         else hit = box_fast(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
     }
-    lane_enter(L, hit ? sc.root_ref : YUNE_REF_DONE);
+    const int ref = hit ? sc.root_ref : YUNE_REF_DONE;
+    const int x = ~ref;                                                 // a root that is a leaf is parked at once
+    L.cur = ref >= 0 ? ref : YUNE_REF_DONE;
+    L.pend_pos = ref >= 0 ? 0 : (x >> 4);
+    L.pend_end = ref >= 0 ? 0 : (x >> 4) + (x & 15);
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const float4* s_box, const int2* s_ref, WorkCount& wc)
+__device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevScene& sc, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)
 {
+    const int top1 = stack[L.sp - 1], top2 = stack[L.sp - 2];       // cur >= 0 implies sp >= YUNE_STACK_BASE
     float4 q0, q1, q2, q3;
     int ref0, ref1;
     if (L.cur < sc.n_smem_pairs) {
         // Shared-memory copy: boxes at a 48-byte stride, child refs in a separate int2 array.  With the 64-byte records of
         // the global layout every lane's q_k would fall into the same two 16-byte bank columns (64 * idx mod 128) and an
         // LDS.128 of 18 scattered lanes took ~15 wavefronts (ncu); 48 * idx mod 128 visits all eight columns.
-        const float4* p = s_box + 3 * L.cur; q0 = p[0]; q1 = p[1]; q2 = p[2];
-        const int2 rr = s_ref[L.cur]; ref0 = rr.x; ref1 = rr.y;
+        const uint32_t p = s_box + 48u * (uint32_t)L.cur;
+        q0 = lds128(p); q1 = lds128(p + 16); q2 = lds128(p + 32);
+        const int2 rr = lds64(s_ref + 8u * (uint32_t)L.cur); ref0 = rr.x; ref1 = rr.y;
     } else {
         const float4* p = sc.pairs + 4 * (size_t)L.cur; q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
         ref0 = __float_as_int(q3.x); ref1 = __float_as_int(q3.y);
@@ -127,18 +149,27 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
         h0 = h0 && (ref0 != YUNE_REF_EMPTY) && !(e0 > L.t_prune);
         h1 = h1 && (ref1 != YUNE_REF_EMPTY) && !(e1 > L.t_prune);
     }
-    const bool both = h0 && h1;
+    const bool both = h0 && h1, any = h0 || h1;
     const bool swap = !ANY && both && (e1 < e0);
-    int next = (h0 && !swap) ? ref0 : ref1;
-    if (both) stack[L.sp++] = swap ? ref0 : ref1;
-    if (!(h0 || h1)) { next = YUNE_REF_DONE; if (L.sp > 0) next = stack[--L.sp]; }
-    lane_enter(L, next);
+    const int near = (h0 && !swap) ? ref0 : ref1;                   // meaningful when any
+    const int far  = swap ? ref0 : ref1;                            // meaningful when both
+    // the next two places the walk would visit, in order
+    const int c0 = any ? near : top1;
+    const int c1 = both ? far : (any ? top1 : top2);
+    const bool park = c0 < 0 && !(L.pend_pos < L.pend_end);         // c0 is a leaf (or DONE = empty leaf) and nothing is parked
+    const int x = ~c0;
+    if (both && !park) stack[L.sp] = far;
+    L.sp += (both ? 1 : (any ? 0 : -1)) - (park ? 1 : 0);
+    L.cur = park ? c1 : c0;
+    L.pend_pos = park ? (x >> 4) : L.pend_pos;
+    L.pend_end = park ? (x >> 4) + (x & 15) : L.pend_end;
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, WorkCount& wc)
 {
-    const int pos = L.leaf_pos++;
+    const int top1 = stack[max(L.sp - 1, 0)];
+    const int pos = L.pend_pos++;
     const float4* p = sc.tris + 3 * (size_t)pos;
     const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     if (COUNT) wc.tri++;
@@ -170,47 +201,54 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
             inside = reach;
         }
     }
-    bool finished_leaf = L.leaf_pos >= L.leaf_end;
+    bool stop = false;
     if (ANY) {
-        if (inside && t > 0.0f && t < L.t_best) { L.tri = 0; L.sp = 0; finished_leaf = true; }        // udpt.cl:306-308
+        stop = inside && t > 0.0f && t < L.t_best;                                  // udpt.cl:306-308
+        L.tri = stop ? 0 : L.tri;
     } else {
         const int rank = __float_as_int(b.w);
         const bool accept = inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && rank < L.best_pos));
-        if (accept) { L.t_best = t; L.u = u; L.v = v; L.tri = __float_as_int(a.w); L.best_pos = rank; L.t_prune = t * 1.00001f; }
+        L.t_best = accept ? t : L.t_best; L.u = accept ? u : L.u; L.v = accept ? v : L.v;
+        L.tri = accept ? __float_as_int(a.w) : L.tri; L.best_pos = accept ? rank : L.best_pos;
+        L.t_prune = accept ? t * 1.00001f : L.t_prune;
     }
-    if (finished_leaf) {
-        int next = YUNE_REF_DONE;
-        if (L.sp > 0) next = stack[--L.sp];
-        lane_enter(L, next);
-    }
+    // parked range used up and the walk stands on a leaf: park that one and move on
+    const bool park = !(L.pend_pos < L.pend_end) && L.cur < 0;
+    const int x = ~L.cur;
+    L.pend_pos = park ? (x >> 4) : L.pend_pos;
+    L.pend_end = park ? (x >> 4) + (x & 15) : L.pend_end;
+    L.sp = park ? max(L.sp - 1, 0) : L.sp;
+    L.cur = park ? top1 : L.cur;
+    if (ANY) { L.cur = stop ? YUNE_REF_DONE : L.cur; L.pend_end = stop ? L.pend_pos : L.pend_end; }
 }
 
-// Drains one ray queue with a persistent warp.  Lanes hold one ray each; the warp alternates between an INNER phase and a
-// TRI phase, and stays in a phase as long as at least `phase_min` lanes still want that operation, so that every executed
-// instruction of the two hot bodies has many lanes behind it.  Lanes that finish are refilled from the queue head (one
-// atomicAdd per warp, ballot/popc ranks) once `refill_idle` of them are idle.
-#define YUNE_PHASE_MAX   8
+// Drains one ray queue with a persistent warp.  Lanes hold one ray each.  Every pass of the inner loop executes ONE operation
+// for all lanes that can take it: a TRI step when at least `tri_min` lanes hold parked triangles (or more lanes than could do
+// an INNER step), otherwise an INNER step -- followed at once by up to `inner_chain` more while at least `inner_min` lanes still can.
+// Lanes that finish are refilled from the queue head (one atomicAdd per YUNE_FETCH_CHUNK rays, ballot/popc ranks) once
+// `refill_idle` of them are idle.
 #define YUNE_FETCH_CHUNK 128
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_box, const int2* s_ref, WorkCount& wc)
+__device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)
 {
     const DevScene& sc = A.sc;
     const int lane = threadIdx.x & 31;
     const unsigned lane_lt = (1u << lane) - 1u;
     const int n = ANY ? *A.n_shadow : *A.n_extend;
     int* fetch = ANY ? A.fetch_shadow : A.fetch_extend;
-    int stack[YUNE_STACK_SIZE];
-    Lane L; L.cur = YUNE_REF_DONE; L.leaf_pos = L.leaf_end = 0; L.sp = 0; L.tri = -1; L.guard = false;
+    int stack[YUNE_STACK_SIZE + YUNE_STACK_BASE];
+    stack[0] = stack[1] = YUNE_REF_DONE;
+    Lane L; L.cur = YUNE_REF_DONE; L.pend_pos = L.pend_end = 0; L.sp = YUNE_STACK_BASE; L.tri = -1; L.guard = false;
     bool have = false;          // this lane holds a ray
     int  where = 0;             // extension: slot index; shadow: answer target
     bool exhausted = (n == 0), last_chunk = false;
     int chunk_next = 0, chunk_end = 0;            // warp-uniform: the private range of queue entries still to hand out
-    const int refill_idle = A.refill_idle, phase_min = A.phase_min;
+    const int refill_idle = A.refill_idle, tri_min = A.phase_min, inner_min = A.inner_min, inner_chain = A.inner_chain;
 
     for (;;) {
         // ---- retire finished rays ----
-        if (have && L.cur == YUNE_REF_DONE) {
+        if (have && L.cur == YUNE_REF_DONE && !(L.pend_pos < L.pend_end)) {
             if (ANY) {
                 const unsigned char vis = L.tri >= 0 ? 0 : 1;
                 if (where >= 0) A.vis_a[where] = vis; else A.vis_b[~where] = vis;
@@ -220,7 +258,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
         // ---- refill: lanes take rays from the warp's private chunk; a new chunk costs one atomic per YUNE_FETCH_CHUNK rays ----
         const unsigned idle = __ballot_sync(0xffffffffu, !have);
         if (idle == 0xffffffffu && exhausted) break;
-        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_idle)) {
+        if (!exhausted) {
             if (chunk_next >= chunk_end) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(fetch, YUNE_FETCH_CHUNK);
@@ -232,35 +270,29 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const float4* s_
             if (!have && q < chunk_end) {
                 float4 o, d;
                 if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
-                else { where = A.eq ? A.eq[q] : q; o = A.ray_o[where]; d = A.ray_d[where]; }
+                else { where = A.eq ? A.eq[q] : q; const size_t k = (size_t)where * A.ray_stride; o = A.ray_o[k]; d = A.ray_d[k]; }
                 lane_init<ANY, COUNT, ACCEL>(L, sc, o, d, wc);
                 have = true;
             }
             chunk_next = min(chunk_next + __popc(idle), chunk_end);
             exhausted = last_chunk && chunk_next >= chunk_end;
         }
-        // ---- INNER phase ----
-        bool progressed = false;
+        // ---- steps, until enough lanes have nothing left to do ----
+        const int busy_min = exhausted ? 1 : 33 - refill_idle;      // keep stepping while at least this many lanes have work
         #pragma unroll 1
-        for (int k = 0; k < YUNE_PHASE_MAX; k++) {        // bounded so that finished lanes are retired / refilled regularly
-            const bool want = L.cur >= 0;
-            if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
-            if (want) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
-            progressed = true;
-        }
-        // ---- TRI phase ----
-        #pragma unroll 1
-        for (int k = 0; k < YUNE_PHASE_MAX; k++) {
-            const bool want = L.leaf_pos < L.leaf_end;
-            if (__popc(__ballot_sync(0xffffffffu, want)) < phase_min) break;
-            if (want) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc);
-            progressed = true;
-        }
-        // ---- thin warp (fewer than phase_min lanes in either mode): one step of each kind ----
-        if (!progressed) {
-            if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
-            __syncwarp();
-            if (L.leaf_pos < L.leaf_end) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc);
+        for (;;) {
+            const bool wt = L.pend_pos < L.pend_end;
+            const unsigned bi = __ballot_sync(0xffffffffu, L.cur >= 0), bt = __ballot_sync(0xffffffffu, wt);
+            if (__popc(bi | bt) < busy_min) break;
+            const int ni = __popc(bi), nt = __popc(bt);
+            if (nt >= tri_min || nt > ni) { if (wt) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc); }
+            else {
+                if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                #pragma unroll 1
+                for (int k = 0; k < inner_chain && __popc(__ballot_sync(0xffffffffu, L.cur >= 0)) >= inner_min; k++) {
+                    if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                }
+            }
             __syncwarp();
         }
     }
@@ -281,8 +313,9 @@ __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
     __syncthreads();
 
     WorkCount wc; wc.box = 0; wc.tri = 0;
-    trace_queue<true, COUNT, ACCEL>(A, s_box, s_ref, wc);      // shadow rays: any hit
-    trace_queue<false, COUNT, ACCEL>(A, s_box, s_ref, wc);     // extension rays: closest hit
+    const uint32_t a_box = (uint32_t)__cvta_generic_to_shared(s_box), a_ref = (uint32_t)__cvta_generic_to_shared(s_ref);
+    trace_queue<true, COUNT, ACCEL>(A, a_box, a_ref, wc);      // shadow rays: any hit
+    trace_queue<false, COUNT, ACCEL>(A, a_box, a_ref, wc);     // extension rays: closest hit
     if (COUNT) {
         const int lane = threadIdx.x & 31;
         unsigned long long b = wc.box, t = wc.tri;

@@ -19,14 +19,16 @@ namespace yune {
 struct TraceArgs {
     DevScene sc;
     // extension rays (closest hit): ray = ray_o/ray_d[eq ? eq[q] : q], answer -> hit[same index]
-    const int* eq; const float4* ray_o; const float4* ray_d; float4* hit;
+    const int* eq; const float4* ray_o; const float4* ray_d; int ray_stride; float4* hit;   // ray k at ray_o/ray_d[k * ray_stride]
     const int* n_extend; int* fetch_extend;
     // shadow rays (any hit): answer -> vis_a[target] (target >= 0) or vis_b[~target]; 1 = unoccluded
     const float4* sq_o; const float4* sq_d; unsigned char* vis_a; unsigned char* vis_b;
     const int* n_shadow; int* fetch_shadow;
     Totals* tot;
     int refill_idle;      // refill a warp once this many of its lanes are idle
-    int phase_min;        // stay in the INNER / TRI phase while at least this many lanes want that operation
+    int phase_min;        // run a TRI step as soon as this many lanes hold postponed triangles
+    int inner_min;        // chain further INNER steps without a new vote while this many lanes can still take one ...
+    int inner_chain;      // ... at most this many
 };
 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st);

@@ -90,7 +90,7 @@ YUNE_HD bool box_hit_own(const RayPre& r, float lox, float hix, float loy, float
     const float t_min = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     const float t_max = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_prune));
     entry = t_min;
-    return YF_MUL(t_max, 1.000001f) >= YF_MUL(t_min, 0.999999f);
+    return YF_MUL(t_max, 1.0000021f) >= t_min;        // (t_min >= 0) at least as wide as t_max (1 + 1e-6) >= t_min (1 - 1e-6)
 }
 
 // Moller-Trumbore, two-sided, no determinant epsilon, borders included (udpt.cl:326-350).  `tri` points at the

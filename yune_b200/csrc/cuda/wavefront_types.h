@@ -55,16 +55,25 @@ struct Totals {
 #define YF_PREV_SPEC  8u    // the vertex that launched the extension ray was specular (udpt.cl:490)
 #define YF_PEND_EVT  16u    // evt_idx points at an MIS event record
 
-// Structure-of-arrays path pool: one entry per slot, every array 16-byte wide so a warp's accesses coalesce.
+// One 16-byte field of a 32-byte two-field record: element s lives at p[2 s].  Fields that are read and written by the same
+// visit of a slot share a record, so that every 32-byte DRAM sector the shade rounds touch belongs to ONE slot: with plain
+// 16-byte arrays a sector holds two neighbouring slots, the neighbour is usually in another list (or idle), and ncu showed
+// 1.9x the algorithmic traffic (half-used sector reads, read-modify-write of half-written sectors).
+struct F4Half {
+    float4* p;
+    __host__ __device__ __forceinline__ float4& operator[](size_t s) const { return p[2 * s]; }
+};
+
+// Path pool: one entry per slot; 32-byte records (ray_o, ray_d) (thr, thr_next) (col, pend_l), 16-byte arrays meta and hit.
 struct PathPool {
     int      n_slots;
-    float4*  ray_o;      // xyz origin, w = ray length so far (t of an analytic light hit, or +inf)
-    float4*  ray_d;      // xyz direction, w = int bits: index of the light that owns that length, or -1
+    F4Half   ray_o;      // xyz origin, w = ray length so far (t of an analytic light hit, or +inf)
+    F4Half   ray_d;      // xyz direction, w = int bits: index of the light that owns that length, or -1
     float4*  hit;        // t, u, v, int bits: original triangle index or -1     (written by the trace kernel)
-    float4*  thr;        // xyz throughput at the current vertex (after Russian roulette)
-    float4*  thr_next;   // xyz throughput once the in-flight extension ray lands on a surface
-    float4*  col;        // xyz radiance gathered so far for the current sample
-    float4*  pend_l;     // xyz unresolved NEE light sample (already MIS-weighted), valid with YF_PEND_L
+    F4Half   thr;        // xyz throughput at the current vertex (after Russian roulette)
+    F4Half   thr_next;   // xyz throughput once the in-flight extension ray lands on a surface
+    F4Half   col;        // xyz radiance gathered so far for the current sample
+    F4Half   pend_l;     // xyz unresolved NEE light sample (already MIS-weighted), valid with YF_PEND_L
     uint4*   meta;       // x pixel, y sample, z index of the vertex the extension ray will reach, w flags
     int*     evt_idx;    // valid with YF_PEND_EVT
     unsigned char* vis_l;   // 1 = NEE shadow ray reached the light (written by the trace kernel)

@@ -68,7 +68,9 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "pool_slots_in_use" reads back the size of the last render), "smem_nodes" (pair records staged in shared memory),
  *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
  *   0 = walk the reference tree itself), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
- *   "trace_block", "trace_blocks_per_sm", "refill_idle", "phase_min" (trace-kernel launch shape / warp scheduling),
+ *   "trace_block", "trace_blocks_per_sm" (trace-kernel launch shape), "refill_idle" (refill a warp once this many lanes are
+ *   idle), "phase_min" (run a triangle step once this many lanes hold postponed triangles), "inner_min" / "inner_chain"
+ *   (chain up to inner_chain further node steps without a new vote while inner_min lanes can take one),
  *   "shade_blocks_per_sm" (persistent shade grid; 0 = what the occupancy query returns),
  *   "isect" (0 = reference Moller-Trumbore), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */

@@ -61,3 +61,12 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
     if (work2) { work2[0] = nb; work2[1] = nt; }
     return 0;
 }
+
+// layout statistics (development aid / test): out[0..3] = n_inner, n_leaf_tris, max_depth, n_inner_ref
+extern "C" int hc_layout_info(const yune_triangle* tris, int ntri, const yune_bvh_node* nodes, int nnodes, int leaf_split, int accel, int* out)
+{
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = lay.max_depth; out[3] = lay.n_inner_ref;
+    return 0;
+}

@@ -291,6 +291,34 @@ def test_every_acceleration_mode_is_bit_exact(gpu_manager, oracle, accel, leaf_s
         m.setOption("accel", old[0]); m.setOption("leaf_split", old[1])
 
 
+def test_trace_result_independent_of_warp_scheduling(gpu_manager, oracle):
+    """The trace kernel postpones leaves (a lane parks the leaf it reaches and keeps walking) and votes per step between a
+    node step and a triangle step; when a triangle is tested relative to the rest of the walk depends on the knobs below and
+    on which rays share a warp.  The hit records must not: closest hit with exact ties by reference rank is order-free."""
+    m = gpu_manager
+    keys = ("refill_idle", "phase_min", "inner_min", "inner_chain", "trace_block")
+    old = [m.getOption(k) for k in keys]
+    try:
+        r, sc = _renderer(m, "teapot", 128, 128)
+        rng = np.random.RandomState(23); n = 100000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:500, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od6 = np.concatenate([o, d], 1).astype(np.float32)
+        tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
+        b = oracle.trace(Oracle.config("udpt"), od6, None, 0, sc.vert_data, sc.bvh)
+        sb = oracle.trace(Oracle.config("udpt"), od6, tm, 1, sc.vert_data, sc.bvh)
+        for combo in ((12, 24, 16, 8, 1024), (1, 1, 1, 0, 32), (32, 32, 33, 0, 256), (6, 8, 1, 64, 512), (20, 2, 30, 3, 1024)):
+            for k, v in zip(keys, combo):
+                m.setOption(k, v)
+            a = r.traceRays(od6)
+            assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (_bits(a[2]) == _bits(b[2])).all(), combo
+            sa = r.traceRays(od6, tm, any_hit=True)
+            assert (((sb[0] >= 0) | (sb[1] >= 0)) == (sa[0] >= 0)).all(), combo
+    finally:
+        for k, v in zip(keys, old):
+            m.setOption(k, v)
+
+
 def test_shade_result_independent_of_scheduling(gpu_manager):
     """The persistent shade kernel sorts slots into per-block lists and runs a round when a list is full; which slots meet
     in a round depends on pool size and grid size, the samples must not.  Repeated renders also exercise the flush pass and

@@ -65,7 +65,7 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "rr_threshold" (udpt.cl:6 / bdpt.cl:4), "bdpt_bounces" (bdpt.cl:7), "oren_nayar" (0/1: use
  *   udpt-primitives.cl:681-725 for pure-diffuse lobes with sigma^2 = alpha_x),
  *   and engine knobs: "pool_slots" (path slots in flight; 0 = sized per job as 512*sqrt(samples), default;
- *   "pool_slots_in_use" reads back the size of the last render), "smem_nodes" (pair records staged in shared memory),
+ *   "pool_slots_in_use" reads back the size of the last render), "smem_nodes" (pair records staged in shared memory; < 0 = all if they fit, else 2340, default),
  *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
  *   0 = walk the reference tree itself), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
  *   "trace_block", "trace_blocks_per_sm" (trace-kernel launch shape), "refill_idle" (refill a warp once this many lanes are

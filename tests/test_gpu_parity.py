@@ -296,7 +296,7 @@ def test_trace_result_independent_of_warp_scheduling(gpu_manager, oracle):
     node step and a triangle step; when a triangle is tested relative to the rest of the walk depends on the knobs below and
     on which rays share a warp.  The hit records must not: closest hit with exact ties by reference rank is order-free."""
     m = gpu_manager
-    keys = ("refill_idle", "phase_min", "inner_min", "inner_chain", "trace_block")
+    keys = ("refill_idle", "phase_min", "inner_min", "inner_chain", "trace_block", "smem_nodes")
     old = [m.getOption(k) for k in keys]
     try:
         r, sc = _renderer(m, "teapot", 128, 128)
@@ -307,7 +307,7 @@ def test_trace_result_independent_of_warp_scheduling(gpu_manager, oracle):
         tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
         b = oracle.trace(Oracle.config("udpt"), od6, None, 0, sc.vert_data, sc.bvh)
         sb = oracle.trace(Oracle.config("udpt"), od6, tm, 1, sc.vert_data, sc.bvh)
-        for combo in ((12, 24, 16, 8, 1024), (1, 1, 1, 0, 32), (32, 32, 33, 0, 256), (6, 8, 1, 64, 512), (20, 2, 30, 3, 1024)):
+        for combo in ((12, 24, 16, 8, 1024, -1), (1, 1, 1, 0, 32, 0), (32, 32, 33, 0, 256, 100), (6, 8, 1, 64, 512, 2340), (20, 2, 30, 3, 1024, 3900)):
             for k, v in zip(keys, combo):
                 m.setOption(k, v)
             a = r.traceRays(od6)

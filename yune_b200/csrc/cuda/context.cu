@@ -78,7 +78,7 @@ struct yune_ctx {
     int cap_iteration = -1, cap_max = 0; int cap_counts[4] = {0, 0, 0, 0};
 
     // options
-    int opt_pool_slots = 0, opt_smem_nodes = 2340, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
+    int opt_pool_slots = 0, opt_smem_nodes = -1, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 12, opt_phase_min = 24, opt_inner_min = 16, opt_inner_chain = 8;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
@@ -187,8 +187,11 @@ static int ensure_scene(yune_ctx* c)
 struct TraceLaunch { int grid, block; size_t smem; };
 static int trace_config(yune_ctx* c, TraceLaunch& tl)
 {
-    int n_smem = c->opt_smem_nodes < c->sc.n_inner ? c->opt_smem_nodes : c->sc.n_inner;
-    if (n_smem < 0) n_smem = 0;
+    // "smem_nodes" < 0 (default): the whole tree if it fits (the kernel variant without a global node path, +3.5 % on C2), else
+    // the first 2340 records -- a bigger staging area would take the L1 capacity that triangles and stacks need (measured).
+    int want = c->opt_smem_nodes;
+    if (want < 0) want = c->sc.n_inner <= 3900 ? c->sc.n_inner : 2340;
+    int n_smem = want < c->sc.n_inner ? want : c->sc.n_inner;
     if (n_smem > 3900) n_smem = 3900;                         // 3900 * 56 B = 213 KB < 227 KB
     c->sc.n_smem_pairs = n_smem;
     tl.smem = (size_t)n_smem * 56;                            // 48 B of boxes + 8 B of child refs per staged record

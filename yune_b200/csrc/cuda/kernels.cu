@@ -101,7 +101,7 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
     L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = YUNE_STACK_BASE;
     L.oi = v3(YF_MUL(L.o.x, L.inv.x), YF_MUL(L.o.y, L.inv.y), YF_MUL(L.o.z, L.inv.z));
     bool hit = sc.root_ref != YUNE_REF_EMPTY;
-    if (ACCEL == 0 && hit) {
+    if ((ACCEL & 1) == 0 && hit) {
         // the reference tests the root box first (udpt.cl:295-296).  With ACCEL 1 the boxes of our own tree only prune -- what the
         // reference would have reached is decided per triangle by the leaf-box filter -- so the root test is skipped there.
         float entry;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
     const int top1 = stack[L.sp - 1], top2 = stack[L.sp - 2];       // cur >= 0 implies sp >= YUNE_STACK_BASE
     float4 q0, q1, q2, q3;
     int ref0, ref1;
-    if (L.cur < sc.n_smem_pairs) {
+    if ((ACCEL & 2) || L.cur < sc.n_smem_pairs) {       // ACCEL bit 1: every pair record is staged, no global path compiled in
         // Shared-memory copy: boxes at a 48-byte stride, child refs in a separate int2 array.  With the 64-byte records of
         // the global layout every lane's q_k would fall into the same two 16-byte bank columns (64 * idx mod 128) and an
         // LDS.128 of 18 scattered lanes took ~15 wavefronts (ncu); 48 * idx mod 128 visits all eight columns.
@@ -134,7 +134,7 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
         ref0 = __float_as_int(q3.x); ref1 = __float_as_int(q3.y);
     }
     float e0, e1; bool h0, h1;
-    if (ACCEL == 1 && !L.guard) {
+    if ((ACCEL & 1) == 1 && !L.guard) {
         h0 = box_own(L, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0);
         h1 = box_own(L, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1);
     } else if (!L.guard) {
@@ -145,7 +145,7 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
         e1 = box_guarded(L.o, L.inv, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w); h1 = e1 >= 0.0f;
     }
     if (COUNT) wc.box += (ref0 != YUNE_REF_EMPTY) + (ref1 != YUNE_REF_EMPTY);
-    if (ACCEL == 0 || L.guard) {        // (ACCEL 1 folds the pruning distance into box_own; its guarded fallback does not)
+    if ((ACCEL & 1) == 0 || L.guard) {        // (ACCEL 1 folds the pruning distance into box_own; its guarded fallback does not)
         h0 = h0 && (ref0 != YUNE_REF_EMPTY) && !(e0 > L.t_prune);
         h1 = h1 && (ref1 != YUNE_REF_EMPTY) && !(e1 > L.t_prune);
     }
@@ -185,7 +185,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     const float v = YF_MUL(vdot(qvec, L.d), inv_det);
     const float t = YF_MUL(vdot(e2, qvec), inv_det);
     bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
-    if (ACCEL == 1) {
+    if ((ACCEL & 1) == 1) {
         // Would the reference have reached this triangle?  <=> the uploaded box of its reference leaf passes the reference's
         // own predicate (its ancestors' boxes contain it exactly, so they pass too).  Geometrically a ray that hits the
         // triangle always crosses that box, so the test can only ever reject in last-bit grazing cases; it is evaluated just
@@ -763,7 +763,9 @@ static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); 
 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
-    if (a.sc.accel == 1) { if (count) k_trace<true, 1><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 1><<<grid, block, smem_bytes, st>>>(a); }
+    const bool all_staged = a.sc.n_smem_pairs >= a.sc.n_inner;      // the whole tree is in shared memory: variant without the global node path
+    if (a.sc.accel == 1 && all_staged && !count) k_trace<false, 3><<<grid, block, smem_bytes, st>>>(a);
+    else if (a.sc.accel == 1) { if (count) k_trace<true, 1><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 1><<<grid, block, smem_bytes, st>>>(a); }
     else                 { if (count) k_trace<true, 0><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 0><<<grid, block, smem_bytes, st>>>(a); }
     return cudaGetLastError();
 }
@@ -773,6 +775,7 @@ cudaError_t trace_set_smem(size_t smem_bytes)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     return e;
 }
 int trace_blocks_per_sm(int block, size_t smem_bytes)

@@ -363,6 +363,10 @@ struct DenseShared {
     int visits[3];                          // rounds' entries by kind (statistics)
 };
 
+#ifndef YUNE_CLASSIFY_SPEC
+#define YUNE_CLASSIFY_SPEC 1
+#endif
+
 // phase A for one slot
 __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
 {
@@ -370,6 +374,12 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
     const bool valid = s < P.n_slots;
     const uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
     const float hit_w = valid ? P.hit[s].w : 0.0f;                             // unconditional: in flight together with meta
+    const unsigned char vis_l = valid ? P.vis_l[s] : 0;                        // likewise: saves the pending-NEE path one dependent round trip
+#if YUNE_CLASSIFY_SPEC
+    // speculative: the state a pending NEE answer needs, requested before the flags are known (one dependent trip less)
+    const float4 spec_col = valid ? P.col[s] : make_float4(0, 0, 0, 0), spec_thr = valid ? P.thr[s] : make_float4(0, 0, 0, 0),
+                 spec_pend = valid ? P.pend_l[s] : make_float4(0, 0, 0, 0);
+#endif
     const unsigned state = meta.w & YS_STATE_MASK;
     bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
     if (state == YS_TRACE || state == YS_DRAIN) {
@@ -377,7 +387,11 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
         if (tri >= 0) { to_s = A.sc.tri_class[tri] != 0; to_d = !to_s; }
         const bool pend = (meta.w & (YF_PEND_EVT | YF_PEND_L)) != 0;
         if (pend || tri < 0) {
+#if YUNE_CLASSIFY_SPEC
+            V3 col = xyz(spec_col);
+#else
             V3 col = xyz(P.col[s]);
+#endif
             bool dirty = false;
             // resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
             if (meta.w & YF_PEND_EVT) {
@@ -392,15 +406,24 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
                 if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
                 else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
                 col = vadd(col, vmul(T, nee)); dirty = true;
-            } else if ((meta.w & YF_PEND_L) && P.vis_l[s]) { col = vadd(col, vmul(xyz(P.thr[s]), xyz(P.pend_l[s]))); dirty = true; }
+            }
+#if YUNE_CLASSIFY_SPEC
+            else if ((meta.w & YF_PEND_L) && vis_l) { col = vadd(col, vmul(xyz(spec_thr), xyz(spec_pend))); dirty = true; }
+#else
+            else if ((meta.w & YF_PEND_L) && vis_l) { col = vadd(col, vmul(xyz(P.thr[s]), xyz(P.pend_l[s]))); dirty = true; }
+#endif
             if (tri < 0) {
                 if (state == YS_TRACE) {                                            // nothing hit, or a light
-                    const float4 rd = P.ray_d[s];
-                    const int lid = __float_as_int(rd.w);
+                    const int lid = (int)((meta.w >> YF_LID_SHIFT) & YF_LID_MASK) - 1;
                     if (meta.z == 0) {                                              // udpt.cl:437-446
-                        if (lid >= 0) col = (vdot(xyz(rd), A.lights.l[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
+                        if (lid >= 0) col = (vdot(xyz(P.ray_d[s]), A.lights.l[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
                         else col = v3(0.4f, 0.4f, 0.4f);
-                    } else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(P.thr[s]), A.lights.l[lid].ke));   // :490-493
+                    }
+#if YUNE_CLASSIFY_SPEC
+                    else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(spec_thr), A.lights.l[lid].ke));   // :490-493
+#else
+                    else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(P.thr[s]), A.lights.l[lid].ke));   // :490-493
+#endif
                 }
                 finish_sample(A, meta.x, col);                                      // udpt.cl:193-210
                 to_regen = true;
@@ -495,7 +518,7 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
                     has_ext = true;
                     ext_d = dir; ext_o = vadd(hp, vscale(dir, YUNE_EPS)); ext_t = INFINITY;
                     ext_lid = light_loop(lights, n_lights, ext_o, ext_d, ext_t);
-                    new_flags = YS_TRACE | (SPEC ? YF_PREV_SPEC : 0u);
+                    new_flags = YS_TRACE | (SPEC ? YF_PREV_SPEC : 0u) | ((unsigned)(ext_lid + 1) << YF_LID_SHIFT);
                     meta.z = vtx + 1;
                 }
             }
@@ -587,7 +610,7 @@ __device__ __forceinline__ void regen_round(const RenderArgs& A, const int from,
             P.eq[sh.ext_base + threadIdx.x] = s;
             P.ray_o[s] = f4(ro, rt);
             P.ray_d[s] = f4(rd, __int_as_float(rl));
-            P.meta[s] = make_uint4(pixel, sample, 0u, YS_TRACE);
+            P.meta[s] = make_uint4(pixel, sample, 0u, YS_TRACE | ((unsigned)(rl + 1) << YF_LID_SHIFT));
             P.col[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             P.thr[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
             live++;

@@ -54,6 +54,8 @@ struct Totals {
 #define YF_PEND_L     4u    // pendL/visL hold an unresolved NEE light sample
 #define YF_PREV_SPEC  8u    // the vertex that launched the extension ray was specular (udpt.cl:490)
 #define YF_PEND_EVT  16u    // evt_idx points at an MIS event record
+#define YF_LID_SHIFT  8     // bits 8..11: 1 + index of the light that bounds the in-flight extension ray (0 = none); a copy of
+#define YF_LID_MASK  15u    //   ray_d.w so that the classify phase knows it from the first load (k_shade_dense only)
 
 // One 16-byte field of a 32-byte two-field record: element s lives at p[2 s].  Fields that are read and written by the same
 // visit of a slot share a record, so that every 32-byte DRAM sector the shade rounds touch belongs to ONE slot: with plain

@@ -68,6 +68,7 @@ struct yune_ctx {
     PathPool pool{}; int pool_alloc = 0; int pool_integrator = 0;
     BdptPool bdpt{};
     IterCounters* d_ctr = nullptr; Totals* d_tot = nullptr; Totals* h_tot = nullptr;
+    unsigned char* d_chunk_live = nullptr;      // one byte per 256 path slots (RenderArgs::chunk_live)
 
     // hook scratch
     float4 *hk_o = nullptr, *hk_d = nullptr, *hk_hit = nullptr; int *hk_tri = nullptr, *hk_light = nullptr; float *hk_t = nullptr, *hk_od = nullptr, *hk_tmax = nullptr;
@@ -98,6 +99,7 @@ static void free_pool(yune_ctx* c)
 {
     PathPool& P = c->pool;
     dfree(P.ray_o.p); P.ray_d.p = nullptr; dfree(P.hit); dfree(P.thr.p); P.thr_next.p = nullptr; dfree(P.col.p); P.pend_l.p = nullptr;
+    dfree(c->d_chunk_live);
     dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
     dfree(c->bdpt.lp); dfree(c->bdpt.pend_c); dfree(c->bdpt.bmeta);
     P.n_slots = 0; c->pool_alloc = 0;
@@ -133,6 +135,7 @@ static int ensure_pool(yune_ctx* c, unsigned long long n_samples)
         Y_CUDA(c, cudaMalloc(&c->bdpt.lp, N * V * 4 * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.pend_c, N * V * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.bmeta, N * 16));
     }
     Y_CUDA(c, cudaMalloc(&P.evt, 2 * 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.evt_vis, 2 * 4 * N));
+    Y_CUDA(c, cudaMalloc(&c->d_chunk_live, N / 256 + 1));
     P.n_slots = n; c->pool_alloc = n; c->pool_integrator = c->integrator;
     return YUNE_OK;
 }
@@ -432,8 +435,10 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     Y_CUDA(c, cudaMemcpyAsync(c->d_tot, c->h_tot, sizeof(Totals), cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(IterCounters), c->stream));
     Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
+    Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
     RenderArgs a = make_args(c);
+    a.tail = 0; a.chunk_live = c->d_chunk_live;
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
     c->bdpt.bounces = c->opt_bdpt_bounces;
     TraceArgs t{};
@@ -473,6 +478,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
         }
         Y_CUDA(c, cudaMemcpyAsync(c->h_tot, c->d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
         Y_CUDA(c, cudaStreamSynchronize(c->stream));
+        a.tail = c->h_tot->next_sample >= c->h_tot->n_samples ? 1 : 0;      // the pool only drains from here on
         if (c->h_tot->live_last == 0) done = true;
         else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
     }

@@ -363,23 +363,21 @@ struct DenseShared {
     int visits[3];                          // rounds' entries by kind (statistics)
 };
 
-#ifndef YUNE_CLASSIFY_SPEC
-#define YUNE_CLASSIFY_SPEC 1
-#endif
-
 // phase A for one slot
-__device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
+// Returns whether the slot goes on to a surface round (it may stay in flight).
+__device__ __forceinline__ bool classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
 {
     const PathPool& P = A.pool;
     const bool valid = s < P.n_slots;
     const uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
     const float hit_w = valid ? P.hit[s].w : 0.0f;                             // unconditional: in flight together with meta
     const unsigned char vis_l = valid ? P.vis_l[s] : 0;                        // likewise: saves the pending-NEE path one dependent round trip
-#if YUNE_CLASSIFY_SPEC
-    // speculative: the state a pending NEE answer needs, requested before the flags are known (one dependent trip less)
-    const float4 spec_col = valid ? P.col[s] : make_float4(0, 0, 0, 0), spec_thr = valid ? P.thr[s] : make_float4(0, 0, 0, 0),
-                 spec_pend = valid ? P.pend_l[s] : make_float4(0, 0, 0, 0);
-#endif
+    // Speculative: the state a pending NEE answer needs is requested before the flags are known (one dependent round trip less
+    // for the ~half of the slots that have one).  Not while the pool drains (A.tail): most slots are DONE then and the scan
+    // itself is what an iteration costs.
+    const bool spec = valid && !A.tail;
+    float4 spec_col = make_float4(0, 0, 0, 0), spec_thr = spec_col, spec_pend = spec_col;
+    if (spec) { spec_col = P.col[s]; spec_thr = P.thr[s]; spec_pend = P.pend_l[s]; }
     const unsigned state = meta.w & YS_STATE_MASK;
     bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
     if (state == YS_TRACE || state == YS_DRAIN) {
@@ -387,11 +385,8 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
         if (tri >= 0) { to_s = A.sc.tri_class[tri] != 0; to_d = !to_s; }
         const bool pend = (meta.w & (YF_PEND_EVT | YF_PEND_L)) != 0;
         if (pend || tri < 0) {
-#if YUNE_CLASSIFY_SPEC
+            if (!spec) { spec_col = P.col[s]; spec_thr = P.thr[s]; if (meta.w & YF_PEND_L) spec_pend = P.pend_l[s]; }
             V3 col = xyz(spec_col);
-#else
-            V3 col = xyz(P.col[s]);
-#endif
             bool dirty = false;
             // resolve the NEE launched at the previous visit (udpt.cl:551-608): nee = light sample [+ BRDF sample]
             if (meta.w & YF_PEND_EVT) {
@@ -406,12 +401,7 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
                 if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
                 else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
                 col = vadd(col, vmul(T, nee)); dirty = true;
-            }
-#if YUNE_CLASSIFY_SPEC
-            else if ((meta.w & YF_PEND_L) && vis_l) { col = vadd(col, vmul(xyz(spec_thr), xyz(spec_pend))); dirty = true; }
-#else
-            else if ((meta.w & YF_PEND_L) && vis_l) { col = vadd(col, vmul(xyz(P.thr[s]), xyz(P.pend_l[s]))); dirty = true; }
-#endif
+            } else if ((meta.w & YF_PEND_L) && vis_l) { col = vadd(col, vmul(xyz(spec_thr), xyz(spec_pend))); dirty = true; }
             if (tri < 0) {
                 if (state == YS_TRACE) {                                            // nothing hit, or a light
                     const int lid = (int)((meta.w >> YF_LID_SHIFT) & YF_LID_MASK) - 1;
@@ -419,11 +409,7 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
                         if (lid >= 0) col = (vdot(xyz(P.ray_d[s]), A.lights.l[lid].normal) < 0.0f) ? v3(1.0f, 1.0f, 1.0f) : v3(0.1f, 0.1f, 0.1f);
                         else col = v3(0.4f, 0.4f, 0.4f);
                     }
-#if YUNE_CLASSIFY_SPEC
                     else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(spec_thr), A.lights.l[lid].ke));   // :490-493
-#else
-                    else if (lid >= 0 && (meta.w & YF_PREV_SPEC)) col = vadd(col, vmul(xyz(P.thr[s]), A.lights.l[lid].ke));   // :490-493
-#endif
                 }
                 finish_sample(A, meta.x, col);                                      // udpt.cl:193-210
                 to_regen = true;
@@ -433,6 +419,7 @@ __device__ __forceinline__ void classify_slot(const RenderArgs& A, const int s, 
     list_push(sh.surf[YL_DIFFUSE], &sh.n_surf[YL_DIFFUSE], to_d, s);
     list_push(sh.surf[YL_SPECULAR], &sh.n_surf[YL_SPECULAR], to_s, s);
     list_push(sh.regen, &sh.n_regen, to_regen, s);
+    return to_d || to_s;
 }
 
 // phases D / S for one list entry per thread (s < 0: idle lane of a flush round); every thread of the block calls it
@@ -630,8 +617,15 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
     int live = 0;                                   // slots this thread left in flight (TRACE or DRAIN)
     for (int chunk = blockIdx.x; ; chunk += gridDim.x) {
         const bool flush = chunk >= n_chunks;       // block-uniform: the pass after the last chunk empties the lists
-        if (!flush) classify_slot(A, chunk * YUNE_SHADE_BLOCK + tid, sh);
-        __syncthreads();
+        // While the pool drains (A.tail: every sample has been handed out) a chunk whose 256 slots had nothing in flight after the
+        // previous iteration is skipped by reading one byte.
+        if (!flush && A.tail && A.chunk_live[chunk] == 0) continue;
+        bool cont = false;
+        if (!flush) cont = classify_slot(A, chunk * YUNE_SHADE_BLOCK + tid, sh);
+        if (A.tail && !flush) {
+            const int any = __syncthreads_or(cont ? 1 : 0);
+            if (tid == 0) A.chunk_live[chunk] = any ? 1 : 0;
+        } else __syncthreads();
         YUNE_NO_UNROLL
         for (int k = 0; k < 2; k++) {
             const int n = sh.n_surf[k];

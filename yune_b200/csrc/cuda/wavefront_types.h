@@ -118,6 +118,8 @@ struct RenderArgs {
     int       oren_nayar;
     int       parity;         // iteration parity -> which IterCounters to use
     int       count_work;
+    int       tail;           // every sample of the job has been handed out: the pool only drains (k_shade_dense skips dead chunks)
+    unsigned char* chunk_live;// [ceil(n_slots / 256)] 1 = the chunk may hold a slot in flight (maintained while tail != 0)
 };
 
 } // namespace yune

@@ -70,3 +70,129 @@ extern "C" int hc_layout_info(const yune_triangle* tris, int ntri, const yune_bv
     out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = lay.max_depth; out[3] = lay.n_inner_ref;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host restatement of the DEVICE scheduling of k_trace (kernels.cu: postponed leaves, sentinel stack with the top entries
+// read up front, per-step vote between a node step and a triangle step, chained node steps, refill of idle lanes), driven for
+// simulated 32-lane warps.  The arithmetic is trace_core.h's; what this checks without a GPU is that WHEN a triangle is
+// tested relative to the rest of the walk -- which depends on the knobs and on which rays share a warp -- cannot change a
+// hit record.  It also reports the lane utilisation of the two step kinds (development aid for the knobs).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+const int REF_DONE = -1, STACK_BASE = 2;
+struct SimLane {
+    RayPre r; float t_best, t_prune, u, v;
+    int tri, best_pos, cur, pend_pos, pend_end, sp, where; bool have;
+    int stack[YUNE_STACK_SIZE + STACK_BASE];
+};
+struct SimScene { const TravLayoutHost* lay; HostPairFetch pf; HostTriFetch tf; HostLeafFetch lf; int accel; };
+
+void sim_init(SimLane& L, const SimScene& S, V3 o, V3 d, float t_in)
+{
+    L.r = make_ray(o, d);
+    L.t_best = t_in; L.t_prune = t_in * 1.00001f;
+    L.u = L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = STACK_BASE;
+    L.stack[0] = L.stack[1] = REF_DONE;
+    bool hit = S.lay->root_ref != YUNE_REF_EMPTY;
+    if (S.accel == 0 && hit) { float e; hit = box_hit(L.r, S.lay->root_lo[0], S.lay->root_hi[0], S.lay->root_lo[1], S.lay->root_hi[1], S.lay->root_lo[2], S.lay->root_hi[2], e); }
+    const int ref = hit ? S.lay->root_ref : REF_DONE;
+    const int x = ~ref;
+    L.cur = ref >= 0 ? ref : REF_DONE;
+    L.pend_pos = ref >= 0 ? 0 : (x >> 4);
+    L.pend_end = ref >= 0 ? 0 : (x >> 4) + (x & 15);
+}
+void sim_inner(SimLane& L, const SimScene& S, bool any_q)
+{
+    const int top1 = L.stack[L.sp - 1], top2 = L.stack[L.sp - 2];
+    F4 q0, q1, q2, q3; S.pf(L.cur, q0, q1, q2, q3);
+    const int ref0 = YF_ASINT(q3.x), ref1 = YF_ASINT(q3.y);
+    float e0, e1; bool h0, h1;
+    if (S.accel == 1) {
+        h0 = box_hit_own(L.r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, L.t_prune, e0);
+        h1 = box_hit_own(L.r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, L.t_prune, e1);
+    } else {
+        h0 = (ref0 != YUNE_REF_EMPTY) && box_hit(L.r, q0.x, q0.y, q0.z, q0.w, q2.x, q2.y, e0) && !(e0 > L.t_prune);
+        h1 = (ref1 != YUNE_REF_EMPTY) && box_hit(L.r, q1.x, q1.y, q1.z, q1.w, q2.z, q2.w, e1) && !(e1 > L.t_prune);
+    }
+    const bool both = h0 && h1, any = h0 || h1;
+    const bool swap = !any_q && both && (e1 < e0);
+    const int near = (h0 && !swap) ? ref0 : ref1, far = swap ? ref0 : ref1;
+    const int c0 = any ? near : top1;
+    const int c1 = both ? far : (any ? top1 : top2);
+    const bool park = c0 < 0 && !(L.pend_pos < L.pend_end);
+    const int x = ~c0;
+    if (both && !park) L.stack[L.sp] = far;
+    L.sp += (both ? 1 : (any ? 0 : -1)) - (park ? 1 : 0);
+    L.cur = park ? c1 : c0;
+    if (park) { L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15); }
+}
+void sim_tri(SimLane& L, const SimScene& S, bool any_q)
+{
+    const int top1 = L.stack[L.sp - 1 > 0 ? L.sp - 1 : 0];
+    const int pos = L.pend_pos++;
+    F4 a, b, c; S.tf(pos, a, b, c);
+    float t, u, v;
+    bool inside = tri_test(L.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v);
+    if (S.accel == 1 && inside && t > 0.0f && !(t > L.t_best)) {
+        F4 lo, hi; S.lf(YF_ASINT(c.w), lo, hi); float e;
+        inside = box_hit(L.r, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, e);
+    }
+    bool stop = false;
+    if (any_q) { stop = inside && t > 0.0f && t < L.t_best; if (stop) L.tri = 0; }
+    else {
+        const int rank = YF_ASINT(b.w);
+        if (inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && rank < L.best_pos))) {
+            L.t_best = t; L.u = u; L.v = v; L.tri = YF_ASINT(a.w); L.best_pos = rank; L.t_prune = t * 1.00001f;
+        }
+    }
+    const bool park = !(L.pend_pos < L.pend_end) && L.cur < 0;
+    if (park) { const int x = ~L.cur; L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15); L.sp = L.sp - 1 > 0 ? L.sp - 1 : 0; L.cur = top1; }
+    if (stop) { L.cur = REF_DONE; L.pend_end = L.pend_pos; }
+}
+}
+
+// knobs[4] = refill_idle, phase_min (tri_min), inner_min, inner_chain;  util[4] = inner steps, lanes in them, tri steps, lanes in them
+extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
+                             const yune_bvh_node* nodes, int nnodes, int* tri_id, float* t_hit, int accel, const int* knobs,
+                             unsigned long long* util)
+{
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
+    SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel};
+    const int refill_idle = knobs[0], tri_min = knobs[1], inner_min = knobs[2], inner_chain = knobs[3];
+    const bool any_q = any != 0;
+    std::vector<SimLane> W(32);
+    for (auto& L : W) { L.have = false; L.cur = REF_DONE; L.pend_pos = L.pend_end = 0; L.sp = STACK_BASE; }
+    int next = 0;                                   // queue head (one warp drains the whole queue here)
+    unsigned long long st[4] = {0, 0, 0, 0};
+    auto busy = [&](const SimLane& L) { return L.cur >= 0 || L.pend_pos < L.pend_end; };
+    for (;;) {
+        for (auto& L : W) if (L.have && !busy(L)) { tri_id[L.where] = L.tri; if (t_hit) t_hit[L.where] = L.t_best; L.have = false; }
+        int idle = 0; for (auto& L : W) idle += !L.have;
+        bool exhausted = next >= n;
+        if (idle == 32 && exhausted) break;
+        for (auto& L : W) if (!L.have && next < n) {                  // refill: idle lanes take the next queue entries
+            const int q = next++; const float* r = od6 + 6 * (size_t)q;
+            sim_init(L, S, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), tmax ? tmax[q] : INFINITY);
+            L.where = q; L.have = true;
+        }
+        exhausted = next >= n;
+        const int busy_min = exhausted ? 1 : 33 - refill_idle;
+        for (;;) {
+            int ni = 0, nt = 0, nb = 0;
+            for (auto& L : W) { ni += L.cur >= 0; nt += L.pend_pos < L.pend_end; nb += busy(L); }
+            if (nb < busy_min) break;
+            if (nt >= tri_min || nt > ni) { st[2]++; st[3] += nt; for (auto& L : W) if (L.pend_pos < L.pend_end) sim_tri(L, S, any_q); }
+            else {
+                st[0]++; st[1] += ni; for (auto& L : W) if (L.cur >= 0) sim_inner(L, S, any_q);
+                for (int k = 0; k < inner_chain; k++) {
+                    int c = 0; for (auto& L : W) c += L.cur >= 0;
+                    if (c < inner_min) break;
+                    st[0]++; st[1] += c; for (auto& L : W) if (L.cur >= 0) sim_inner(L, S, any_q);
+                }
+            }
+        }
+    }
+    if (util) for (int i = 0; i < 4; i++) util[i] = st[i];
+    return 0;
+}

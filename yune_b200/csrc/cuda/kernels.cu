@@ -227,7 +227,9 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 // an INNER step), otherwise an INNER step -- followed at once by up to `inner_chain` more while at least `inner_min` lanes still can.
 // Lanes that finish are refilled from the queue head (one atomicAdd per YUNE_FETCH_CHUNK rays, ballot/popc ranks) once
 // `refill_idle` of them are idle.
+#ifndef YUNE_FETCH_CHUNK
 #define YUNE_FETCH_CHUNK 128
+#endif
 
 template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)

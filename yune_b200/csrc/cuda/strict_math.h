@@ -34,7 +34,18 @@
   #define YUNE_NO_UNROLL
 #endif
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(YUNE_MEASURE_FMA)
+  /* MEASUREMENT ONLY (tools/build_variant.py fma -DYUNE_MEASURE_FMA -fmad=true): plain operators, which nvcc contracts into
+     FFMA.  Hit records are then no longer bit-identical to the oracle; the product is never built this way.  It exists to
+     price the no-contraction convention. */
+  #define YF_MUL(a, b) ((a) * (b))
+  #define YF_ADD(a, b) ((a) + (b))
+  #define YF_SUB(a, b) ((a) - (b))
+  #define YF_DIV(a, b) __fdiv_rn((a), (b))
+  #define YF_SQRT(a)   __fsqrt_rn((a))
+  #define YF_ASINT(f)  __float_as_int(f)
+  #define YF_ASFLOAT(i) __int_as_float(i)
+#elif defined(__CUDA_ARCH__)
   #define YF_MUL(a, b) __fmul_rn((a), (b))
   #define YF_ADD(a, b) __fadd_rn((a), (b))
   #define YF_SUB(a, b) __fsub_rn((a), (b))

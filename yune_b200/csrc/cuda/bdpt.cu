@@ -56,22 +56,26 @@ __device__ __forceinline__ int bdpt_classify(const RenderArgs& A, const BdptPool
 {
     const PathPool& P = A.pool;
     if (s >= P.n_slots) return -1;
+    // Everything whose address depends on s alone is requested at once (k_shade_dense's classify phase, DESIGN.md section 5: the
+    // flags -> state -> answers chain was three dependent DRAM round trips for all eight warps of the block).
+    const float4* pend_c = B.pend_c + (size_t)s * YB_MAXV;
     const uint4 meta = P.meta[s];
+    const float hit_w = P.hit[s].w;
+    const float4 col4 = P.col[s], thr4 = P.thr[s], pend_l4 = P.pend_l[s], pend_c0 = pend_c[0];
+    int4 bm = B.bmeta[s];
+    const unsigned char vis_l0 = P.vis_l[s];
     const unsigned state = meta.w & YS_STATE_MASK;
     if (state == YS_FREE) return BL_REGEN;
     if (state == YS_DONE) return -1;
-    const float hit_w = P.hit[s].w;
     const bool light_phase = (meta.w & YB_PHASE_LIGHT) != 0;
     const int tri = state == YS_TRACE ? __float_as_int(hit_w) : -1;
     if (light_phase) return tri < 0 ? BL_CAMERA : BL_LIGHT;           // missed or hit a light: the path stops before this vertex (:458)
 
-    V3 col = xyz(P.col[s]);
+    V3 col = xyz(col4);
     bool dirty = false;
-    int4 bm = B.bmeta[s];
     float epw = __int_as_float(bm.z);                                   // eye_path_weight BEFORE the vertex whose answers are pending
     if (meta.w & YB_PENDING) {
-        const V3 T = xyz(P.thr[s]);
-        const float4* pend_c = B.pend_c + (size_t)s * YB_MAXV;
+        const V3 T = xyz(thr4);
         V3 nee = v3(0, 0, 0);
         if (meta.w & YF_PEND_EVT) {
             const int e = P.evt_idx[s];
@@ -83,9 +87,9 @@ __device__ __forceinline__ int bdpt_classify(const RenderArgs& A, const BdptPool
             if (visS) nee = vadd(xyz(e0), visMV ? xyz(e1) : v3(0, 0, 0));
             else      nee = ((ef & (YE_HAS_MO | YE_MO_IS_MV)) && visMO) ? xyz(e2) : v3(0, 0, 0);
         } else if (meta.w & YF_PEND_L) {
-            if (P.vis_l[s]) nee = xyz(P.pend_l[s]);
+            if (vis_l0) nee = xyz(pend_l4);
         }
-        const V3 emission = xyz(pend_c[0]);
+        const V3 emission = xyz(pend_c0);
         // color += throughput * (emission + NEE) * eye_path_weight          (:593; NEE's own return value already adds emission once)
         col = vadd(col, vscale(vmul(T, vadd(emission, vadd(nee, emission))), epw));
         V3 sub = v3(0, 0, 0);

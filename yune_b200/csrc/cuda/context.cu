@@ -115,7 +115,7 @@ static int ensure_pool(yune_ctx* c, unsigned long long n_samples)
     if (n <= 0) {
         const double want = 512.0 * std::sqrt((double)n_samples);
         int e = (int)std::lround(std::log2(want > 1.0 ? want : 1.0));
-        const int e_max = bd ? 22 : 24;                      // a BDPT slot carries 4 KB of path vertices
+        const int e_max = bd ? 23 : 24;                      // a BDPT slot carries 4 KB of path vertices: 8 M slots = 35 GB of the 180 GB
         if (e < 16) e = 16;
         if (e > e_max) e = e_max;
         n = 1 << e;

@@ -3,11 +3,12 @@
 //   k_trace        persistent-thread BVH walk: drains the shadow queue (any-hit) then the extension queue
 //                  (closest hit).  Replaces traceRay/traverseBVH/rayTriangleIntersection/rayAabbIntersection
 //                  (kernels/legacy/udpt.cl:240-431).
-//   k_shade_udpt   "logic + material" stage, one thread per path slot: collects last iteration's NEE answers,
-//                  processes the hit (udpt.cl:433-533 `shading`), creates the NEE / MIS shadow rays
-//                  (:535-609 `evaluateDirectLighting`), samples the next direction, regenerates finished
-//                  slots with fresh camera rays (:158-238 `pathtracer`/`createRay`) and accumulates finished
-//                  samples (:193-210).  Queues are compacted with warp ballot/popc.
+//   k_shade_dense  "logic + material" stage as a persistent kernel that sorts path slots inside each block (classify /
+//                  diffuse / specular / regenerate rounds): collects last iteration's NEE answers, processes the hit
+//                  (udpt.cl:433-533 `shading`), creates the NEE / MIS shadow rays (:535-609 `evaluateDirectLighting`),
+//                  samples the next direction, regenerates finished slots with fresh camera rays (:158-238
+//                  `pathtracer`/`createRay`) and accumulates finished samples (:193-210).  Queue space: one atomic per
+//                  counter per round.
 //   k_tonemap      kernels/post-proc/tonemap.cl:14-47 on the mean image.
 //   k_hook_*       parity hooks: primary rays / arbitrary rays through the same k_trace.
 //

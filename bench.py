@@ -272,11 +272,24 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    def ncu_metric(fname, metric):
+        """A committed ncu figure of the same kernel (profiles/, captured under the profiler -- context, never a bench value)."""
+        try:
+            for line in open(os.path.join(ROOT, "profiles", fname)):
+                if metric in line:
+                    return float(line.split()[-1])
+        except Exception:
+            pass
+        return None
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "bytes_per_launch": bytes_per_launch,
                 "rays_per_launch": {"extend": ext_per_launch, "shadow": sh_per_launch},
                 "work_model": work, "trace_share_of_step": agg["trace_ms"] / max(agg["trace_ms"] + agg["shade_ms"], 1e-9),
-                "note": "scene is 0.9 MB and cache resident: this is effective bandwidth of the work model vs HBM peak (SURVEY.md 8d)"}
+                "note": "scene is 0.9 MB and cache resident: this is effective bandwidth of the work model vs HBM peak (SURVEY.md 8d); "
+                        "the kernel's real bound is the issue rate (ncu_issue_slot_pct, lanes per instruction ncu_lanes_per_inst)",
+                "ncu_issue_slot_pct": ncu_metric("r1_trace_v11_all_staged.txt", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "ncu_lanes_per_inst": ncu_metric("r1_trace_v11_all_staged.txt", "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "ncu_source": "profiles/r1_trace_v11_all_staged.txt (steady-state launch, pool full)"}
 
     # ---- second kernel of the step: k_shade_dense streams the path pool (DESIGN.md "Kernels"): algorithmic bytes per slot visit
     # = the state a visit of that kind must read and write (16-byte fields), counted by the kernel itself per kind ----
@@ -295,7 +308,10 @@ def run_ours(args):
     roofline_shade = {"bound": "hbm", "kernel": "k_shade_dense", "achieved": shade_ach, "peak": peak, "unit": "GB/s", "frac": shade_ach / peak,
                       "traffic": shade_traffic, "avg_launch_ms": shade_ms, "bytes_per_launch": shade_bytes,
                       "visits_per_launch": {"slots": agg["visits"] / n_l, "diffuse": agg["vd"] / n_l, "specular": agg["vs"] / n_l, "regenerate": agg["vr"] / n_l},
-                      "bytes_per_visit": {"classify": B_CLASSIFY, "diffuse": B_DIFFUSE, "specular": B_SPECULAR, "regenerate": B_REGEN}}
+                      "bytes_per_visit": {"classify": B_CLASSIFY, "diffuse": B_DIFFUSE, "specular": B_SPECULAR, "regenerate": B_REGEN},
+                      "ncu_issue_slot_pct": ncu_metric("r1_shade_v7_spec_classify.txt", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                      "ncu_dram_pct_of_peak": ncu_metric("r1_shade_v7_spec_classify.txt", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                      "ncu_source": "profiles/r1_shade_v7_spec_classify.txt (steady-state launch, pool full)"}
 
     # ---- CPU baseline: the reference's kernel on this box's cores, bounded sample of the same workload (N = 1 only) ----
     from tests.refbind import ncores

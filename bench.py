@@ -170,6 +170,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version / debug lines must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     tris, mats, nodes = load_scene()

@@ -166,11 +166,15 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON: whatever libraries write to file descriptor 1 meanwhile (NCCL prints its
+    # version there) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version / debug lines must not land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     tris, mats, nodes = load_scene()
@@ -339,7 +343,8 @@ def run_ours(args):
         "cpu_baseline": None if world > 1 else {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": kind,
                          "sample": "%dx%dx%dspp of the C2 workload, reference RNG" % (cw, cw, cspp)},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

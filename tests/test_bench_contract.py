@@ -14,7 +14,7 @@ OURS_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"]
 
 
-@pytest.mark.parametrize("name,n", [("bench_r1_n1.json", 1), ("bench_r1_n2.json", 2), ("bench_r1_n8.json", 8)])
+@pytest.mark.parametrize("name,n", [("bench_r1_n1.json", 1), ("bench_r1_n2.json", 2), ("bench_r1_n4.json", 4), ("bench_r1_n8.json", 8)])
 def test_committed_bench_lines_follow_the_contract(name, n):
     line = json.load(open(os.path.join(ROOT, "profiles", name)))
     for k in OURS_KEYS:

@@ -246,6 +246,11 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
     bool have = false;          // this lane holds a ray
     int  where = 0;             // extension: slot index; shadow: answer target
     bool exhausted = (n == 0), last_chunk = false;
+    // Queue entries a warp takes per atomic: YUNE_FETCH_CHUNK when the queue is long; when it is short (the drain of a job: a
+    // few thousand rays for 4736 warps) just enough to give every warp one refill, so that the rays run side by side instead
+    // of 128 at a time in a few warps (launch list of a 1-spp frame: the trace kernel took 100-200 us for a handful of rays).
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+    const int fetch_chunk = min(YUNE_FETCH_CHUNK, max(8, ((n / n_warps) + 7) & ~7));
     int chunk_next = 0, chunk_end = 0;            // warp-uniform: the private range of queue entries still to hand out
     const int refill_idle = A.refill_idle, tri_min = A.phase_min, inner_min = A.inner_min, inner_chain = A.inner_chain;
 
@@ -264,10 +269,10 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
         if (!exhausted) {
             if (chunk_next >= chunk_end) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(fetch, YUNE_FETCH_CHUNK);
+                if (lane == 0) base = atomicAdd(fetch, fetch_chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                chunk_next = base; chunk_end = min(base + YUNE_FETCH_CHUNK, n);
-                last_chunk = base + YUNE_FETCH_CHUNK >= n;
+                chunk_next = base; chunk_end = min(base + fetch_chunk, n);
+                last_chunk = base + fetch_chunk >= n;
             }
             const int q = chunk_next + __popc(idle & lane_lt);
             if (!have && q < chunk_end) {

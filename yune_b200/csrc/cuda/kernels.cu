@@ -226,7 +226,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 // Drains one ray queue with a persistent warp.  Lanes hold one ray each.  Every pass of the inner loop executes ONE operation
 // for all lanes that can take it: a TRI step when at least `tri_min` lanes hold parked triangles (or more lanes than could do
 // an INNER step), otherwise an INNER step -- followed at once by up to `inner_chain` more while at least `inner_min` lanes still can.
-// Lanes that finish are refilled from the queue head (one atomicAdd per YUNE_FETCH_CHUNK rays, ballot/popc ranks) once
+// Lanes that finish are refilled from the queue head (one atomicAdd per chunk of up to YUNE_FETCH_CHUNK rays, ballot/popc ranks) once
 // `refill_idle` of them are idle.
 #ifndef YUNE_FETCH_CHUNK
 #define YUNE_FETCH_CHUNK 128

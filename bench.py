@@ -9,7 +9,7 @@ One STEP = one full render of that workload (1.07 G samples) on every rank.
   python bench.py --impl reference [...]                      the reference's own kernel arithmetic on the host CPU cores
 
 Prints ONE JSON line (rank 0).  `value` = Msamples/s with inputs resident in HBM, timed on the device with CUDA events;
-`e2e` = the same metric through the C ABI with HOST buffers (scene upload + render + tonemap + image read-back);
+`e2e` = the same metric through the C ABI with pinned HOST buffers (scene upload + render + tonemap + image read-back);
 `roofline` = the trace kernel against the measured HBM bandwidth using the oracle's work model (DESIGN.md);
 `cpu_baseline` = the reference's kernels (oracle/_ref, else the restatement) on this box's cores, bounded sample.
 The oracle is only ever used here as the CPU baseline / work counter, never on the measured GPU path.
@@ -177,7 +177,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    def pinned(a):
+        """A page-locked copy of a numpy array (same dtype / shape), so that the e2e uploads and the read-back run from pinned host memory."""
+        t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8).pin_memory()
+        v = t.numpy()[:a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        return v, t
+
     tris, mats, nodes = load_scene()
+    (tris, _k1), (mats, _k2), (nodes, _k3) = pinned(tris), pinned(mats), pinned(nodes)
     cam = yb.default_camera()
     m = yb.CUDAManager().setup(local)
     r = yb.RendererCore(m, WIDTH, HEIGHT)
@@ -241,7 +249,7 @@ def run_ours(args):
     value = samples_per_step * args.steps / (dev_ms * 1e-3) / 1e6
 
     # ---- end-to-end through the C ABI with host buffers: upload + render + tonemap + read-back, wall clock ----
-    ldr = np.zeros((HEIGHT, WIDTH, 4), np.float32)
+    ldr, _k4 = pinned(np.zeros((HEIGHT, WIDTH, 4), np.float32))
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -200,3 +200,26 @@ def test_synthetic_c4_scene_and_in_memory_geometry(tmp_path):
     # spheres rest inside the box and do not touch each other
     p = np.stack([T["v1"], T["v2"], T["v3"]], 1)[40:, :, :3]
     assert p[..., 1].min() > -1.0039 and np.abs(p[: 1280].mean((0, 1)) - [-0.45, -0.55, -3.2]).max() < 1e-3
+
+
+def test_threaded_bvh_build_equals_sequential_and_reference(tmp_path):
+    """The builder decides the nodes of one level in parallel and splits the passes over nodes of >= 131072 primitives across
+    threads; 655 400 triangles (two icospheres of 327 680) exercise both.  Output must be byte-identical to the single-thread
+    build and -- masked for the reference's uninitialised bytes -- to the reference's own builder."""
+    from yune_b200.scenes import synthetic_c4
+    from tests.refbind import have_ref, RefHost
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    T = synthetic_c4(tris, 7)
+    assert T.size == 40 + 2 * 327680
+    a = yb.Scene().setGeometry(T, mats)
+    os.environ["YUNE_BVH_THREADS"] = "1"
+    try:
+        b = yb.Scene().setGeometry(T, mats)
+    finally:
+        del os.environ["YUNE_BVH_THREADS"]
+    assert a.bvh.tobytes() == b.bvh.tobytes() and a.bvh.size > 90000
+    if have_ref():
+        obj = str(tmp_path / "c4_7.obj")
+        write_obj(obj, T, mats)
+        rt, rm, rn, rroot = RefHost().load(obj)
+        assert tris_equal(rt, a.vert_data) and masked_nodes_equal(rn, a.bvh)

@@ -71,6 +71,21 @@ extern "C" int hc_layout_info(const yune_triangle* tris, int ntri, const yune_bv
     return 0;
 }
 
+// FNV-1a hashes of the four layout arrays (pairs, tris, shade, leaf_boxes): lets a test compare two builds of the same scene
+extern "C" int hc_layout_hash(const yune_triangle* tris, int ntri, const yune_bvh_node* nodes, int nnodes, int leaf_split, int accel, unsigned long long* out)
+{
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    auto fnv = [](const std::vector<F4>& v) {
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data());
+        for (size_t i = 0; i < v.size() * sizeof(F4); i++) { h ^= p[i]; h *= 1099511628211ull; }
+        return h;
+    };
+    out[0] = fnv(lay.pairs); out[1] = fnv(lay.tris); out[2] = fnv(lay.shade); out[3] = fnv(lay.leaf_boxes);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Host restatement of the DEVICE scheduling of k_trace (kernels.cu: postponed leaves, sentinel stack with the top entries
 // read up front, per-step vote between a node step and a triangle step, chained node steps, refill of idle lanes), driven for

@@ -126,3 +126,22 @@ def test_device_scheduling_restatement_is_order_free(hc, oracle, accel):
         assert ((occ[sfree] >= 0) == (stri[sfree] >= 0)).all(), knobs
     # the default knobs keep most lanes of a node step busy; one-lane-at-a-time settings do not (sanity of the statistics)
     assert lanes[(12, 24, 16, 8)][0] > 16 and lanes[(12, 24, 16, 8)][0] > lanes[(32, 32, 33, 0)][0]
+
+
+def test_threaded_layout_build_equals_sequential(hc):
+    """relayout.cpp builds the two subtrees of big nodes of its own SAH tree on two threads; the traversal layout (pair records
+    in breadth-first order, triangles in leaf order, shading records, leaf boxes) must not depend on it."""
+    import yune_b200 as yb
+    from yune_b200.scenes import synthetic_c4
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    sc = yb.Scene().setGeometry(synthetic_c4(tris, 6), mats)          # 163 880 triangles: the parallel path starts at 65 536
+    h = []
+    for threads in (None, "1"):
+        if threads: os.environ["YUNE_BVH_THREADS"] = threads
+        try:
+            out = np.zeros(4, np.uint64)
+            assert hc.hc_layout_hash(ptr(sc.vert_data), int(sc.vert_data.size), ptr(sc.bvh), int(sc.bvh.size), 0, 1, ptr(out)) == 0
+        finally:
+            os.environ.pop("YUNE_BVH_THREADS", None)
+        h.append(out.tolist())
+    assert h[0] == h[1] and all(x != 0 for x in h[0])

@@ -7,7 +7,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace yune {
 
@@ -96,7 +98,11 @@ struct OwnBuilder {
     std::vector<OwnTri>& t; std::vector<OwnNode> nodes; int depth_max = 0, leaf_max = 2;
     OwnBuilder(std::vector<OwnTri>& tt, int lm) : t(tt), leaf_max(lm) {}
     static float area(const float* lo, const float* hi) { float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return dx * dy + dx * dz + dy * dz; }
-    int build(int b, int e, int depth)
+    // `par_levels` > 0: the two subtrees of a big node are built by two sub-builders on two threads and their node arrays are
+    // appended (indices shifted).  The TREE is the same as in a sequential build -- every split only looks at its own range of
+    // `t` -- and the layout derived from it (breadth-first pair records, triangles in `t` order) does not depend on how the
+    // builder numbered its nodes.
+    int build(int b, int e, int depth, int par_levels = 0)
     {
         if (depth > depth_max) depth_max = depth;
         OwnNode nd; nd.left = nd.right = -1; nd.first = b; nd.count = e - b;
@@ -133,6 +139,19 @@ struct OwnBuilder {
                 mid = (int)(std::partition(t.begin() + b, t.begin() + e, [&](const OwnTri& x) { return bin_of(x) <= best; }) - t.begin());
                 if (mid == b || mid == e) mid = (b + e) / 2;
             }
+        }
+        if (par_levels > 0 && e - b >= (1 << 16)) {
+            OwnBuilder LB(t, leaf_max), RB(t, leaf_max);
+            std::thread th([&]() { LB.build(b, mid, depth + 1, par_levels - 1); });
+            RB.build(mid, e, depth + 1, par_levels - 1);
+            th.join();
+            for (OwnBuilder* sub : {&LB, &RB}) {
+                const int off = (int)nodes.size();
+                (sub == &LB ? nodes[me].left : nodes[me].right) = off;       // a sub-builder's root is its node 0
+                for (OwnNode n : sub->nodes) { if (n.left >= 0) { n.left += off; n.right += off; } nodes.push_back(n); }
+                depth_max = std::max(depth_max, sub->depth_max);
+            }
+            return me;
         }
         const int l = build(b, mid, depth + 1);
         const int r = build(mid, e, depth + 1);
@@ -198,7 +217,11 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     out.n_leaf_tris = (int)t.size();
     if (t.empty()) { out.root_ref = YUNE_REF_EMPTY; out.n_inner = out.n_inner_ref = 0; out.max_depth = 0; return true; }
     OwnBuilder B(t, leaf_max < 1 ? 2 : (leaf_max > 8 ? 8 : leaf_max));
-    const int root = B.build(0, (int)t.size(), 0);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("YUNE_BVH_THREADS")) hw = (unsigned)std::max(1, std::atoi(e));      // 1 = sequential (tests compare both)
+    int par_levels = 0;
+    while (par_levels < 5 && (2u << par_levels) <= hw) par_levels++;
+    const int root = B.build(0, (int)t.size(), 0, par_levels);
     if (B.depth_max + 2 > YUNE_STACK_SIZE) { err = "BVH deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
     out.max_depth = B.depth_max;
     for (int k = 0; k < 3; k++) { out.root_lo[k] = B.nodes[root].lo[k]; out.root_hi[k] = B.nodes[root].hi[k]; }

@@ -10,10 +10,25 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <chrono>
+#include <cstdio>
 
 namespace yune {
 
 static inline float bits(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+// fn(i) for i in [0, n) on the host's threads (independent iterations only; YUNE_BVH_THREADS=1 runs it in place)
+template <class F> static void parallel_for(size_t n, const F& fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("YUNE_BVH_THREADS")) hw = (unsigned)std::max(1, std::atoi(e));
+    const size_t n_thr = n < (1u << 16) ? 1 : std::min<size_t>(hw ? hw : 1, 32);
+    if (n_thr <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < n_thr; t++)
+        pool.emplace_back([&fn, n, n_thr, t]() { for (size_t i = n * t / n_thr, e = n * (t + 1) / n_thr; i < e; i++) fn(i); });
+    for (auto& th : pool) th.join();
+}
 
 namespace {
 
@@ -186,7 +201,10 @@ static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n
 
 static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes, TravLayoutHost& out, std::string& err, int leaf_max)
 {
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (std::getenv("YUNE_BVH_TIMING")) { auto T1 = std::chrono::steady_clock::now(); std::fprintf(stderr, "  relayout %s: %.2f s\n", what, std::chrono::duration<double>(T1 - T0).count()); T0 = T1; } };
     if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    lap("validate");
     // reference leaves: id, box, visiting rank of every triangle slot
     std::vector<OwnTri> t; t.reserve(n_tris);
     int rank = 0, n_leaves = 0;
@@ -214,6 +232,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
         }
         n_leaves++;
     }
+    lap("gather leaves");
     out.n_leaf_tris = (int)t.size();
     if (t.empty()) { out.root_ref = YUNE_REF_EMPTY; out.n_inner = out.n_inner_ref = 0; out.max_depth = 0; return true; }
     OwnBuilder B(t, leaf_max < 1 ? 2 : (leaf_max > 8 ? 8 : leaf_max));
@@ -222,12 +241,13 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     int par_levels = 0;
     while (par_levels < 5 && (2u << par_levels) <= hw) par_levels++;
     const int root = B.build(0, (int)t.size(), 0, par_levels);
+    lap("own tree");
     if (B.depth_max + 2 > YUNE_STACK_SIZE) { err = "BVH deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
     out.max_depth = B.depth_max;
     for (int k = 0; k < 3; k++) { out.root_lo[k] = B.nodes[root].lo[k]; out.root_hi[k] = B.nodes[root].hi[k]; }
     // triangles in builder order (each leaf contiguous)
     out.tris.resize((size_t)t.size() * 3);
-    for (size_t i = 0; i < t.size(); i++) {
+    parallel_for(t.size(), [&](size_t i) {
         const yune_triangle& T = tris[t[i].tri];
         V3 v1 = v3(T.v1.s[0], T.v1.s[1], T.v1.s[2]);
         V3 e1 = vsub(v3(T.v2.s[0], T.v2.s[1], T.v2.s[2]), v1);
@@ -235,7 +255,8 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
         out.tris[3 * i + 0] = {v1.x, v1.y, v1.z, bits(t[i].tri)};
         out.tris[3 * i + 1] = {e1.x, e1.y, e1.z, bits(t[i].rank)};
         out.tris[3 * i + 2] = {e2.x, e2.y, e2.z, bits(t[i].leaf)};
-    }
+    });
+    lap("triangle records");
     // pair records in breadth-first order of the inner nodes
     std::vector<int> pair_of(B.nodes.size(), -1), order;
     auto ref_of = [&](int n) { const OwnNode& nd = B.nodes[n]; return nd.left < 0 ? ~((nd.first << 4) | nd.count) : pair_of[n]; };
@@ -256,6 +277,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     }
     out.n_inner = out.n_inner_ref = (int)order.size();
     out.root_ref = ref_of(root);
+    lap("pair records");
     return true;
 }
 
@@ -347,7 +369,7 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     }
 shade_records:
     out.shade.resize((size_t)n_tris * 4);
-    for (int i = 0; i < n_tris; i++) {
+    parallel_for((size_t)n_tris, [&](size_t i) {
         const yune_triangle& t = tris[i];
         V3 n1 = vnormalize(v3(t.vn1.s[0], t.vn1.s[1], t.vn1.s[2]));       // udpt.cl:377-379
         V3 n2 = vnormalize(v3(t.vn2.s[0], t.vn2.s[1], t.vn2.s[2]));
@@ -357,7 +379,7 @@ shade_records:
         s[1] = {n2.x, n2.y, n2.z, 0.0f};
         s[2] = {n3.x, n3.y, n3.z, 0.0f};
         s[3] = {0.0f, 0.0f, 0.0f, 0.0f};
-    }
+    });
     return true;
 }
 

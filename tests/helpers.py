@@ -75,6 +75,50 @@ def write_obj(path, tris, mats, mtl_name="scene.mtl", mat_names=None):
             f.write("f %d//%d %d//%d %d//%d\n" % (b, b, b + 1, b + 1, b + 2, b + 2))
 
 
+def random_soup(rng, n, kind):
+    """Random triangle soups that stress different branches of BVH::createBVH: uniform (SAH wins), clustered (SAH loses, spatial
+    median with empty children), axis-aligned flats (the +0.2 padding of src/TriangleCPU.cpp:63-67), slivers of mixed size."""
+    T = np.zeros(n, dtype=TRI_DTYPE)
+    if kind == "uniform":
+        c = rng.uniform(-1, 1, (n, 1, 3)); p = c + rng.uniform(-0.05, 0.05, (n, 3, 3))
+    elif kind == "clustered":
+        centres = rng.uniform(-4, 4, (6, 3))
+        c = centres[rng.integers(0, 6, n)][:, None, :] + rng.normal(0, 0.02, (n, 1, 3)); p = c + rng.normal(0, 0.01, (n, 3, 3))
+    elif kind == "flats":
+        c = rng.uniform(-1, 1, (n, 1, 3)); p = c + rng.uniform(-0.1, 0.1, (n, 3, 3))
+        ax = rng.integers(0, 3, n)
+        p[np.arange(n), :, ax] = c[np.arange(n), 0, ax][:, None]            # zero extent on one axis
+    else:  # mixed sizes over 4 decades, long slivers
+        c = rng.uniform(-10, 10, (n, 1, 3)); s = 10.0 ** rng.uniform(-3, 1, (n, 1, 1))
+        p = c + s * rng.uniform(-1, 1, (n, 3, 3)) * np.array([1.0, 0.02, 1.0])
+    p = p.astype(np.float32)
+    for k, name in enumerate(("v1", "v2", "v3")):
+        T[name][:, :3] = p[:, k]; T[name][:, 3] = 1.0
+    nrm = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]).astype(np.float32)
+    for name in ("vn1", "vn2", "vn3"):
+        T[name][:, :3] = nrm
+    T["matID"] = rng.integers(0, 7, n)
+    return T
+
+
+def soup_rays(rng, T, m):
+    """m rays for a random_soup scene: origins in (and a little around) the scene box, half aimed at points inside triangles,
+    half near them; some axis-degenerate directions (NaN-guarded slabs).  Returns (origin+direction [m, 6], segment lengths)."""
+    p = np.stack([T["v1"], T["v2"], T["v3"]], 1)[..., :3].astype(np.float64)
+    lo, hi = p.min((0, 1)), p.max((0, 1))
+    o = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), (m, 3))
+    w = rng.dirichlet([1, 1, 1], m)
+    target = (p[rng.integers(0, T.size, m)] * w[:, :, None]).sum(1)
+    target[m // 2:] += rng.normal(0, 0.02, (m - m // 2, 3)) * (hi - lo)
+    d = target - o
+    k = max(m // 100, 1)
+    d[:k, 0] = 0; d[k:2 * k, 1] = 0; d[2 * k:3 * k, 2] = 0; d[3 * k:3 * k + k // 3, :2] = 0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    tm = (np.linalg.norm(target - o, axis=1) * rng.uniform(0.2, 1.5, m)).astype(np.float32)
+    return od, tm
+
+
 def luminance(img):
     return 0.212671 * img[..., 0] + 0.715160 * img[..., 1] + 0.072169 * img[..., 2]
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import yune_b200 as yb
-from tests.helpers import (REF_GEOMETRY, load_golden_scene, masked_nodes_equal, tris_equal, write_obj)
+from tests.helpers import (REF_GEOMETRY, load_golden_scene, masked_nodes_equal, random_soup, tris_equal, write_obj)
 
 
 @pytest.mark.parametrize("name", ["cornellbox", "teapot"])
@@ -225,32 +225,6 @@ def test_threaded_bvh_build_equals_sequential_and_reference(tmp_path):
         assert tris_equal(rt, a.vert_data) and masked_nodes_equal(rn, a.bvh)
 
 
-def _soup(rng, n, kind):
-    """Random triangle soups that stress different branches of BVH::createBVH: uniform (SAH wins), clustered (SAH loses, spatial
-    median with empty children), axis-aligned flats (the +0.2 padding of src/TriangleCPU.cpp:63-67), slivers of mixed size."""
-    T = np.zeros(n, dtype=load_golden_scene("cornellbox")[0].dtype)
-    if kind == "uniform":
-        c = rng.uniform(-1, 1, (n, 1, 3)); p = c + rng.uniform(-0.05, 0.05, (n, 3, 3))
-    elif kind == "clustered":
-        centres = rng.uniform(-4, 4, (6, 3))
-        c = centres[rng.integers(0, 6, n)][:, None, :] + rng.normal(0, 0.02, (n, 1, 3)); p = c + rng.normal(0, 0.01, (n, 3, 3))
-    elif kind == "flats":
-        c = rng.uniform(-1, 1, (n, 1, 3)); p = c + rng.uniform(-0.1, 0.1, (n, 3, 3))
-        ax = rng.integers(0, 3, n)
-        p[np.arange(n), :, ax] = c[np.arange(n), 0, ax][:, None]            # zero extent on one axis
-    else:  # mixed sizes over 4 decades, long slivers
-        c = rng.uniform(-10, 10, (n, 1, 3)); s = 10.0 ** rng.uniform(-3, 1, (n, 1, 1))
-        p = c + s * rng.uniform(-1, 1, (n, 3, 3)) * np.array([1.0, 0.02, 1.0])
-    p = p.astype(np.float32)
-    for k, name in enumerate(("v1", "v2", "v3")):
-        T[name][:, :3] = p[:, k]; T[name][:, 3] = 1.0
-    nrm = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]).astype(np.float32)
-    for name in ("vn1", "vn2", "vn3"):
-        T[name][:, :3] = nrm
-    T["matID"] = rng.integers(0, 7, n)
-    return T
-
-
 @pytest.mark.skipif(not os.path.isdir(REF_GEOMETRY), reason="needs the reference tree")
 @pytest.mark.parametrize("kind,n,bins,seed", [("uniform", 900, 20, 1), ("uniform", 21, 20, 2), ("uniform", 11, 20, 3), ("uniform", 10, 20, 4),
                                               ("clustered", 1500, 20, 5), ("clustered", 700, 3, 6), ("flats", 1200, 20, 7),
@@ -259,7 +233,7 @@ def test_random_soups_against_reference_host_code(ref_host, tmp_path, kind, n, b
     """Randomised geometry through the reference's compiled Scene/BVH sources and through ours: triangles, root box and every
     node (masked for the bytes the reference leaves uninitialised) must be identical -- including the leaf threshold (10 / 11
     primitives), the SAH-vs-median decision (> 20 primitives and bins > 2, src/BVH.cpp:89-128) and empty children."""
-    T = _soup(np.random.default_rng(seed), n, kind)
+    T = random_soup(np.random.default_rng(seed), n, kind)
     mats = load_golden_scene("cornellbox")[1]
     obj = str(tmp_path / "soup.obj")
     write_obj(obj, T, mats)

@@ -145,3 +145,31 @@ def test_threaded_layout_build_equals_sequential(hc):
             os.environ.pop("YUNE_BVH_THREADS", None)
         h.append(out.tolist())
     assert h[0] == h[1] and all(x != 0 for x in h[0])
+
+
+@pytest.mark.parametrize("kind,n,seed,offset", [("uniform", 1500, 31, 0.0), ("clustered", 1200, 32, 0.0), ("flats", 1000, 33, 0.0),
+                                                ("mixed", 1800, 34, 0.0), ("uniform", 1500, 35, 1000.0), ("flats", 1000, 36, 10000.0)])
+def test_random_soups_closest_and_any(hc, oracle, kind, n, seed, offset):
+    """Geometry the shipped scenes do not have -- overlapping boxes everywhere, axis-aligned flats whose boxes carry the
+    reference's +0.2 padding, slivers over four decades of size, empty children -- walked by the reference's breadth-first
+    queue (oracle) and by the product's three walks (reference tree, refined leaves, own tree + leaf-box filter): same hit
+    record bit for bit, same occlusion answer.  `offset` moves the scene away from the origin (coordinates of 1e3 / 1e4 with
+    0.05-sized triangles: the own-tree slab test o * (1/d) cancels heavily and still must never lose a reference hit)."""
+    import yune_b200 as yb
+    from tests.helpers import random_soup, soup_rays
+    rng = np.random.default_rng(seed)
+    T = random_soup(rng, n, kind)
+    for k in ("v1", "v2", "v3"):
+        T[k][:, :3] += np.float32([offset, -offset / 2, 2 * offset])
+    sc = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
+    tris, nodes = sc.vert_data, sc.bvh
+    od, tm = soup_rays(rng, T, 30000)
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    assert (otri >= 0).mean() > 0.3
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, nodes)
+    for leaf_split, accel in ((0, 0), (2, 0), (0, 1)):
+        tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
+        assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)
+        atri, _, _, _ = _trace(hc, od, tm, 1, tris, nodes, leaf_split, accel)
+        assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all(), (leaf_split, accel)

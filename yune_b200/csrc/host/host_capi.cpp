@@ -50,22 +50,24 @@ int yune_scene_reload_mat_file(yune_scene* s)
     try { s->scene.reloadMatFile(); } catch (const std::exception& e) { s->err = e.what(); return -1; }
     return 0;
 }
-int yune_scene_num_triangles(const yune_scene* s) { return (int)s->scene.vert_data.size(); }
-int yune_scene_num_materials(const yune_scene* s) { return (int)s->scene.mat_data.size(); }
-int yune_scene_num_bvh_nodes(const yune_scene* s) { return (int)s->scene.bvh.gpu_node_list.size(); }
-const yune_triangle* yune_scene_vert_data(const yune_scene* s) { return s->scene.vert_data.data(); }
-const yune_material* yune_scene_mat_data(const yune_scene* s) { return s->scene.mat_data.data(); }
-yune_material* yune_scene_mat_data_mut(yune_scene* s) { return s->scene.mat_data.data(); }
-const yune_bvh_node* yune_scene_bvh_data(const yune_scene* s) { return s->scene.bvh.gpu_node_list.data(); }
-void yune_scene_root_aabb(const yune_scene* s, yune_aabb* out) { *out = s->scene.root; }
+int yune_scene_num_triangles(const yune_scene* s) { return s ? (int)s->scene.vert_data.size() : 0; }
+int yune_scene_num_materials(const yune_scene* s) { return s ? (int)s->scene.mat_data.size() : 0; }
+int yune_scene_num_bvh_nodes(const yune_scene* s) { return s ? (int)s->scene.bvh.gpu_node_list.size() : 0; }
+const yune_triangle* yune_scene_vert_data(const yune_scene* s) { return s ? s->scene.vert_data.data() : nullptr; }
+const yune_material* yune_scene_mat_data(const yune_scene* s) { return s ? s->scene.mat_data.data() : nullptr; }
+yune_material* yune_scene_mat_data_mut(yune_scene* s) { return s ? s->scene.mat_data.data() : nullptr; }
+const yune_bvh_node* yune_scene_bvh_data(const yune_scene* s) { return s ? s->scene.bvh.gpu_node_list.data() : nullptr; }
+void yune_scene_root_aabb(const yune_scene* s, yune_aabb* out) { if (s && out) *out = s->scene.root; }
 
 void yune_camera_default(float fov, yune_cam* out)
 {
+    if (!out) return;
     yune::Camera cam(fov);
     cam.setBuffer(out);
 }
 void yune_camera_set(const float side[4], const float up[4], const float look_at[4], const float eye[4], float fov, yune_cam* out)
 {
+    if (!side || !up || !look_at || !eye || !out) return;
     yune::Camera cam(fov);
     cam.setViewMatrix(yune::Vec4{side[0], side[1], side[2], side[3]}, yune::Vec4{up[0], up[1], up[2], up[3]},
                       yune::Vec4{look_at[0], look_at[1], look_at[2], look_at[3]}, yune::Vec4{eye[0], eye[1], eye[2], eye[3]});
@@ -78,10 +80,10 @@ yune_camera* yune_camera_create(float fov) { return new (std::nothrow) yune_came
 void yune_camera_destroy(yune_camera* c) { delete c; }
 void yune_camera_set_orientation(yune_camera* c, const float dir[4], float pitch, float yaw)
 {
-    c->cam.setOrientation(yune::Vec4{dir[0], dir[1], dir[2], dir[3]}, pitch, yaw);
+    if (c && dir) c->cam.setOrientation(yune::Vec4{dir[0], dir[1], dir[2], dir[3]}, pitch, yaw);
 }
-void yune_camera_reset(yune_camera* c) { c->cam.resetCamera(); }
-int  yune_camera_is_changed(const yune_camera* c) { return c->cam.is_changed ? 1 : 0; }
-void yune_camera_set_buffer(yune_camera* c, yune_cam* out) { c->cam.setBuffer(out); }
+void yune_camera_reset(yune_camera* c) { if (c) c->cam.resetCamera(); }
+int  yune_camera_is_changed(const yune_camera* c) { return (c && c->cam.is_changed) ? 1 : 0; }
+void yune_camera_set_buffer(yune_camera* c, yune_cam* out) { if (c && out) c->cam.setBuffer(out); }
 
 }

@@ -54,7 +54,7 @@ int yune_create_postproc_program(yune_ctx* ctx, const char* kernel, const char* 
 /* ---- buffer set-up: CLManager::setup*Buffer (src/CLManager.cpp:381-484) = kernel args 2-7 ---- */
 int yune_setup_vertex_buffer(yune_ctx* ctx, const yune_triangle* tris, int n_triangles);   /* args 3,4 */
 int yune_setup_mat_buffer(yune_ctx* ctx, const yune_material* mats, int n_materials);      /* arg 5    */
-int yune_setup_bvh_buffer(yune_ctx* ctx, const yune_bvh_node* nodes, int n_nodes);         /* args 6,7; n = 0: no BVH is NOT supported (udpt.cl:280-284 brute force) */
+int yune_setup_bvh_buffer(yune_ctx* ctx, const yune_bvh_node* nodes, int n_nodes);         /* args 6,7; n = 0 (nodes may be NULL): the reference's brute-force mode, udpt.cl:280-284 -- same hit records (every triangle, index order, no box test), answered by a walk over our own tree */
 int yune_setup_camera_buffer(yune_ctx* ctx, const yune_cam* cam);                          /* arg 2    */
 int yune_setup_image_buffers(yune_ctx* ctx, int width, int height);                        /* args 0,1 */
 /* Replaces the kernels' __constant Quad light_sources[LIGHT_SIZE]; n in [1, 8].  n = 0 restores the

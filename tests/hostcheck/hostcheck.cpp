@@ -32,6 +32,7 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
 {
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    accel = lay.accel;                               // bvh_size == 0 (brute-force mode) always walks the own tree
     HostLeafFetch lf{lay.leaf_boxes.data()};
     HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()};
     LightDev L[YUNE_MAX_LIGHTS];
@@ -173,6 +174,7 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
 {
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
+    accel = lay.accel;
     SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel};
     const int refill_idle = knobs[0], tri_min = knobs[1], inner_min = knobs[2], inner_chain = knobs[3];
     const bool any_q = any != 0;

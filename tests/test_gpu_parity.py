@@ -407,7 +407,8 @@ def test_error_behaviour_on_device(gpu_manager):
         assert m.setupVertexBuffer(tris) and m.setupMatBuffer(mats) and m.setupBVHBuffer(bad) and m.setupImageBuffers(16, 16)
         m.setupCameraBuffer(yb.default_camera())
         assert r._lib.yune_render(m._ctx, 0, 1, 1, 0, 1) == -4            # malformed BVH rejected at upload, not traversed
-        assert m.setupBVHBuffer(nodes[:0]) is False                        # bvh_size == 0 (brute force) unsupported
+        assert m.setupBVHBuffer(nodes[:0]) is True                         # bvh_size == 0 = the reference's brute-force mode
+        assert r._lib.yune_render(m._ctx, 0, 1, 1, 0, 1) == 0
     finally:
         m.close()
 
@@ -461,3 +462,36 @@ def test_random_soups_bit_exact(gpu_manager, oracle, kind, n, seed):
             assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all(), accel
     finally:
         m.setOption("accel", 1)
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
+def test_brute_force_mode_bvh_size_zero(gpu_manager, oracle, scene):
+    """Kernel arg 6 bvh_size == 0 (udpt.cl:280-284: every triangle in index order, no box tests): hit records equal to the
+    oracle's loop bit for bit, same occlusion answers, one sample per pixel equal to the oracle's for the same (seed, pixel,
+    sample).  tests/test_traversal_hostcheck.py pins the same mode on the CPU, also against the compiled reference kernel."""
+    m = gpu_manager
+    sc = golden_scene_object(scene)
+    sc.bvh = sc.bvh[:0]
+    W = 48
+    r = yb.RendererCore(m, W, W)
+    assert m.createRenderProgram("udpt.cl") and r.setup(sc), m.last_message
+    cfg = Oracle.config("udpt")
+    tri, light, t = r.tracePrimary(1, 77)
+    otri, olight, ot, _, _ = oracle.primary(cfg, CAM, sc.vert_data, sc.bvh, 77, 1, W, W)
+    assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all()
+    rng = np.random.default_rng(78); n = 20000 if scene == "teapot" else 200000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d[:300, 0] = 0; d[300:600, 1] = 0; d[600:900, 2] = 0
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    tm = rng.uniform(0.01, 2.5, n).astype(np.float32)
+    a = r.traceRays(od); b = oracle.trace(cfg, od, None, 0, sc.vert_data, sc.bvh)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (_bits(a[2]) == _bits(b[2])).all()
+    sa = r.traceRays(od, tm, any_hit=True); sb = oracle.trace(cfg, od, tm, 1, sc.vert_data, sc.bvh)
+    assert (((sb[0] >= 0) | (sb[1] >= 0)) == (sa[0] >= 0)).all()
+    r.seed = 9
+    m.check(r._lib.yune_render(r._ctx, 0, 1, 1, r.seed, 1))
+    ours = r.readSum()
+    ref = oracle.samples(Oracle.config("udpt", rng_mode=1, seed=9), CAM, sc.vert_data, sc.mat_data, sc.bvh, W, W, 0)
+    close = (np.abs(ours[..., :3] - ref[..., :3]) <= 1e-3 * np.abs(ref[..., :3]) + 1e-6).all(-1)
+    assert close.mean() >= 0.99, close.mean()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from tests.helpers import ROOT, GOLDEN, load_golden_scene
-from tests.refbind import Oracle, default_cam_array, ptr
+from tests.refbind import NODE_DTYPE, Oracle, default_cam_array, ptr
 
 LIGHT_UDPT = np.zeros(32, np.float32)
 LIGHT_UDPT[0:4] = [-0.1979, 0.92, -3.1972, 1]; LIGHT_UDPT[4:8] = [0, -1, 0, 0]; LIGHT_UDPT[8:12] = [16, 16, 16, 0]
@@ -173,3 +173,44 @@ def test_random_soups_closest_and_any(hc, oracle, kind, n, seed, offset):
         assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)
         atri, _, _, _ = _trace(hc, od, tm, 1, tris, nodes, leaf_split, accel)
         assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all(), (leaf_split, accel)
+
+
+@pytest.mark.parametrize("scene", ["cornellbox", "teapot", "soup"])
+def test_brute_force_mode_bvh_size_zero(hc, oracle, scene):
+    """Kernel arg 6 bvh_size == 0: the reference intersects every triangle in index order with no box test at all
+    (udpt.cl:280-284).  The product answers that mode with its own tree and a filter that always passes; hit records must be
+    those of the reference's loop bit for bit -- they differ from the BVH mode's where a box test rejected a grazing hit or
+    an exact tie went to the other triangle -- and the occlusion answers must agree."""
+    from tests.helpers import random_soup, soup_rays
+    from tests.refbind import have_ref, RefKernels
+    rng = np.random.default_rng(77)
+    if scene == "soup":
+        tris = random_soup(rng, 1200, "flats")
+        od, tm = soup_rays(rng, tris, 20000)
+    else:
+        tris, mats, nodes = load_golden_scene(scene)
+        n = 6000 if scene == "teapot" else 60000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:300, 0] = 0; d[300:600, 1] = 0; d[600:900, 2] = 0
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od = np.concatenate([o, d], 1).astype(np.float32)
+        tm = rng.uniform(0.01, 2.5, n).astype(np.float32)
+    none = np.zeros(0, NODE_DTYPE)
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, none)
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, none)
+    if have_ref():      # the oracle's loop is the reference's: same answers from the compiled kernel text
+        rtri, rlight, rt = RefKernels().trace("udpt", od, None, 0, tris, none)
+        assert (rtri == otri).all() and (rlight == olight).all() and (rt.view(np.uint32) == ot.view(np.uint32)).all()
+    for accel in (1, 0):                                  # the option is ignored in this mode (there is no reference tree to walk)
+        tri, light, t, work = _trace(hc, od, None, 0, tris, none, 0, accel)
+        assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all()
+        assert work[1] < 0.2 * od.shape[0] * tris.size        # and nowhere near n_rays x n_triangles tests
+        atri, _, _, _ = _trace(hc, od, tm, 1, tris, none, 0, accel)
+        assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
+    # the device scheduling restatement on the same layout
+    tri_w = np.zeros(od.shape[0], np.int32); t_w = np.zeros(od.shape[0], np.float32)
+    knobs = np.array([12, 24, 16, 8], np.int32)
+    assert hc.hc_trace_warp(od.shape[0], ptr(od), None, 0, ptr(tris), int(tris.size), None, 0, ptr(tri_w), ptr(t_w), 1, ptr(knobs), None) == 0
+    free = olight < 0
+    assert (tri_w[free] == otri[free]).all()

@@ -329,8 +329,8 @@ int yune_setup_mat_buffer(yune_ctx* c, const yune_material* mats, int n)
 int yune_setup_bvh_buffer(yune_ctx* c, const yune_bvh_node* nodes, int n)
 {
     if (!c || n < 0 || (n > 0 && !nodes)) { if (c) c->err = "yune_setup_bvh_buffer: bad arguments"; return YUNE_ERR_INVALID; }
-    if (n == 0) Y_FAIL(c, YUNE_ERR_INVALID, "bvh_size == 0 (brute-force intersection, udpt.cl:280-284) is not supported; build a BVH");
-    c->h_nodes.assign(nodes, nodes + n);
+    // n == 0: the reference's brute-force mode (kernel arg 6 bvh_size == 0, udpt.cl:280-284) -- same hits, see relayout.cpp
+    if (n > 0) c->h_nodes.assign(nodes, nodes + n); else c->h_nodes.clear();
     c->have_nodes = true; c->layout_dirty = true;
     return YUNE_OK;
 }

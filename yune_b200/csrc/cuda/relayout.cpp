@@ -203,11 +203,34 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
 {
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (std::getenv("YUNE_BVH_TIMING")) { auto T1 = std::chrono::steady_clock::now(); std::fprintf(stderr, "  relayout %s: %.2f s\n", what, std::chrono::duration<double>(T1 - T0).count()); T0 = T1; } };
-    if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    const bool brute = n_nodes == 0;       // no reference tree: the reference tests every triangle in index order (udpt.cl:280-284)
+    if (!brute && !validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
     lap("validate");
     // reference leaves: id, box, visiting rank of every triangle slot
     std::vector<OwnTri> t; t.reserve(n_tris);
     int rank = 0, n_leaves = 0;
+    auto padded_bounds = [&](OwnTri& x) {
+        const yune_triangle& T = tris[x.tri];
+        float ext = 0.0f, mag = 0.0f;
+        for (int k = 0; k < 3; k++) {
+            x.lo[k] = std::min(T.v1.s[k], std::min(T.v2.s[k], T.v3.s[k]));
+            x.hi[k] = std::max(T.v1.s[k], std::max(T.v2.s[k], T.v3.s[k]));
+            x.c[k] = 0.5f * (x.lo[k] + x.hi[k]);
+            ext = std::max(ext, x.hi[k] - x.lo[k]); mag = std::max(mag, std::max(std::fabs(x.lo[k]), std::fabs(x.hi[k])));
+        }
+        const float pad = 2.0e-3f * ext + 4.0e-6f * mag + 1.0e-30f;      // same conservative margin as the leaf refinement
+        for (int k = 0; k < 3; k++) { x.lo[k] -= pad; x.hi[k] += pad; }
+    };
+    if (brute) {
+        // One pseudo-leaf whose box every ray passes (the filter 'would the reference have reached this triangle?' is always
+        // yes), visiting rank = triangle index (exact ties in t go to the lower index, as in the reference's loop).
+        const float big = 3.4028234e38f;
+        out.leaf_boxes.push_back({-big, -big, -big, 0.0f});
+        out.leaf_boxes.push_back({big, big, big, 0.0f});
+        t.resize(n_tris);
+        parallel_for((size_t)n_tris, [&](size_t i) { OwnTri& x = t[i]; x.tri = (int)i; x.rank = (int)i; x.leaf = 0; padded_bounds(x); });
+        n_leaves = 1;
+    }
     for (int i = 0; i < n_nodes; i++) {
         const yune_bvh_node& nd = nodes[i];
         if (!(nd.child_idx == -1 && nd.vert_len > 0)) continue;
@@ -218,16 +241,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
             const int id = nd.vert_list[j];
             if (id < 0 || id >= n_tris) { err = "leaf references a triangle out of range"; return false; }
             OwnTri x; x.tri = id; x.rank = rank++; x.leaf = n_leaves;
-            const yune_triangle& T = tris[id];
-            float ext = 0.0f, mag = 0.0f;
-            for (int k = 0; k < 3; k++) {
-                x.lo[k] = std::min(T.v1.s[k], std::min(T.v2.s[k], T.v3.s[k]));
-                x.hi[k] = std::max(T.v1.s[k], std::max(T.v2.s[k], T.v3.s[k]));
-                x.c[k] = 0.5f * (x.lo[k] + x.hi[k]);
-                ext = std::max(ext, x.hi[k] - x.lo[k]); mag = std::max(mag, std::max(std::fabs(x.lo[k]), std::fabs(x.hi[k])));
-            }
-            const float pad = 2.0e-3f * ext + 4.0e-6f * mag + 1.0e-30f;      // same conservative margin as the leaf refinement
-            for (int k = 0; k < 3; k++) { x.lo[k] -= pad; x.hi[k] += pad; }
+            padded_bounds(x);
             t.push_back(x);
         }
         n_leaves++;
@@ -287,12 +301,15 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
                      TravLayoutHost& out, std::string& err, int leaf_split, int accel)
 {
     out = TravLayoutHost();
-    if (n_nodes <= 0 || !nodes) { err = "no BVH nodes (brute-force mode, bvh_size == 0, is not supported)"; return false; }
+    if (n_nodes < 0 || (n_nodes > 0 && !nodes)) { err = "bad BVH buffer"; return false; }
     if (n_tris < 0 || (n_tris > 0 && !tris)) { err = "bad triangle buffer"; return false; }
     if (n_tris >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
+    // bvh_size == 0 is the reference's brute-force mode (udpt.cl:280-284: every triangle, in index order, no box tests).  The
+    // result is reproduced by the own-tree walk with a filter that always passes; only the cost differs (a tree walk here).
+    if (n_nodes == 0) accel = 1;
     out.n_tris = n_tris; out.accel = accel;
 
-    if (!validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    if (n_nodes > 0 && !validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
     if (accel == 1) {
         if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err, leaf_split)) return false;
         goto shade_records;

@@ -57,6 +57,9 @@ struct TravLayoutHost {
 //            exactly (getExtent / refit, src/BVH.cpp:218-278) and float subtraction / multiplication are monotone, so
 //            "the leaf's box passes" implies "every ancestor's box passes" (rays with a non-finite 1/d excepted).
 //            Same hit records, roughly half the box tests and a third of the triangle tests.
+//
+// n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
+//        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
                      TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0);
 

@@ -35,6 +35,15 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def write_image(path, rgba):
+    """Encode a bottom-up RGBA float image (H, W, 4) by the extension of `path` (.hdr .pfm .png .jpg .ppm): the product's own
+    encoders behind yune_write_image (include/yune_host.h).  Returns True on success."""
+    a = np.ascontiguousarray(rgba, np.float32)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("write_image expects an (H, W, 4) float image")
+    return _native.load().yune_write_image(path.encode(), _ptr(a), int(a.shape[1]), int(a.shape[0])) == 0
+
+
 def default_camera(y_fov=60.0):
     """The reference's default camera (src/Camera.cpp:93-103) as the 80-byte Cam record."""
     cam = np.zeros(1, CAM_DTYPE)
@@ -317,6 +326,20 @@ class RendererCore:
 
     def readLDR(self):
         return self._read(self._lib.yune_read_ldr)
+
+    def saveImage(self, save_fn, save_ext=None):
+        """RendererCore::saveImage (src/RendererCore.cpp:608-646): ".hdr" (and ".pfm") from the float image, ".png" / ".jpg"
+        (and ".ppm") from the 8-bit view of the tonemapped one.  Returns False with cl_manager.last_message set on failure."""
+        ext = (save_ext or os.path.splitext(save_fn)[1]).lower()
+        if ext in (".png", ".jpg", ".jpeg", ".ppm"):
+            self.postProcess()
+            img = self.readLDR()
+        elif ext in (".hdr", ".pfm"):
+            img = self.readHDR()
+        else:
+            self.cl_manager.last_message = "unsupported image extension (use .hdr, .png, .jpg, .pfm or .ppm)"
+            return False
+        return write_image(save_fn if save_ext is None or save_fn.lower().endswith(ext) else save_fn + ext, img)
 
     def writeSum(self, img):
         a = np.ascontiguousarray(img, np.float32)

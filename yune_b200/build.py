@@ -13,7 +13,7 @@ CSRC = os.path.join(ROOT, "yune_b200", "csrc")
 LIB = os.path.join(ROOT, "yune_b200", "libyune_b200.so")
 
 CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu"]
-HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/RendererCore.cpp", "host/host_capi.cpp"]
+HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/RendererCore.cpp", "host/ImageIO.cpp", "host/host_capi.cpp"]
 APP = os.path.join(ROOT, "yune_b200", "yune_headless")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

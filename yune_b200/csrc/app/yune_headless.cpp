@@ -1,7 +1,7 @@
 // yune_headless -- command-line front end of the headless renderer (replaces RendererGUI's menus, src/RendererGUI.cpp:
 // "Load OBJ", kernel file, window size, GI check, "Save At Samples").  Usage:
 //   yune_headless --obj scene.obj [--kernel udpt.cl|bdpt.cl] [--opts -DMIS] [--width 1024 --height 1024] [--spp 64]
-//                 [--seed 12345] [--no-gi] [--bins 20] [--fov 60] [--out image.hdr|.pfm|.ppm] [--device 0]
+//                 [--seed 12345] [--no-gi] [--bins 20] [--fov 60] [--out image.hdr|.png|.jpg|.pfm|.ppm] [--device 0]
 #include "RendererCore.h"
 
 #include <cstdio>
@@ -25,7 +25,7 @@ int main(int argc, char** argv)
         else if (a == "--fov") fov = (float)std::atof(next()); else if (a == "--out") out = next(); else if (a == "--no-gi") gi = false;
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
-    if (obj.empty()) { std::cerr << "usage: yune_headless --obj scene.obj [--kernel udpt.cl] [--opts -DMIS] [--width W --height H] [--spp N] [--out image.hdr]\n"; return 2; }
+    if (obj.empty()) { std::cerr << "usage: yune_headless --obj scene.obj [--kernel udpt.cl] [--opts -DMIS] [--width W --height H] [--spp N] [--out image.hdr|.png|.jpg]\n"; return 2; }
     try {
         yune::CUDAManager manager;
         manager.setup(device);                                           // throws without a B200: there is no CPU path

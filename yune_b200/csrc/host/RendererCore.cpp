@@ -1,4 +1,5 @@
 #include "RendererCore.h"
+#include "ImageIO.h"
 
 #include <cmath>
 #include <cstdint>
@@ -115,43 +116,20 @@ namespace yune
         return true;
     }
 
-    bool RendererCore::saveImage(const std::string& path)
+    bool RendererCore::saveImage(const std::string& path) { return saveImage(path, imageExtension(path)); }
+
+    // RendererCore::saveImage(save_fn, save_ext) (src/RendererCore.cpp:608-646): ".hdr" from the float image, ".png" / ".jpg" from
+    // the 8-bit view of the tonemapped one (the reference reads COLOR_ATTACHMENT3, the post-processing output).
+    bool RendererCore::saveImage(const std::string& save_fn, const std::string& save_ext)
     {
-        const size_t n = (size_t)width * height;
-        std::vector<float> img(n * 4);
-        const std::string ext = path.size() >= 4 ? path.substr(path.size() - 4) : "";
-        const bool ldr = ext == ".ppm";
-        if (ldr) { if (!postProcess()) return false; }
+        std::vector<float> img((size_t)width * height * 4);
+        const bool ldr = imageIsLdr(save_ext);
+        if (!ldr && !imageIsHdr(save_ext)) { cl_manager.last_message = "unsupported image extension (use .hdr, .png, .jpg, .pfm or .ppm)"; return false; }
+        if (ldr && !postProcess()) return false;
         const int rc = ldr ? yune_read_ldr(cl_manager.ctx, img.data()) : yune_read_hdr(cl_manager.ctx, img.data());
         if (rc != YUNE_OK) { cl_manager.last_message = yune_last_error(cl_manager.ctx); return false; }
-        std::ofstream f(path, std::ios::binary);
-        if (!f.is_open()) { cl_manager.last_message = "Error opening image file for writing."; return false; }
-        if (ext == ".pfm") {                                   // bottom-up float RGB, little endian: our row order as is
-            f << "PF\n" << width << " " << height << "\n-1.0\n";
-            for (size_t i = 0; i < n; i++) f.write(reinterpret_cast<const char*>(&img[4 * i]), 12);
-        } else if (ext == ".hdr") {                            // Radiance RGBE, flat (no RLE), top-down
-            f << "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y " << height << " +X " << width << "\n";
-            for (int y = height - 1; y >= 0; y--)
-                for (int x = 0; x < width; x++) {
-                    const float* p = &img[4 * ((size_t)y * width + x)];
-                    const float m = std::fmax(p[0], std::fmax(p[1], p[2]));
-                    unsigned char px[4] = {0, 0, 0, 0};
-                    if (m > 1e-32f && std::isfinite(m)) {
-                        int e; const float s = std::frexp(m, &e) * 256.0f / m;
-                        px[0] = (unsigned char)(p[0] * s); px[1] = (unsigned char)(p[1] * s); px[2] = (unsigned char)(p[2] * s); px[3] = (unsigned char)(e + 128);
-                    }
-                    f.write(reinterpret_cast<const char*>(px), 4);
-                }
-        } else if (ldr) {                                      // 8-bit tonemapped, top-down
-            f << "P6\n" << width << " " << height << "\n255\n";
-            for (int y = height - 1; y >= 0; y--)
-                for (int x = 0; x < width; x++) {
-                    const float* p = &img[4 * ((size_t)y * width + x)];
-                    unsigned char px[3];
-                    for (int k = 0; k < 3; k++) { float v = p[k]; v = v != v ? 0.0f : (v < 0 ? 0 : (v > 1 ? 1 : v)); px[k] = (unsigned char)(v * 255.0f + 0.5f); }
-                    f.write(reinterpret_cast<const char*>(px), 3);
-                }
-        } else { cl_manager.last_message = "unsupported image extension (use .hdr, .pfm or .ppm)"; return false; }
+        std::string err;
+        if (!writeImage(save_fn, save_ext, img.data(), width, height, err)) { cl_manager.last_message = err; return false; }
         return true;
     }
 }

@@ -45,7 +45,8 @@ namespace yune
             bool postProcess();
             /** src/RendererCore.cpp:608-646 without stb: ".hdr" (Radiance RGBE), ".pfm" (float RGB), ".ppm" (8-bit, tonemapped). Rows are
              *  flipped to top-down on the way out like the reference does. */
-            bool saveImage(const std::string& path);
+            bool saveImage(const std::string& path);                                      /**< format by extension: .hdr .png .jpg (.pfm .ppm) */
+            bool saveImage(const std::string& save_fn, const std::string& save_ext);      /**< the reference's signature (src/RendererCore.cpp:608) */
 
             Scene render_scene;
             std::uint32_t seed;

@@ -1,6 +1,7 @@
 // host_capi.cpp -- C ABI of include/yune_host.h over yune::Scene / yune::Camera.
 #include "yune_host.h"
 #include "Scene.h"
+#include "ImageIO.h"
 
 #include <new>
 #include <string>
@@ -74,6 +75,17 @@ void yune_camera_set(const float side[4], const float up[4], const float look_at
     cam.setBuffer(out);
 }
 
+
+int yune_write_image(const char* path, const float* rgba, int width, int height)
+{
+    if (!path || !rgba || width <= 0 || height <= 0) return -1;
+    try {
+        const std::string ext = yune::imageExtension(path);
+        if (!yune::imageIsLdr(ext) && !yune::imageIsHdr(ext)) return -2;
+        std::string err;
+        return yune::writeImage(path, ext, rgba, width, height, err) ? 0 : -3;
+    } catch (const std::exception&) { return -3; }
+}
 
 struct yune_camera { yune::Camera cam; explicit yune_camera(float fov) : cam(fov) {} };
 yune_camera* yune_camera_create(float fov) { return new (std::nothrow) yune_camera(fov); }

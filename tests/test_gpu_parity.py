@@ -495,3 +495,29 @@ def test_brute_force_mode_bvh_size_zero(gpu_manager, oracle, scene):
     ref = oracle.samples(Oracle.config("udpt", rng_mode=1, seed=9), CAM, sc.vert_data, sc.mat_data, sc.bvh, W, W, 0)
     close = (np.abs(ours[..., :3] - ref[..., :3]) <= 1e-3 * np.abs(ref[..., :3]) + 1e-6).all(-1)
     assert close.mean() >= 0.99, close.mean()
+
+
+def test_headless_cli_writes_png_and_jpg(gpu_manager, tmp_path):
+    """saveImage's 8-bit formats through the C++ front end (RendererCore::saveImage -> postProcess -> ImageIO.cpp): the decoded
+    .png is the 8-bit view of the tonemapped image the Python harness reads back for the same render, the .jpg is close."""
+    import subprocess
+    Image = pytest.importorskip("PIL.Image")
+    from tests.helpers import write_obj, ROOT
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    obj = str(tmp_path / "cb.obj")
+    write_obj(obj, tris, mats)
+    exe = os.path.join(ROOT, "yune_b200", "yune_headless")
+    r, sc = _renderer(gpu_manager, "cornellbox", 64, 48)
+    assert gpu_manager.createPostProcProgram("tonemap.cl")
+    r.seed = 5
+    r.enqueueKernels(8)
+    r.postProcess()
+    want = (np.clip(np.nan_to_num(r.readLDR()[::-1, :, :3]), 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+    for ext, tol in ((".png", 1), (".jpg", 6)):      # a second render: fp32 accumulation order may move a value across a rounding step
+        out = str(tmp_path / ("cb" + ext))
+        p = subprocess.run([exe, "--obj", obj, "--width", "64", "--height", "48", "--spp", "8", "--seed", "5", "--out", out], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        got = np.asarray(Image.open(out).convert("RGB"))
+        assert got.shape == (48, 64, 3)
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= tol, ext
+    assert r.saveImage(str(tmp_path / "py.png")) and np.array_equal(np.asarray(Image.open(str(tmp_path / "py.png")).convert("RGB")), want)

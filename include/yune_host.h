@@ -57,12 +57,13 @@ void yune_camera_reset(yune_camera* cam);
 int  yune_camera_is_changed(const yune_camera* cam);
 void yune_camera_set_buffer(yune_camera* cam, yune_cam* out);       /* Camera::setBuffer: writes the record, clears is_changed */
 
-/* Image export: the stb_image_write calls of RendererCore::saveImage (src/RendererCore.cpp:608-646).  `rgba` is a bottom-up
- * RGBA float image as returned by yune_read_hdr / yune_read_ldr; the format follows the extension of `path`:
+/* Image export: the stb_image_write calls of RendererCore::saveImage(save_fn, save_ext) (src/RendererCore.cpp:608-646).  `rgba`
+ * is a bottom-up RGBA float image as returned by yune_read_hdr / yune_read_ldr; the file is `path` as given and the format
+ * follows `save_ext` (".png" ...; NULL or "" = the extension of `path`):
  * ".hdr" (Radiance RGBE) and ".pfm" keep the float values; ".png", ".jpg" (baseline, quality 100) and ".ppm" store
  * clamp(v, 0, 1) * 255 rounded, as the reference's GL_UNSIGNED_BYTE read-back does.  The file's first row is the top of the
  * picture; alpha is dropped.  Returns 0, -1 (bad argument), -2 (unsupported extension) or -3 (file could not be written). */
-int yune_write_image(const char* path, const float* rgba, int width, int height);
+int yune_write_image(const char* path, const char* save_ext, const float* rgba, int width, int height);
 
 #ifdef __cplusplus
 }

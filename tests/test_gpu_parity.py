@@ -521,3 +521,14 @@ def test_headless_cli_writes_png_and_jpg(gpu_manager, tmp_path):
         assert got.shape == (48, 64, 3)
         assert np.abs(got.astype(int) - want.astype(int)).max() <= tol, ext
     assert r.saveImage(str(tmp_path / "py.png")) and np.array_equal(np.asarray(Image.open(str(tmp_path / "py.png")).convert("RGB")), want)
+    # "Save At Samples" (src/RendererCore.cpp:447-449): the image after 3 of the 8 samples, written to the name as given
+    shot = str(tmp_path / "after3")
+    p = subprocess.run([exe, "--obj", obj, "--width", "64", "--height", "48", "--spp", "8", "--seed", "5", "--save-at", "3", "--save-at-out", shot,
+                        "--save-at-ext", ".png"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r.samples_taken = 0
+    r.enqueueKernels(3)
+    r.postProcess()
+    want3 = (np.clip(np.nan_to_num(r.readLDR()[::-1, :, :3]), 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
+    got3 = np.asarray(Image.open(shot).convert("RGB"))
+    assert np.abs(got3.astype(int) - want3.astype(int)).max() <= 1 and np.abs(got3.astype(int) - want.astype(int)).max() > 1

@@ -90,12 +90,16 @@ def test_error_codes(tmp_path):
     lib = _native.load()
     img = _picture(4, 4)
     ok = img.ctypes.data
-    assert lib.yune_write_image(None, ok, 4, 4) == -1
-    assert lib.yune_write_image(str(tmp_path / "a.png").encode(), None, 4, 4) == -1
-    assert lib.yune_write_image(str(tmp_path / "a.png").encode(), ok, 0, 4) == -1
-    assert lib.yune_write_image(str(tmp_path / "a.bmp").encode(), ok, 4, 4) == -2
-    assert lib.yune_write_image(str(tmp_path / "noext").encode(), ok, 4, 4) == -2
-    assert lib.yune_write_image(str(tmp_path / "no" / "such" / "dir.png").encode(), ok, 4, 4) == -3
+    assert lib.yune_write_image(None, None, ok, 4, 4) == -1
+    assert lib.yune_write_image(str(tmp_path / "a.png").encode(), None, None, 4, 4) == -1
+    assert lib.yune_write_image(str(tmp_path / "a.png").encode(), None, ok, 0, 4) == -1
+    assert lib.yune_write_image(str(tmp_path / "a.bmp").encode(), None, ok, 4, 4) == -2
+    assert lib.yune_write_image(str(tmp_path / "noext").encode(), None, ok, 4, 4) == -2
+    assert lib.yune_write_image(str(tmp_path / "no" / "such" / "dir.png").encode(), None, ok, 4, 4) == -3
     assert not os.path.exists(str(tmp_path / "a.bmp"))
+    # explicit format, file name as given (RendererCore::saveImage(save_fn, save_ext), "Save At Samples")
+    assert lib.yune_write_image(str(tmp_path / "shot").encode(), b".png", ok, 4, 4) == 0
+    assert open(str(tmp_path / "shot"), "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+    assert yb.write_image(str(tmp_path / "shot2"), img, ".jpg") and open(str(tmp_path / "shot2"), "rb").read(2) == b"\xff\xd8"
     with pytest.raises(ValueError):
         yb.write_image(str(tmp_path / "a.png"), np.zeros((4, 4, 3), np.float32))

@@ -74,7 +74,7 @@ HOST_API = {
     "yune_camera_reset": (None, [C.c_void_p]),
     "yune_camera_is_changed": (C.c_int, [C.c_void_p]),
     "yune_camera_set_buffer": (None, [C.c_void_p, C.c_void_p]),
-    "yune_write_image": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "yune_write_image": (C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -35,13 +35,13 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def write_image(path, rgba):
-    """Encode a bottom-up RGBA float image (H, W, 4) by the extension of `path` (.hdr .pfm .png .jpg .ppm): the product's own
-    encoders behind yune_write_image (include/yune_host.h).  Returns True on success."""
+def write_image(path, rgba, save_ext=None):
+    """Encode a bottom-up RGBA float image (H, W, 4) into `path`; format = `save_ext` or else the extension of `path`
+    (.hdr .pfm .png .jpg .ppm): the product's own encoders behind yune_write_image (include/yune_host.h).  True on success."""
     a = np.ascontiguousarray(rgba, np.float32)
     if a.ndim != 3 or a.shape[2] != 4:
         raise ValueError("write_image expects an (H, W, 4) float image")
-    return _native.load().yune_write_image(path.encode(), _ptr(a), int(a.shape[1]), int(a.shape[0])) == 0
+    return _native.load().yune_write_image(path.encode(), save_ext.encode() if save_ext else None, _ptr(a), int(a.shape[1]), int(a.shape[0])) == 0
 
 
 def default_camera(y_fov=60.0):
@@ -339,7 +339,7 @@ class RendererCore:
         else:
             self.cl_manager.last_message = "unsupported image extension (use .hdr, .png, .jpg, .pfm or .ppm)"
             return False
-        return write_image(save_fn if save_ext is None or save_fn.lower().endswith(ext) else save_fn + ext, img)
+        return write_image(save_fn, img, ext)          # the file is save_fn as given, like the reference
 
     def writeSum(self, img):
         a = np.ascontiguousarray(img, np.float32)

@@ -2,6 +2,7 @@
 // "Load OBJ", kernel file, window size, GI check, "Save At Samples").  Usage:
 //   yune_headless --obj scene.obj [--kernel udpt.cl|bdpt.cl] [--opts -DMIS] [--width 1024 --height 1024] [--spp 64]
 //                 [--seed 12345] [--no-gi] [--bins 20] [--fov 60] [--out image.hdr|.png|.jpg|.pfm|.ppm] [--device 0]
+//                 [--save-at N --save-at-out file [--save-at-ext .jpg|.png|.hdr]]     ("Save At Samples": image after N spp)
 #include "RendererCore.h"
 
 #include <cstdio>
@@ -12,7 +13,8 @@
 
 int main(int argc, char** argv)
 {
-    std::string obj, kernel = "udpt.cl", opts, out;
+    std::string obj, kernel = "udpt.cl", opts, out, save_at_out, save_at_ext;
+    int save_at = 0;
     int width = 1024, height = 1024, spp = 64, bins = 20, device = 0;
     unsigned seed = 12345; bool gi = true; float fov = 60.0f;
     for (int i = 1; i < argc; i++) {
@@ -23,6 +25,7 @@ int main(int argc, char** argv)
         else if (a == "--spp") spp = std::atoi(next()); else if (a == "--seed") seed = (unsigned)std::strtoul(next(), nullptr, 10);
         else if (a == "--bins") bins = std::atoi(next()); else if (a == "--device") device = std::atoi(next());
         else if (a == "--fov") fov = (float)std::atof(next()); else if (a == "--out") out = next(); else if (a == "--no-gi") gi = false;
+        else if (a == "--save-at") save_at = std::atoi(next()); else if (a == "--save-at-out") save_at_out = next(); else if (a == "--save-at-ext") save_at_ext = next();
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
     if (obj.empty()) { std::cerr << "usage: yune_headless --obj scene.obj [--kernel udpt.cl] [--opts -DMIS] [--width W --height H] [--spp N] [--out image.hdr|.png|.jpg]\n"; return 2; }
@@ -33,6 +36,7 @@ int main(int argc, char** argv)
         if (!manager.createRenderProgram(kernel) || !manager.createPostProcProgram("tonemap.cl")) { std::cerr << manager.last_message << "\n"; return 1; }
         yune::RendererCore core(manager, width, height);
         core.seed = seed;
+        if (save_at > 0 && !save_at_out.empty()) { core.save_at_samples = save_at; core.save_samples_fn = save_at_out; if (!save_at_ext.empty()) core.save_samples_ext = save_at_ext; }
         core.render_scene.bvh.bins = bins;
         if (!core.loadScene(obj, obj.substr(obj.find_last_of("/") + 1))) { std::cerr << manager.last_message << "\n"; return 1; }
         if (bins > 0 && bins != 20) core.render_scene.loadBVH(bins);

@@ -60,7 +60,7 @@ namespace yune
 
     RendererCore::RendererCore(CUDAManager& m, int w, int h)
         : seed(12345), samples_taken(0), mspf_avg(0), ms_per_rk(0), ms_per_ppk(0), time_passed(0), msamples_per_s(0), mrays_per_s(0),
-          cl_manager(m), width(w), height(h), gi_check(true)
+          save_at_samples(0), save_samples_ext(".jpg"), cl_manager(m), width(w), height(h), gi_check(true)
     {
         std::memset(&stats, 0, sizeof(stats));
     }
@@ -93,19 +93,32 @@ namespace yune
         }
         if (new_gi_check != gi_check) { gi_check = new_gi_check; reset = true; }      // :556-565
         if (reset) samples_taken = 0;
-        if (yune_render(cl_manager.ctx, samples_taken, frames, gi_check ? 1 : 0, seed, reset ? 1 : 0) != YUNE_OK) {
-            cl_manager.last_message = yune_last_error(cl_manager.ctx);
-            return false;
-        }
-        samples_taken += frames;
-        yune_get_stats(cl_manager.ctx, &stats);
+        // "Save At Samples" (src/RendererCore.cpp:447-449): when the count passes save_at_samples inside this batch, the batch is
+        // rendered in two calls with the save in between -- the image written holds exactly that many samples per pixel.
+        bool ok = true;
+        double ms = 0, samples = 0, rays = 0;
+        int left = frames;
+        do {
+            int n = left;
+            if (save_at_samples > 0 && samples_taken < save_at_samples && samples_taken + left > save_at_samples) n = save_at_samples - samples_taken;
+            if (yune_render(cl_manager.ctx, samples_taken, n, gi_check ? 1 : 0, seed, reset ? 1 : 0) != YUNE_OK) {
+                cl_manager.last_message = yune_last_error(cl_manager.ctx);
+                return false;
+            }
+            reset = false;
+            const bool reached = save_at_samples > 0 && n > 0 && samples_taken < save_at_samples && samples_taken + n == save_at_samples;
+            samples_taken += n; left -= n;
+            yune_get_stats(cl_manager.ctx, &stats);
+            ms += stats.render_ms; samples += (double)stats.samples; rays += (double)(stats.extend_rays + stats.shadow_rays);
+            if (reached) ok = saveImage(save_samples_fn, save_samples_ext) && ok;
+        } while (left > 0);
         // endFrame() metrics (:483-505): one frame = one sample per pixel
-        mspf_avg = frames > 0 ? (float)(stats.render_ms / frames) : 0.0f;
+        mspf_avg = frames > 0 ? (float)(ms / frames) : 0.0f;
         ms_per_rk = mspf_avg;
-        time_passed += (float)(stats.render_ms / 1000.0);
-        msamples_per_s = stats.render_ms > 0 ? stats.samples / stats.render_ms / 1e3 : 0;
-        mrays_per_s = stats.render_ms > 0 ? (stats.extend_rays + stats.shadow_rays) / stats.render_ms / 1e3 : 0;
-        return true;
+        time_passed += (float)(ms / 1000.0);
+        msamples_per_s = ms > 0 ? samples / ms / 1e3 : 0;
+        mrays_per_s = ms > 0 ? rays / ms / 1e3 : 0;
+        return ok;
     }
 
     bool RendererCore::postProcess()

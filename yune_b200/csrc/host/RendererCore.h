@@ -54,6 +54,8 @@ namespace yune
             float mspf_avg, ms_per_rk, ms_per_ppk, time_passed;                           /**< endFrame() metrics, :483-505 */
             double msamples_per_s, mrays_per_s;
             yune_stats stats;
+            int save_at_samples;                                                          /**< "Save At Samples" (src/RendererCore.cpp:447-449): 0 = off */
+            std::string save_samples_fn, save_samples_ext;                                /**< file as given; format ".jpg" (default, :57) ".png" ".hdr" */
         private:
             CUDAManager& cl_manager;
             int width, height;

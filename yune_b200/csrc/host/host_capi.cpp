@@ -76,11 +76,11 @@ void yune_camera_set(const float side[4], const float up[4], const float look_at
 }
 
 
-int yune_write_image(const char* path, const float* rgba, int width, int height)
+int yune_write_image(const char* path, const char* save_ext, const float* rgba, int width, int height)
 {
     if (!path || !rgba || width <= 0 || height <= 0) return -1;
     try {
-        const std::string ext = yune::imageExtension(path);
+        const std::string ext = (save_ext && save_ext[0]) ? yune::imageExtension(save_ext) : yune::imageExtension(path);
         if (!yune::imageIsLdr(ext) && !yune::imageIsHdr(ext)) return -2;
         std::string err;
         return yune::writeImage(path, ext, rgba, width, height, err) ? 0 : -3;

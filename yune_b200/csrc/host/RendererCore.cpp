@@ -24,7 +24,7 @@ namespace yune
     bool CUDAManager::report(int rc)
     {
         if (rc == YUNE_OK) return true;
-        last_message = yune_last_error(ctx);          // the reference pushes this to the GUI callback (src/CLManager.cpp:261-265)
+        message(yune_last_error(ctx), "Error!");      // the reference pushes this to the GUI callback (src/CLManager.cpp:261-265)
         return false;
     }
     void CUDAManager::setup(int device)
@@ -68,8 +68,31 @@ namespace yune
     bool RendererCore::loadScene(std::string path, std::string fn)
     {
         try { render_scene.loadModel(path, fn); }
-        catch (const std::exception& e) { cl_manager.last_message = e.what(); return false; }
+        catch (const std::exception& e) { cl_manager.message(e.what(), "Error loading File!"); return false; }
         return true;
+    }
+
+    bool RendererCore::reloadMatFile()
+    {
+        try { render_scene.reloadMatFile(); }
+        catch (const std::exception& e) { cl_manager.message(e.what(), "Error loading File!"); return false; }
+        if (!cl_manager.setupMatBuffer(render_scene.mat_data)) return false;
+        samples_taken = 0;                                     // new materials: the accumulated image is stale
+        return true;
+    }
+
+    void RendererCore::resetValues()
+    {
+        gi_check = true;
+        samples_taken = 0; save_at_samples = 0; time_passed = 0;
+        mspf_avg = ms_per_ppk = ms_per_rk = 0;
+        msamples_per_s = mrays_per_s = 0;
+    }
+
+    void RendererCore::stop()
+    {
+        if (cl_manager.ctx) yune_synchronize(cl_manager.ctx);
+        resetValues();
     }
 
     bool RendererCore::setup(bool gi)

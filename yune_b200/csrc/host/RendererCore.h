@@ -8,6 +8,7 @@
 #include "yune_cuda.h"
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -29,10 +30,16 @@ namespace yune
             bool setupMatBuffer(std::vector<Material>& mat_data);
             static void checkError(int err_code, yune_ctx* ctx, std::string filename, int line_number);   /**< negative code -> std::runtime_error */
 
+            /** CLManager::setGuiMessageCb (include/CLManager.h:76): called as cb(message, title, log) whenever a bool method fails
+             *  (src/CLManager.cpp:261-265); last_message keeps the text either way. */
+            void setGuiMessageCb(std::function<void(const std::string&, const std::string&, const std::string&)> cb) { message_cb = cb; }
+            void message(const std::string& msg, const std::string& title, const std::string& log = "") { last_message = msg; if (message_cb) message_cb(msg, title, log); }
+
             std::string rk_file, rk_compiler_opts, ppk_file, last_message;
             yune_ctx* ctx;
         private:
             bool report(int rc);
+            std::function<void(const std::string&, const std::string&, const std::string&)> message_cb;
     };
 
     class RendererCore
@@ -43,6 +50,10 @@ namespace yune
             bool setup(bool gi_check);                                                    /**< upload scene + camera, allocate images */
             bool enqueueKernels(int frames, bool new_gi_check);                           /**< `frames` more samples per pixel; blocks until done */
             bool postProcess();
+            bool reloadMatFile();                                                         /**< src/RendererCore.cpp:109-122 + the buffer update the GUI triggers (src/RendererGUI.cpp:203-220) */
+            void resetValues();                                                           /**< src/RendererCore.cpp:77-86: counters and metrics back to zero; the next frame starts a new image */
+            void stop();                                                                  /**< src/RendererCore.cpp:88-107: wait for the device, then resetValues() */
+            void setGuiMessageCb(std::function<void(const std::string&, const std::string&, const std::string&)> cb) { cl_manager.setGuiMessageCb(cb); }
             /** src/RendererCore.cpp:608-646 without stb: ".hdr" (Radiance RGBE), ".pfm" (float RGB), ".ppm" (8-bit, tonemapped). Rows are
              *  flipped to top-down on the way out like the reference does. */
             bool saveImage(const std::string& path);                                      /**< format by extension: .hdr .png .jpg (.pfm .ppm) */

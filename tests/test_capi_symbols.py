@@ -51,6 +51,12 @@ def test_no_cpu_fallback():
         import yune_b200 as yb
         with pytest.raises(yb.YuneError):
             yb.CUDAManager().setup(0)
+        # the C++ front end says so too and writes nothing
+        import subprocess
+        from tests.helpers import ROOT
+        out = os.path.join(ROOT, "gpurun_out", "_never_written.png")
+        p = subprocess.run([os.path.join(ROOT, "yune_b200", "yune_headless"), "--obj", "missing.obj", "--spp", "1", "--out", out], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr and not os.path.exists(out)
 
 
 def test_argument_errors_do_not_crash():

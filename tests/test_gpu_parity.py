@@ -407,8 +407,6 @@ def test_error_behaviour_on_device(gpu_manager):
         assert m.setupVertexBuffer(tris) and m.setupMatBuffer(mats) and m.setupBVHBuffer(bad) and m.setupImageBuffers(16, 16)
         m.setupCameraBuffer(yb.default_camera())
         assert r._lib.yune_render(m._ctx, 0, 1, 1, 0, 1) == -4            # malformed BVH rejected at upload, not traversed
-        assert m.setupBVHBuffer(nodes[:0]) is True                         # bvh_size == 0 = the reference's brute-force mode
-        assert r._lib.yune_render(m._ctx, 0, 1, 1, 0, 1) == 0
     finally:
         m.close()
 

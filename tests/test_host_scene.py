@@ -247,3 +247,103 @@ def test_random_soups_against_reference_host_code(ref_host, tmp_path, kind, n, b
     leaves = s.bvh[s.bvh["child_idx"] == -1]
     ids = np.concatenate([l["vert_list"][: l["vert_len"]] for l in leaves]) if leaves.size else np.zeros(0, int)
     assert np.array_equal(np.sort(ids), np.arange(n))
+
+
+QUIRK_MTL = """# materials in the reference's dialect
+newmtl   first
+kd 0.1 0.2 0.3
+ks .5 .25 0.125
+ke 1 2 3
+n 1.33
+k 2.5
+px 7
+py 9
+alpha_x 0.5
+alpha_y 0.75
+is_specular 1
+is_transmissive 1
+Kd 0.9 0.9 0.9
+unknown_key 4 5 6
+
+newmtl second
+kd 0.7 0.7 0.7
+
+newmtl third
+ks 1 1 1
+px 40
+"""
+
+QUIRK_OBJ = """mtllib q.mtl
+# comment line
+o first_object
+v 0 0 0
+v 1 0 0
+v 0 1 0
+v  0.25   0.25   1.5
+v -1e-3 2.5E+0 -.5
+vt 0.5 0.5
+vt 0 1
+vn 0 0 1
+vn 0 1 0
+vn 0.6 0 0.8
+
+usemtl second
+f 1//1 2//1 3//1
+f 1/1/2 2/2/2 4/1/3
+s off
+g group_name
+usemtl third
+f 2//3 3//3 5//3
+usemtl nosuch
+f 5//1 4//2 1//3
+o second_object
+usemtl first
+f 3//2 4//2 5//2
+f 1//1 3//1 4//1
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GEOMETRY), reason="needs the reference tree")
+@pytest.mark.parametrize("newline", ["\n", "\r\n"])
+def test_text_quirks_live_against_reference_loader(ref_host, tmp_path, newline):
+    """OBJ / MTL text the shipped scenes do not contain -- vt lines and a/b/c corners, exponents, repeated blanks, s / g / o
+    statements, an unknown usemtl, unknown and wrongly-cased MTL keys, CRLF line ends -- through the reference's compiled
+    Scene.cpp and through ours: triangles, materials, BVH and root box identical."""
+    (tmp_path / "q.mtl").write_bytes(QUIRK_MTL.replace("\n", newline).encode())
+    (tmp_path / "q.obj").write_bytes(QUIRK_OBJ.replace("\n", newline).encode())
+    path = str(tmp_path / "q.obj")
+    rt, rm, rn, rroot = ref_host.load(path)
+    s = yb.Scene().loadModel(path)
+    assert rt.size == 6 and rm.size == 3
+    assert tris_equal(s.vert_data, rt)
+    assert s.mat_data.tobytes() == rm.tobytes()
+    assert masked_nodes_equal(rn, s.bvh)
+    assert s.root.tobytes() == rroot.tobytes()
+
+
+_QBASE = "mtllib q.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\n"
+SMALL_QUIRKS = {
+    "quad_face_keeps_first_three_corners": _QBASE + "usemtl a\nf 1//1 2//1 4//1 3//1\n",
+    "tabs": _QBASE.replace(" ", "\t") + "usemtl\ta\nf\t1//1\t2//1\t3//1\n",
+    "trailing_spaces": _QBASE + "usemtl a   \nf 1//1 2//1 3//1   \n",
+    "no_usemtl": _QBASE + "f 1//1 2//1 3//1\n",
+    "v_with_w": "mtllib q.mtl\nv 0 0 0 1\nv 1 0 0 1\nv 0 1 0 1\nvn 0 0 1\nf 1//1 2//1 3//1\n",
+    "leading_spaces": "mtllib q.mtl\n  v 0 0 0\n  v 1 0 0\n v 0 1 0\n vn 0 0 1\n  f 1//1 2//1 3//1\n",
+    "comment_before_mtllib": "# c\n\nmtllib q.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n",
+    "usemtl_twice": _QBASE + "usemtl a\nusemtl zzz\nf 1//1 2//1 3//1\nusemtl a\nf 2//1 3//1 4//1\n",
+    "vn_before_v": "mtllib q.mtl\nvn 0 0 1\nv 0 0 0\nv 1 0 0\nv 0 1 0\nf 1//1 2//1 3//1\n",
+    "no_final_newline": _QBASE + "f 1//1 2//1 3//1",
+    "vt_corners": _QBASE + "vt 0 0\nf 1/1/1 2/1/1 3/1/1\n",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GEOMETRY), reason="needs the reference tree")
+@pytest.mark.parametrize("case", sorted(SMALL_QUIRKS))
+def test_small_text_quirks_live_against_reference_loader(ref_host, tmp_path, case):
+    (tmp_path / "q.mtl").write_text("newmtl a\nkd 0.5 0.5 0.5\n")
+    (tmp_path / "q.obj").write_text(SMALL_QUIRKS[case])
+    path = str(tmp_path / "q.obj")
+    rt, rm, rn, rroot = ref_host.load(path)
+    s = yb.Scene().loadModel(path)
+    assert rt.size >= 1 and tris_equal(s.vert_data, rt) and s.mat_data.tobytes() == rm.tobytes()
+    assert masked_nodes_equal(rn, s.bvh) and s.root.tobytes() == rroot.tobytes()

@@ -213,3 +213,84 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
     if (util) for (int i = 0; i < 4; i++) util[i] = st[i];
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Design aid (no product path): how many steps would a WIDER tree take?  The own tree (accel 1) is collapsed into nodes of up
+// to `width` children (the inner child with the largest box is replaced by its two children until the node is full) and
+// walked front to back with the same conservative box test and pruning; width 2 is the shipped tree.  Returns per-ray
+// totals: out[0] = node visits, out[1] = child boxes tested, out[2] = triangle tests, out[3] = rays that hit.
+// ------------------------------------------------------------------------------------------------------------------
+#include <algorithm>
+namespace {
+struct WideNode { int n; float lo[8][3], hi[8][3]; int ref[8]; };      // ref >= 0: wide node index; < 0: ~((first << 4) | count)
+}
+extern "C" int hc_wide_stats(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
+                             const yune_bvh_node* nodes, int nnodes, int width, unsigned long long* out)
+{
+    if (width < 2 || width > 8) return -1;
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, 0, 1)) return -1;
+    const F4* P = lay.pairs.data();
+    struct Child { float lo[3], hi[3]; int ref; };
+    auto children_of = [&](int pair, Child* c) {
+        const F4* q = P + (size_t)pair * 4;
+        c[0] = {{q[0].x, q[0].z, q[2].x}, {q[0].y, q[0].w, q[2].y}, YF_ASINT(q[3].x)};
+        c[1] = {{q[1].x, q[1].z, q[2].z}, {q[1].y, q[1].w, q[2].w}, YF_ASINT(q[3].y)};
+    };
+    std::vector<WideNode> wide;
+    std::vector<int> wide_of(lay.n_inner, -1), todo;
+    auto area = [](const Child& c) { const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2]; return dx * dy + dx * dz + dy * dz; };
+    if (lay.root_ref >= 0) { wide_of[lay.root_ref] = 0; wide.push_back(WideNode()); todo.push_back(lay.root_ref); }
+    for (size_t k = 0; k < todo.size(); k++) {
+        const int pair = todo[k];
+        std::vector<Child> cs(2); children_of(pair, cs.data());
+        while ((int)cs.size() < width) {
+            int pick = -1;
+            for (int i = 0; i < (int)cs.size(); i++) if (cs[i].ref >= 0 && (pick < 0 || area(cs[i]) > area(cs[pick]))) pick = i;
+            if (pick < 0) break;
+            Child two[2]; children_of(cs[pick].ref, two);
+            cs[pick] = two[0]; cs.push_back(two[1]);
+        }
+        WideNode w; w.n = (int)cs.size();
+        for (int i = 0; i < w.n; i++) {
+            for (int a = 0; a < 3; a++) { w.lo[i][a] = cs[i].lo[a]; w.hi[i][a] = cs[i].hi[a]; }
+            if (cs[i].ref >= 0) { wide_of[cs[i].ref] = (int)wide.size() + 0; wide.push_back(WideNode()); todo.push_back(cs[i].ref); w.ref[i] = wide_of[cs[i].ref]; }
+            else w.ref[i] = cs[i].ref;
+        }
+        wide[wide_of[pair]] = w;
+    }
+    HostTriFetch tf{lay.tris.data()}; HostLeafFetch lf{lay.leaf_boxes.data()};
+    unsigned long long visits = 0, boxes = 0, tests = 0, hits = 0;
+    std::vector<int> stack;
+    for (int i = 0; i < n; i++) {
+        const float* r = od6 + 6 * (size_t)i;
+        RayPre ray = make_ray(v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]));
+        float t_best = tmax ? tmax[i] : INFINITY, t_prune = t_best * 1.00001f; int tri = -1, best_pos = -1;
+        stack.clear();
+        if (lay.root_ref != YUNE_REF_EMPTY) stack.push_back(lay.root_ref >= 0 ? 0 : lay.root_ref);
+        bool done = false;
+        while (!stack.empty() && !done) {
+            const int ref = stack.back(); stack.pop_back();
+            if (ref < 0) {
+                const int x = ~ref;
+                for (int pos = x >> 4; pos < (x >> 4) + (x & 15) && !done; pos++) {
+                    F4 a, b, c; tf(pos, a, b, c); float t, u, v; tests++;
+                    if (!tri_test(ray, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v) || !(t > 0.0f) || t > t_best) continue;
+                    F4 lo, hi; lf(YF_ASINT(c.w), lo, hi); float e;
+                    if (!box_hit(ray, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, e)) continue;
+                    if (any) { if (t < t_best) { tri = 0; done = true; } }
+                    else if (t < t_best || (best_pos >= 0 && YF_ASINT(b.w) < best_pos)) { t_best = t; t_prune = t * 1.00001f; tri = YF_ASINT(a.w); best_pos = YF_ASINT(b.w); }
+                }
+                continue;
+            }
+            const WideNode& w = wide[ref]; visits++; boxes += w.n;
+            std::pair<float, int> hit[8]; int nh = 0;
+            for (int k = 0; k < w.n; k++) { float e; if (box_hit_own(ray, w.lo[k][0], w.hi[k][0], w.lo[k][1], w.hi[k][1], w.lo[k][2], w.hi[k][2], t_prune, e)) hit[nh++] = {e, w.ref[k]}; }
+            if (!any) std::sort(hit, hit + nh, [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+            for (int k = 0; k < nh; k++) stack.push_back(hit[k].second);      // nearest on top
+        }
+        hits += tri >= 0;
+    }
+    out[0] = visits; out[1] = boxes; out[2] = tests; out[3] = hits;
+    return 0;
+}

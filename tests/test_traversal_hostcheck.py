@@ -214,3 +214,21 @@ def test_brute_force_mode_bvh_size_zero(hc, oracle, scene):
     assert hc.hc_trace_warp(od.shape[0], ptr(od), None, 0, ptr(tris), int(tris.size), None, 0, ptr(tri_w), ptr(t_w), 1, ptr(knobs), None) == 0
     free = olight < 0
     assert (tri_w[free] == otri[free]).all()
+
+
+def test_wide_tree_model_finds_the_same_hits(hc):
+    """tests/hostcheck hc_wide_stats (design aid behind DESIGN.md's wide-node figures): collapsing the own tree into nodes of up
+    to 4 or 8 children must not change which rays hit, and must cut the node visits roughly in half at equal box tests."""
+    tris, mats, nodes = load_golden_scene("teapot")
+    rng = np.random.RandomState(5); n = 20000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    res = {}
+    for width in (2, 4, 8):
+        out = np.zeros(4, np.uint64)
+        assert hc.hc_wide_stats(n, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), width, ptr(out)) == 0
+        res[width] = [int(x) for x in out]
+    assert res[2][3] == res[4][3] == res[8][3]
+    assert res[4][0] < 0.6 * res[2][0] and res[4][1] < 1.1 * res[2][1] and res[8][0] < res[4][0]
+    assert hc.hc_wide_stats(n, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), 9, ptr(out)) == -1

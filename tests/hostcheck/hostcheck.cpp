@@ -12,6 +12,7 @@ using namespace yune;
 namespace {
 struct HostPairFetch { const F4* p; void operator()(int i, F4& a, F4& b, F4& c, F4& d) const { const F4* q = p + (size_t)i * 4; a = q[0]; b = q[1]; c = q[2]; d = q[3]; } };
 struct HostTriFetch { const F4* p; void operator()(int i, F4& a, F4& b, F4& c) const { const F4* q = p + (size_t)i * 3; a = q[0]; b = q[1]; c = q[2]; } };
+struct HostQuadFetch { const F4* p; void operator()(int i, F4* q) const { const F4* s = p + (size_t)i * 7; for (int k = 0; k < 7; k++) q[k] = s[k]; } };
 struct HostLeafFetch { const F4* p; void operator()(int i, F4& lo, F4& hi) const { lo = p[2 * (size_t)i]; hi = p[2 * (size_t)i + 1]; } };
 LightDev unpack(const yune_quad_light& q)
 {
@@ -34,7 +35,7 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
     accel = lay.accel;                               // bvh_size == 0 (brute-force mode) always walks the own tree
     HostLeafFetch lf{lay.leaf_boxes.data()};
-    HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()};
+    HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()}; HostQuadFetch qf{lay.quads.data()};
     LightDev L[YUNE_MAX_LIGHTS];
     for (int i = 0; i < nlights; i++) L[i] = unpack(lights[i]);
     unsigned long long nb = 0, nt = 0;
@@ -47,13 +48,15 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
         if (any) {
             bool occ = lid >= 0;
             if (!occ) {
-                if (accel == 1) { HitRec h; trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
+                if (accel == 2) { HitRec h; trace_wide<HostQuadFetch, HostTriFetch, HostLeafFetch, true, true>(qf, tf, lf, lay.root_wide_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
+                else if (accel == 1) { HitRec h; trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
                 else occ = any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, &wc);
             }
             tri_id[i] = occ ? 0 : -1; light_id[i] = lid; if (t_hit) t_hit[i] = t;
         } else {
             HitRec h;
-            if (accel == 1) trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, false, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
+            if (accel == 2) trace_wide<HostQuadFetch, HostTriFetch, HostLeafFetch, false, true>(qf, tf, lf, lay.root_wide_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
+            else if (accel == 1) trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, false, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             else closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             tri_id[i] = h.tri; light_id[i] = h.tri >= 0 ? -1 : lid; if (t_hit) t_hit[i] = h.t;
         }
@@ -68,7 +71,7 @@ extern "C" int hc_layout_info(const yune_triangle* tris, int ntri, const yune_bv
 {
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
-    out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = lay.max_depth; out[3] = lay.n_inner_ref;
+    out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = lay.max_depth; out[3] = accel == 2 ? lay.n_wide : lay.n_inner_ref;
     return 0;
 }
 
@@ -175,6 +178,7 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
     accel = lay.accel;
+    if (accel == 2) return -1;                       // the device scheduling restated here walks pair records only
     SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel};
     const int refill_idle = knobs[0], tri_min = knobs[1], inner_min = knobs[2], inner_chain = knobs[3];
     const bool any_q = any != 0;

@@ -61,7 +61,7 @@ def test_random_rays_closest_and_any(hc, oracle, scene):
 
 
 @pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
-@pytest.mark.parametrize("leaf_split,accel", [(2, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize("leaf_split,accel", [(2, 0), (1, 0), (0, 1), (0, 2)])
 def test_refined_leaves_and_own_tree_return_the_same_hits(hc, oracle, scene, leaf_split, accel):
     """Both accelerations of the reference walk -- padded subtrees inside big leaves (accel 0, leaf_split) and our own SAH
     tree with the exact leaf-box filter (accel 1) -- must give the reference's hit record bit for bit while testing far
@@ -168,7 +168,7 @@ def test_random_soups_closest_and_any(hc, oracle, kind, n, seed, offset):
     otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
     assert (otri >= 0).mean() > 0.3
     stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, nodes)
-    for leaf_split, accel in ((0, 0), (2, 0), (0, 1)):
+    for leaf_split, accel in ((0, 0), (2, 0), (0, 1), (0, 2)):
         tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
         assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)
         atri, _, _, _ = _trace(hc, od, tm, 1, tris, nodes, leaf_split, accel)
@@ -202,7 +202,7 @@ def test_brute_force_mode_bvh_size_zero(hc, oracle, scene):
     if have_ref():      # the oracle's loop is the reference's: same answers from the compiled kernel text
         rtri, rlight, rt = RefKernels().trace("udpt", od, None, 0, tris, none)
         assert (rtri == otri).all() and (rlight == olight).all() and (rt.view(np.uint32) == ot.view(np.uint32)).all()
-    for accel in (1, 0):                                  # the option is ignored in this mode (there is no reference tree to walk)
+    for accel in (1, 0, 2):                               # 0 is answered like 1 in this mode (there is no reference tree to walk)
         tri, light, t, work = _trace(hc, od, None, 0, tris, none, 0, accel)
         assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all()
         assert work[1] < 0.2 * od.shape[0] * tris.size        # and nowhere near n_rays x n_triangles tests

@@ -292,6 +292,53 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     out.n_inner = out.n_inner_ref = (int)order.size();
     out.root_ref = ref_of(root);
     lap("pair records");
+    if (out.accel != 2) return true;
+
+    // ---- accel 2 (host-verified groundwork, not yet a device path): the same tree collapsed into nodes of up to 4 children ----
+    // A wide node starts from the two children of a binary node; the inner child with the largest box is replaced by its own two
+    // children until there are four (or only leaves are left).  Breadth-first order again, so the top of the tree is a prefix.
+    std::vector<int> wide_of(B.nodes.size(), -1), worder;
+    auto wref_of = [&](int n) { const OwnNode& nd = B.nodes[n]; return nd.left < 0 ? ~((nd.first << 4) | nd.count) : wide_of[n]; };
+    std::vector<int> wdepth;
+    if (B.nodes[root].left >= 0) { worder.push_back(root); wide_of[root] = 0; wdepth.push_back(1); }
+    std::vector<int> kids;
+    int wide_depth = 0;
+    for (size_t h = 0; h < worder.size(); h++) {
+        const OwnNode& nd = B.nodes[worder[h]];
+        kids.clear(); kids.push_back(nd.left); kids.push_back(nd.right);
+        while (kids.size() < 4) {
+            int pick = -1; float best_area = -1.0f;
+            for (size_t i = 0; i < kids.size(); i++) {
+                const OwnNode& c = B.nodes[kids[i]];
+                if (c.left < 0) continue;
+                const float a = OwnBuilder::area(c.lo, c.hi);
+                if (a > best_area) { best_area = a; pick = (int)i; }
+            }
+            if (pick < 0) break;
+            const OwnNode c = B.nodes[kids[pick]];
+            kids[pick] = c.left; kids.push_back(c.right);
+        }
+        for (int c : kids) if (B.nodes[c].left >= 0) { wide_of[c] = (int)worder.size(); worder.push_back(c); wdepth.push_back(wdepth[h] + 1); }
+        wide_depth = std::max(wide_depth, wdepth[h]);
+        F4 q[7];
+        float* f = &q[0].x;                                    // 24 floats: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4]
+        int refs[4];
+        for (int i = 0; i < 4; i++) {
+            const bool used = i < (int)kids.size();
+            for (int a = 0; a < 3; a++) {
+                f[8 * a + i]     = used ? B.nodes[kids[i]].lo[a] :  3.0e38f;      // an unused slot is an inverted box: never hit
+                f[8 * a + 4 + i] = used ? B.nodes[kids[i]].hi[a] : -3.0e38f;
+            }
+            refs[i] = used ? wref_of(kids[i]) : YUNE_REF_EMPTY;
+        }
+        q[6] = {bits(refs[0]), bits(refs[1]), bits(refs[2]), bits(refs[3])};
+        out.quads.insert(out.quads.end(), q, q + 7);
+    }
+    out.n_wide = (int)worder.size();
+    out.root_wide_ref = wref_of(root);
+    out.wide_depth = wide_depth;
+    if (3 * wide_depth + 2 > YUNE_STACK_SIZE) { err = "wide tree deeper than the traversal stack (YUNE_STACK_SIZE)"; return false; }
+    lap("wide records");
     return true;
 }
 
@@ -306,11 +353,12 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     if (n_tris >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
     // bvh_size == 0 is the reference's brute-force mode (udpt.cl:280-284: every triangle, in index order, no box tests).  The
     // result is reproduced by the own-tree walk with a filter that always passes; only the cost differs (a tree walk here).
-    if (n_nodes == 0) accel = 1;
+    if (n_nodes == 0 && accel == 0) accel = 1;
+    if (accel < 0 || accel > 2) { err = "accel must be 0, 1 or 2"; return false; }
     out.n_tris = n_tris; out.accel = accel;
 
     if (n_nodes > 0 && !validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
-    if (accel == 1) {
+    if (accel >= 1) {
         if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err, leaf_split)) return false;
         goto shade_records;
     }

@@ -277,6 +277,43 @@ YUNE_HD void trace_own(const PairFetch& fetch_pair, const TriFetch& fetch_tri, c
     out.t = s.t_best; out.u = s.u; out.v = s.v; out.tri = s.tri;
 }
 
+// ---- accel 2: the own tree with up to four children per node (trav_layout.h `quads`) ----
+// One step fetches a 112-byte record, tests the (up to) four child boxes, enters the nearest hit child and pushes the others
+// far to near.  Leaves are the same triangle ranges as in accel 1, tested by ts_tri_step_own.
+template <class QuadFetch, bool ANY, bool COUNT>
+YUNE_HD void ts_inner_step_wide(TraceState& s, int* stack, const QuadFetch& fetch_quad, WorkCount* wc)
+{
+    F4 q[7];
+    fetch_quad(s.cur, q);
+    const float* f = &q[0].x;
+    const int refs[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
+    float e[4]; int ref[4]; int n = 0;
+    for (int i = 0; i < 4; i++) {
+        if (refs[i] == YUNE_REF_EMPTY) continue;
+        if (COUNT) wc->box++;
+        float ent;
+        if (!box_hit_own(s.r, f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], s.t_prune, ent)) continue;
+        int k = n++;                                                  // insertion sort, nearest first (ANY keeps the slot order)
+        if (!ANY) while (k > 0 && e[k - 1] > ent) { e[k] = e[k - 1]; ref[k] = ref[k - 1]; k--; }
+        e[k] = ent; ref[k] = refs[i];
+    }
+    if (n == 0) { ts_pop(s, stack); return; }
+    for (int k = n - 1; k >= 1; k--) stack[s.sp++] = ref[k];
+    ts_enter(s, ref[0]);
+}
+template <class QuadFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
+YUNE_HD void trace_wide(const QuadFetch& fetch_quad, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, int root_ref,
+                        const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)
+{
+    TraceState s; int stack[YUNE_STACK_SIZE];
+    ts_init_own<COUNT>(s, o, d, t_in, root_ref, root_lo, root_hi, wc);
+    while (!s.done) {
+        if (s.leaf_pos < s.leaf_end) ts_tri_step_own<TriFetch, LeafBoxFetch, ANY, COUNT>(s, stack, fetch_tri, fetch_leaf_box, wc);
+        else ts_inner_step_wide<QuadFetch, ANY, COUNT>(s, stack, fetch_quad, wc);
+    }
+    out.t = s.t_best; out.u = s.u; out.v = s.v; out.tri = s.tri;
+}
+
 // ---- whole-ray wrappers (host check, hooks): drive the machine until done ----
 template <class PairFetch, class TriFetch, bool COUNT>
 YUNE_HD void closest_hit(const PairFetch& fetch_pair, const TriFetch& fetch_tri, int root_ref,

@@ -38,6 +38,8 @@ struct TravLayoutHost {
     std::vector<F4> tris;        // 3 per leaf-ordered triangle
     std::vector<F4> shade;       // 4 per original triangle
     std::vector<F4> leaf_boxes;  // accel 1: 2 per REFERENCE leaf (p_min, p_max exactly as uploaded), indexed by the id in triangle record t2.w
+    std::vector<F4> quads;       // accel 2: 7 per wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4]; unused slot = inverted box + YUNE_REF_EMPTY
+    int   n_wide = 0, root_wide_ref = YUNE_REF_EMPTY, wide_depth = 0;
     int   accel = 0;
     int   n_inner = 0, n_inner_ref = 0, n_leaf_tris = 0, n_tris = 0;   // n_inner counts refinement pairs too; n_inner_ref = reference inner nodes
     int   root_ref = YUNE_REF_EMPTY;
@@ -57,6 +59,11 @@ struct TravLayoutHost {
 //            exactly (getExtent / refit, src/BVH.cpp:218-278) and float subtraction / multiplication are monotone, so
 //            "the leaf's box passes" implies "every ancestor's box passes" (rays with a non-finite 1/d excepted).
 //            Same hit records, roughly half the box tests and a third of the triangle tests.
+//
+//        2 = accel 1's tree collapsed into nodes of up to FOUR children (`quads`; half the steps per ray at the same number of
+//            box tests).  Host-verified groundwork for the next trace kernel: the layout and the walk in
+//            trace_core.h are pinned against the oracle by tests/test_traversal_hostcheck.py; the device does not use it yet
+//            (the C ABI's "accel" option accepts 0 and 1 only).
 //
 // n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
 //        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.

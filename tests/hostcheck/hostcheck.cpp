@@ -104,7 +104,7 @@ struct SimLane {
     int tri, best_pos, cur, pend_pos, pend_end, sp, where; bool have;
     int stack[YUNE_STACK_SIZE + STACK_BASE];
 };
-struct SimScene { const TravLayoutHost* lay; HostPairFetch pf; HostTriFetch tf; HostLeafFetch lf; int accel; };
+struct SimScene { const TravLayoutHost* lay; HostPairFetch pf; HostTriFetch tf; HostLeafFetch lf; int accel; HostQuadFetch qf; };
 
 void sim_init(SimLane& L, const SimScene& S, V3 o, V3 d, float t_in)
 {
@@ -114,7 +114,7 @@ void sim_init(SimLane& L, const SimScene& S, V3 o, V3 d, float t_in)
     L.stack[0] = L.stack[1] = REF_DONE;
     bool hit = S.lay->root_ref != YUNE_REF_EMPTY;
     if (S.accel == 0 && hit) { float e; hit = box_hit(L.r, S.lay->root_lo[0], S.lay->root_hi[0], S.lay->root_lo[1], S.lay->root_hi[1], S.lay->root_lo[2], S.lay->root_hi[2], e); }
-    const int ref = hit ? S.lay->root_ref : REF_DONE;
+    const int ref = hit ? (S.accel == 2 ? S.lay->root_wide_ref : S.lay->root_ref) : REF_DONE;
     const int x = ~ref;
     L.cur = ref >= 0 ? ref : REF_DONE;
     L.pend_pos = ref >= 0 ? 0 : (x >> 4);
@@ -145,6 +145,31 @@ void sim_inner(SimLane& L, const SimScene& S, bool any_q)
     L.cur = park ? c1 : c0;
     if (park) { L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15); }
 }
+// accel 2: one step over a 4-wide record.  Same rules as sim_inner, stated as "push every hit child far to near, then take
+// the next place of the walk": a leaf on top is parked when nothing is parked (and the walk moves on to the place after it),
+// otherwise the lane stands on it until its parked triangles have been tested.
+void sim_inner_wide(SimLane& L, const SimScene& S, bool any_q)
+{
+    F4 q[7]; S.qf(L.cur, q);
+    const float* f = &q[0].x;
+    const int refs[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
+    float e[4]; int ref[4]; int n = 0;
+    for (int i = 0; i < 4; i++) {
+        if (refs[i] == YUNE_REF_EMPTY) continue;
+        float ent;
+        if (!box_hit_own(L.r, f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], L.t_prune, ent)) continue;
+        int k = n++;
+        if (!any_q) while (k > 0 && e[k - 1] > ent) { e[k] = e[k - 1]; ref[k] = ref[k - 1]; k--; }
+        e[k] = ent; ref[k] = refs[i];
+    }
+    for (int k = n - 1; k >= 0; k--) L.stack[L.sp++] = ref[k];
+    int c0 = L.stack[L.sp - 1]; L.sp = L.sp - 1 > STACK_BASE ? L.sp - 1 : STACK_BASE;
+    if (c0 < 0 && !(L.pend_pos < L.pend_end)) {
+        const int x = ~c0; L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15);
+        c0 = L.stack[L.sp - 1]; L.sp = L.sp - 1 > STACK_BASE ? L.sp - 1 : STACK_BASE;
+    }
+    L.cur = c0;
+}
 void sim_tri(SimLane& L, const SimScene& S, bool any_q)
 {
     const int top1 = L.stack[L.sp - 1 > 0 ? L.sp - 1 : 0];
@@ -152,7 +177,7 @@ void sim_tri(SimLane& L, const SimScene& S, bool any_q)
     F4 a, b, c; S.tf(pos, a, b, c);
     float t, u, v;
     bool inside = tri_test(L.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v);
-    if (S.accel == 1 && inside && t > 0.0f && !(t > L.t_best)) {
+    if (S.accel >= 1 && inside && t > 0.0f && !(t > L.t_best)) {
         F4 lo, hi; S.lf(YF_ASINT(c.w), lo, hi); float e;
         inside = box_hit(L.r, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, e);
     }
@@ -170,6 +195,7 @@ void sim_tri(SimLane& L, const SimScene& S, bool any_q)
 }
 }
 
+namespace { inline bool any_q_of(int any) { return any != 0; } }
 // knobs[4] = refill_idle, phase_min (tri_min), inner_min, inner_chain;  util[4] = inner steps, lanes in them, tri steps, lanes in them
 extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
                              const yune_bvh_node* nodes, int nnodes, int* tri_id, float* t_hit, int accel, const int* knobs,
@@ -178,8 +204,8 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
     accel = lay.accel;
-    if (accel == 2) return -1;                       // the device scheduling restated here walks pair records only
-    SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel};
+    SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel, {lay.quads.data()}};
+    auto sim_step = [&](SimLane& L) { if (accel == 2) sim_inner_wide(L, S, any_q_of(any)); else sim_inner(L, S, any_q_of(any)); };
     const int refill_idle = knobs[0], tri_min = knobs[1], inner_min = knobs[2], inner_chain = knobs[3];
     const bool any_q = any != 0;
     std::vector<SimLane> W(32);
@@ -205,11 +231,11 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
             if (nb < busy_min) break;
             if (nt >= tri_min || nt > ni) { st[2]++; st[3] += nt; for (auto& L : W) if (L.pend_pos < L.pend_end) sim_tri(L, S, any_q); }
             else {
-                st[0]++; st[1] += ni; for (auto& L : W) if (L.cur >= 0) sim_inner(L, S, any_q);
+                st[0]++; st[1] += ni; for (auto& L : W) if (L.cur >= 0) sim_step(L);
                 for (int k = 0; k < inner_chain; k++) {
                     int c = 0; for (auto& L : W) c += L.cur >= 0;
                     if (c < inner_min) break;
-                    st[0]++; st[1] += c; for (auto& L : W) if (L.cur >= 0) sim_inner(L, S, any_q);
+                    st[0]++; st[1] += c; for (auto& L : W) if (L.cur >= 0) sim_step(L);
                 }
             }
         }

@@ -94,7 +94,7 @@ def test_layout_rejects_malformed_input(hc):
     assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(bad), int(bad.size), ptr(LIGHT_UDPT), 1, ptr(tri), ptr(light), None, None, 0, 0) == -1
 
 
-@pytest.mark.parametrize("accel", [0, 1])
+@pytest.mark.parametrize("accel", [0, 1, 2])
 def test_device_scheduling_restatement_is_order_free(hc, oracle, accel):
     """The DEVICE walk postpones leaves, votes per step and refills idle lanes (kernels.cu); tests/hostcheck restates that
     scheduling for simulated 32-lane warps on top of trace_core.h's arithmetic.  Whatever the knobs, and whichever rays share a

@@ -6,6 +6,7 @@
 #include "lights.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 using namespace yune;
 
@@ -202,7 +203,8 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
                              unsigned long long* util)
 {
     TravLayoutHost lay; std::string err;
-    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
+    const char* leaf_env = std::getenv("YUNE_SIM_LEAF");             // development: own-tree leaf size for the step model
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : (leaf_env ? std::atoi(leaf_env) : 0), accel)) return -1;
     accel = lay.accel;
     SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel, {lay.quads.data()}};
     auto sim_step = [&](SimLane& L) { if (accel == 2) sim_inner_wide(L, S, any_q_of(any)); else sim_inner(L, S, any_q_of(any)); };

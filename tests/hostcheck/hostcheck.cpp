@@ -231,7 +231,10 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
             int ni = 0, nt = 0, nb = 0;
             for (auto& L : W) { ni += L.cur >= 0; nt += L.pend_pos < L.pend_end; nb += busy(L); }
             if (nb < busy_min) break;
-            if (nt >= tri_min || nt > ni) { st[2]++; st[3] += nt; for (auto& L : W) if (L.pend_pos < L.pend_end) sim_tri(L, S, any_q); }
+            static const int rule = [] { const char* e = std::getenv("YUNE_SIM_TRI_RULE"); return e ? std::atoi(e) : 0; }();      // development: other vote rules
+            const bool tri_now = rule == 0 ? (nt >= tri_min || nt > ni) : rule == 1 ? (nt >= tri_min || ni == 0) : rule == 2 ? (nt >= tri_min || nt > 2 * ni)
+                                : (nt >= tri_min || (nt > ni && ni < 8));
+            if (tri_now) { st[2]++; st[3] += nt; for (auto& L : W) if (L.pend_pos < L.pend_end) sim_tri(L, S, any_q); }
             else {
                 st[0]++; st[1] += ni; for (auto& L : W) if (L.cur >= 0) sim_step(L);
                 for (int k = 0; k < inner_chain; k++) {
@@ -239,6 +242,58 @@ extern "C" int hc_trace_warp(int n, const float* od6, const float* tmax, int any
                     if (c < inner_min) break;
                     st[0]++; st[1] += c; for (auto& L : W) if (L.cur >= 0) sim_step(L);
                 }
+            }
+        }
+    }
+    if (util) for (int i = 0; i < 4; i++) util[i] = st[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Design aid (no product path): the same scheduling with R ray slots per lane.  A lane takes part in a step when ANY of its
+// slots wants the voted operation (one slot advances per lane and step), which is what raises the lanes per step; the price on
+// the device would be R times the per-ray registers and stack.  util as in hc_trace_warp (lanes = lanes, not slots).
+extern "C" int hc_trace_warp_multi(int n, const float* od6, const float* tmax, int any, const yune_triangle* tris, int ntri,
+                                   const yune_bvh_node* nodes, int nnodes, int* tri_id, float* t_hit, int accel, const int* knobs,
+                                   int rays_per_lane, unsigned long long* util)
+{
+    if (rays_per_lane < 1 || rays_per_lane > 4) return -1;
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, accel == 0 ? 2 : 0, accel)) return -1;
+    accel = lay.accel;
+    const bool any_q = any != 0;
+    SimScene S{&lay, {lay.pairs.data()}, {lay.tris.data()}, {lay.leaf_boxes.data()}, accel, {lay.quads.data()}};
+    const int R = rays_per_lane, NS = 32 * R;
+    const int refill_idle = knobs[0], tri_min = knobs[1], inner_min = knobs[2], inner_chain = knobs[3];
+    std::vector<SimLane> W(NS);
+    for (auto& L : W) { L.have = false; L.cur = REF_DONE; L.pend_pos = L.pend_end = 0; L.sp = STACK_BASE; }
+    int next = 0; unsigned long long st[4] = {0, 0, 0, 0};
+    auto busy = [&](const SimLane& L) { return L.cur >= 0 || L.pend_pos < L.pend_end; };
+    auto lanes_wanting = [&](bool tri) { int c = 0; for (int l = 0; l < 32; l++) { bool w = false; for (int r = 0; r < R; r++) { const SimLane& L = W[l * R + r]; w = w || (tri ? L.pend_pos < L.pend_end : L.cur >= 0); } c += w; } return c; };
+    auto step = [&](bool tri) {
+        for (int l = 0; l < 32; l++) for (int r = 0; r < R; r++) {
+            SimLane& L = W[l * R + r];
+            if (tri ? L.pend_pos < L.pend_end : L.cur >= 0) { if (tri) sim_tri(L, S, any_q); else if (accel == 2) sim_inner_wide(L, S, any_q); else sim_inner(L, S, any_q); break; }
+        }
+    };
+    for (;;) {
+        for (auto& L : W) if (L.have && !busy(L)) { tri_id[L.where] = L.tri; if (t_hit) t_hit[L.where] = L.t_best; L.have = false; }
+        int idle = 0; for (auto& L : W) idle += !L.have;
+        if (idle == NS && next >= n) break;
+        for (auto& L : W) if (!L.have && next < n) {
+            const int q = next++; const float* r = od6 + 6 * (size_t)q;
+            sim_init(L, S, v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), tmax ? tmax[q] : INFINITY);
+            L.where = q; L.have = true;
+        }
+        const int busy_min = next >= n ? 1 : NS + 1 - refill_idle * R;
+        for (;;) {
+            int nb = 0; for (auto& L : W) nb += busy(L);
+            if (nb < busy_min) break;
+            const int ni = lanes_wanting(false), nt = lanes_wanting(true);
+            if (nt >= tri_min || nt > ni) { st[2]++; st[3] += nt; step(true); }
+            else {
+                st[0]++; st[1] += ni; step(false);
+                for (int k = 0; k < inner_chain; k++) { const int c = lanes_wanting(false); if (c < inner_min) break; st[0]++; st[1] += c; step(false); }
             }
         }
     }

@@ -232,3 +232,24 @@ def test_wide_tree_model_finds_the_same_hits(hc):
     assert res[2][3] == res[4][3] == res[8][3]
     assert res[4][0] < 0.6 * res[2][0] and res[4][1] < 1.1 * res[2][1] and res[8][0] < res[4][0]
     assert hc.hc_wide_stats(n, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), 9, ptr(out)) == -1
+
+
+@pytest.mark.parametrize("accel", [1, 2])
+def test_ray_slots_model_is_order_free(hc, oracle, accel):
+    """hc_trace_warp_multi (design aid behind DESIGN.md's ray-slot figures): two or three ray slots per lane change when a ray
+    advances, never its hit record; lanes per triangle step go up."""
+    tris, mats, nodes = load_golden_scene("teapot")
+    rng = np.random.RandomState(41); n = 12000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    otri, olight, ot = oracle.trace(Oracle.config("udpt"), od, None, 0, tris, nodes)
+    free = olight < 0
+    k = np.array([12, 24, 16, 8], np.int32); lanes = {}
+    for R in (1, 2, 3):
+        tri = np.zeros(n, np.int32); t = np.zeros(n, np.float32); util = np.zeros(4, np.uint64)
+        assert hc.hc_trace_warp_multi(n, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(tri), ptr(t), accel, ptr(k), R, ptr(util)) == 0
+        assert (tri[free] == otri[free]).all() and (t[free].view(np.uint32) == ot[free].view(np.uint32)).all(), R
+        lanes[R] = float(util[3]) / float(util[2])
+    assert lanes[2] > lanes[1] + 4 and lanes[3] > lanes[2]
+    assert hc.hc_trace_warp_multi(n, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(tri), ptr(t), accel, ptr(k), 5, None) == -1

@@ -373,7 +373,7 @@ extern "C" int hc_wide_stats(int n, const float* od6, const float* tmax, int any
             const WideNode& w = wide[ref]; visits++; boxes += w.n;
             std::pair<float, int> hit[8]; int nh = 0;
             for (int k = 0; k < w.n; k++) { float e; if (box_hit_own(ray, w.lo[k][0], w.hi[k][0], w.lo[k][1], w.hi[k][1], w.lo[k][2], w.hi[k][2], t_prune, e)) hit[nh++] = {e, w.ref[k]}; }
-            if (!any) std::sort(hit, hit + nh, [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+            if (!any) for (int a = 1; a < nh; a++) { const std::pair<float, int> v = hit[a]; int b = a; while (b > 0 && hit[b - 1].first < v.first) { hit[b] = hit[b - 1]; b--; } hit[b] = v; }      // farthest first
             for (int k = 0; k < nh; k++) stack.push_back(hit[k].second);      // nearest on top
         }
         hits += tri >= 0;

@@ -72,7 +72,7 @@ extern "C" int hc_layout_info(const yune_triangle* tris, int ntri, const yune_bv
 {
     TravLayoutHost lay; std::string err;
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
-    out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = lay.max_depth; out[3] = accel == 2 ? lay.n_wide : lay.n_inner_ref;
+    out[0] = lay.n_inner; out[1] = lay.n_leaf_tris; out[2] = accel == 2 ? lay.wide_depth : lay.max_depth; out[3] = accel == 2 ? lay.n_wide : lay.n_inner_ref;
     return 0;
 }
 

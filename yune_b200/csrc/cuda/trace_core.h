@@ -280,25 +280,44 @@ YUNE_HD void trace_own(const PairFetch& fetch_pair, const TriFetch& fetch_tri, c
 // ---- accel 2: the own tree with up to four children per node (trav_layout.h `quads`) ----
 // One step fetches a 112-byte record, tests the (up to) four child boxes, enters the nearest hit child and pushes the others
 // far to near.  Leaves are the same triangle ranges as in accel 1, tested by ts_tri_step_own.
+// Ascending sort of four (entry, ref) pairs with the 5-comparator network (0,1)(2,3)(0,2)(1,3)(1,2): branch-free selects, the
+// form the device step will use.  Misses carry entry = +inf and sink to the end; the order among equal entries is irrelevant
+// (hit records do not depend on the visiting order, tests/test_traversal_hostcheck.py).
+YUNE_HD void cmp_swap(float& ea, int& ra, float& eb, int& rb)
+{
+    const bool sw = eb < ea;
+    const float e_lo = sw ? eb : ea, e_hi = sw ? ea : eb; const int r_lo = sw ? rb : ra, r_hi = sw ? ra : rb;
+    ea = e_lo; eb = e_hi; ra = r_lo; rb = r_hi;
+}
+YUNE_HD void sort4(float* e, int* r)
+{
+    cmp_swap(e[0], r[0], e[1], r[1]); cmp_swap(e[2], r[2], e[3], r[3]);
+    cmp_swap(e[0], r[0], e[2], r[2]); cmp_swap(e[1], r[1], e[3], r[3]);
+    cmp_swap(e[1], r[1], e[2], r[2]);
+}
 template <class QuadFetch, bool ANY, bool COUNT>
 YUNE_HD void ts_inner_step_wide(TraceState& s, int* stack, const QuadFetch& fetch_quad, WorkCount* wc)
 {
     F4 q[7];
     fetch_quad(s.cur, q);
     const float* f = &q[0].x;
-    const int refs[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
-    float e[4]; int ref[4]; int n = 0;
+    int ref[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
+    float e[4]; int n = 0;
     for (int i = 0; i < 4; i++) {
-        if (refs[i] == YUNE_REF_EMPTY) continue;
-        if (COUNT) wc->box++;
         float ent;
-        if (!box_hit_own(s.r, f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], s.t_prune, ent)) continue;
-        int k = n++;                                                  // insertion sort, nearest first (ANY keeps the slot order)
-        if (!ANY) while (k > 0 && e[k - 1] > ent) { e[k] = e[k - 1]; ref[k] = ref[k - 1]; k--; }
-        e[k] = ent; ref[k] = refs[i];
+        const bool used = ref[i] != YUNE_REF_EMPTY;
+        if (COUNT && used) wc->box++;
+        const bool hit = used && box_hit_own(s.r, f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], s.t_prune, ent);
+        e[i] = hit ? fminf(ent, 3.0e38f) : INFINITY;      // a hit's key stays finite: +inf marks a miss
+        n += hit;
     }
+    if (ANY) {       // shadow query: keep the record's order, just move the misses behind the hits (stable compaction)
+        int k = 0; float e2[4]; int r2[4];
+        for (int i = 0; i < 4; i++) if (e[i] < INFINITY) { e2[k] = e[i]; r2[k] = ref[i]; k++; }
+        for (int i = 0; i < k; i++) { e[i] = e2[i]; ref[i] = r2[i]; }
+    } else sort4(e, ref);
     if (n == 0) { ts_pop(s, stack); return; }
-    for (int k = n - 1; k >= 1; k--) stack[s.sp++] = ref[k];
+    for (int k = 3; k >= 1; k--) if (k < n) stack[s.sp++] = ref[k];      // far to near: the nearest pushed child is popped first
     ts_enter(s, ref[0]);
 }
 template <class QuadFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>

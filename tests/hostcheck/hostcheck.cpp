@@ -152,24 +152,9 @@ void sim_inner(SimLane& L, const SimScene& S, bool any_q)
 void sim_inner_wide(SimLane& L, const SimScene& S, bool any_q)
 {
     F4 q[7]; S.qf(L.cur, q);
-    const float* f = &q[0].x;
-    const int refs[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
-    float e[4]; int ref[4]; int n = 0;
-    for (int i = 0; i < 4; i++) {
-        if (refs[i] == YUNE_REF_EMPTY) continue;
-        float ent;
-        if (!box_hit_own(L.r, f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], L.t_prune, ent)) continue;
-        int k = n++;
-        if (!any_q) while (k > 0 && e[k - 1] > ent) { e[k] = e[k - 1]; ref[k] = ref[k - 1]; k--; }
-        e[k] = ent; ref[k] = refs[i];
-    }
-    for (int k = n - 1; k >= 0; k--) L.stack[L.sp++] = ref[k];
-    int c0 = L.stack[L.sp - 1]; L.sp = L.sp - 1 > STACK_BASE ? L.sp - 1 : STACK_BASE;
-    if (c0 < 0 && !(L.pend_pos < L.pend_end)) {
-        const int x = ~c0; L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15);
-        c0 = L.stack[L.sp - 1]; L.sp = L.sp - 1 > STACK_BASE ? L.sp - 1 : STACK_BASE;
-    }
-    L.cur = c0;
+    auto box = [&](float lox, float hix, float loy, float hiy, float loz, float hiz, float& e) { return box_hit_own(L.r, lox, hix, loy, hiy, loz, hiz, L.t_prune, e); };
+    if (any_q) lane_wide_step<SimLane, decltype(box), true>(L, L.stack, q, box, STACK_BASE);
+    else lane_wide_step<SimLane, decltype(box), false>(L, L.stack, q, box, STACK_BASE);
 }
 void sim_tri(SimLane& L, const SimScene& S, bool any_q)
 {

@@ -320,6 +320,40 @@ YUNE_HD void ts_inner_step_wide(TraceState& s, int* stack, const QuadFetch& fetc
     for (int k = 3; k >= 1; k--) if (k < n) stack[s.sp++] = ref[k];      // far to near: the nearest pushed child is popped first
     ts_enter(s, ref[0]);
 }
+// The wide step in the form the DEVICE scheduling needs (postponed leaves, sentinel stack: kernels.cu's Lane and the simulated
+// lanes of tests/hostcheck share the fields used here).  `q` = the seven 16-byte vectors of the record, already fetched;
+// box_test(lox, hix, loy, hiy, loz, hiz, entry) = the conservative slab test against the lane's ray and pruning distance.
+// Every hit child is pushed far to near, then the walk takes its next place: a leaf on top is PARKED when nothing is parked
+// (and the walk moves on to the place after it), otherwise the lane stands on it until its parked triangles have been tested.
+// stack[0 .. stack_base) hold the sentinel `ref_done` (< 0, an empty triangle range), so popping an empty stack ends the walk.
+template <class LaneT, class BoxTest, bool ANY>
+YUNE_HD void lane_wide_step(LaneT& L, int* stack, const F4* q, const BoxTest& box_test, int stack_base)
+{
+    const float* f = &q[0].x;
+    int ref[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
+    float e[4]; int n = 0;
+    for (int i = 0; i < 4; i++) {
+        float ent = 0.0f;
+        const bool hit = ref[i] != YUNE_REF_EMPTY && box_test(f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], ent);
+        e[i] = hit ? fminf(ent, 3.0e38f) : INFINITY;
+        n += hit;
+    }
+    if (ANY) {
+        int k = 0; int r2[4];
+        for (int i = 0; i < 4; i++) if (e[i] < INFINITY) r2[k++] = ref[i];
+        for (int i = 0; i < k; i++) ref[i] = r2[i];
+    } else sort4(e, ref);
+    for (int k = 3; k >= 0; k--) if (k < n) stack[L.sp++] = ref[k];
+    int c0 = stack[L.sp - 1];
+    L.sp = L.sp - 1 > stack_base ? L.sp - 1 : stack_base;
+    if (c0 < 0 && !(L.pend_pos < L.pend_end)) {
+        const int x = ~c0; L.pend_pos = x >> 4; L.pend_end = (x >> 4) + (x & 15);
+        c0 = stack[L.sp - 1];
+        L.sp = L.sp - 1 > stack_base ? L.sp - 1 : stack_base;
+    }
+    L.cur = c0;
+}
+
 template <class QuadFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
 YUNE_HD void trace_wide(const QuadFetch& fetch_quad, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, int root_ref,
                         const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)

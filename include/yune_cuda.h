@@ -67,7 +67,8 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   and engine knobs: "pool_slots" (path slots in flight; 0 = sized per job as 512*sqrt(samples), default;
  *   "pool_slots_in_use" reads back the size of the last render), "smem_nodes" (pair records staged in shared memory; < 0 = all if they fit, else 2340, default),
  *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
- *   0 = walk the reference tree itself), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
+ *   0 = walk the reference tree itself; 2 = EXPERIMENTAL: the own tree collapsed into 4-wide records -- verified on the host build,
+ *   not yet run on a device, not covered by the GPU tests), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
  *   "trace_block", "trace_blocks_per_sm" (trace-kernel launch shape), "refill_idle" (refill a warp once this many lanes are
  *   idle), "phase_min" (run a triangle step once this many lanes hold postponed triangles), "inner_min" / "inner_chain"
  *   (chain up to inner_chain further node steps without a new vote while inner_min lanes can take one),

@@ -175,13 +175,16 @@ static int ensure_scene(yune_ctx* c)
     Y_CUDA(c, cudaMalloc(&c->d_pairs, std::max<size_t>(L.pairs.size(), 4) * 16));
     Y_CUDA(c, cudaMalloc(&c->d_tris, std::max<size_t>(L.tris.size(), 3) * 16));
     Y_CUDA(c, cudaMalloc(&c->d_shade, std::max<size_t>(L.shade.size(), 4) * 16));
-    if (!L.pairs.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_pairs, L.pairs.data(), L.pairs.size() * 16, cudaMemcpyHostToDevice, c->stream));
+    const std::vector<F4>& node_records = L.accel == 2 ? L.quads : L.pairs;       // accel 2: the kernel walks the 4-wide records instead
+    if (L.accel == 2) { dfree(c->d_pairs); Y_CUDA(c, cudaMalloc(&c->d_pairs, std::max<size_t>(node_records.size(), 7) * 16)); }
+    if (!node_records.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_pairs, node_records.data(), node_records.size() * 16, cudaMemcpyHostToDevice, c->stream));
     if (!L.tris.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_tris, L.tris.data(), L.tris.size() * 16, cudaMemcpyHostToDevice, c->stream));
     if (!L.shade.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_shade, L.shade.data(), L.shade.size() * 16, cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
     DevScene& s = c->sc;
     s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats; s.leaf_boxes = c->d_leaf_boxes; s.accel = L.accel;
     s.n_inner = L.n_inner; s.n_tris = L.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = L.root_ref;
+    if (L.accel == 2) { s.n_inner = L.n_wide; s.root_ref = L.root_wide_ref; }
     for (int k = 0; k < 3; k++) { s.root_lo[k] = L.root_lo[k]; s.root_hi[k] = L.root_hi[k]; }
     c->layout_dirty = false;
     return YUNE_OK;
@@ -192,12 +195,14 @@ static int trace_config(yune_ctx* c, TraceLaunch& tl)
 {
     // "smem_nodes" < 0 (default): the whole tree if it fits (the kernel variant without a global node path, +3.5 % on C2), else
     // the first 2340 records -- a bigger staging area would take the L1 capacity that triangles and stacks need (measured).
+    const bool wide = c->sc.accel == 2;                       // 4-wide records: 112 B each, half as many (experimental)
+    const int rec_bytes = wide ? 112 : 56, rec_max = wide ? 1950 : 3900, rec_part = wide ? 1170 : 2340;
     int want = c->opt_smem_nodes;
-    if (want < 0) want = c->sc.n_inner <= 3900 ? c->sc.n_inner : 2340;
+    if (want < 0) want = c->sc.n_inner <= rec_max ? c->sc.n_inner : rec_part;
     int n_smem = want < c->sc.n_inner ? want : c->sc.n_inner;
-    if (n_smem > 3900) n_smem = 3900;                         // 3900 * 56 B = 213 KB < 227 KB
+    if (n_smem > rec_max) n_smem = rec_max;                   // 3900 * 56 B = 1950 * 112 B = 213 KB < 227 KB
     c->sc.n_smem_pairs = n_smem;
-    tl.smem = (size_t)n_smem * 56;                            // 48 B of boxes + 8 B of child refs per staged record
+    tl.smem = (size_t)n_smem * rec_bytes;                     // 48 B of boxes + 8 B of child refs per staged record
     Y_CUDA(c, trace_set_smem(tl.smem > 0 ? tl.smem : 16));
     tl.block = c->opt_trace_block;
     int per_sm = trace_blocks_per_sm(tl.block, tl.smem);
@@ -399,7 +404,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
-    if (p == &c->opt_accel) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree) or 1 (own tree + exact leaf-box filter)"); if (v != *p) c->layout_dirty = true; }
+    if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (experimental: own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     *p = v;
     return YUNE_OK;

@@ -166,6 +166,39 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
     L.pend_end = park ? (x >> 4) + (x & 15) : L.pend_end;
 }
 
+// ACCEL bit 2 (value 4; accel option 2): the own tree collapsed into 4-wide records (trav_layout.h `quads`: 7 float4 per record;
+// sc.pairs points at them, sc.n_inner counts them, the first sc.n_smem_pairs are staged at a 112-byte stride).  The step itself
+// is trace_core.h's lane_wide_step, the function tests/hostcheck runs for simulated warps.  EXPERIMENTAL: verified on the host
+// (bit-exact hit records for every scheduling), not yet run or measured on a device -- DESIGN.md section 10.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void lane_inner_step_wide(Lane& L, int* stack, const DevScene& sc, const uint32_t s_quad, WorkCount& wc)
+{
+    F4 q[7];
+    if (L.cur < sc.n_smem_pairs) {
+        const uint32_t p = s_quad + 112u * (uint32_t)L.cur;
+        #pragma unroll
+        for (int k = 0; k < 7; k++) { const float4 v = lds128(p + 16u * k); q[k].x = v.x; q[k].y = v.y; q[k].z = v.z; q[k].w = v.w; }
+    } else {
+        const float4* p = sc.pairs + 7 * (size_t)L.cur;
+        #pragma unroll
+        for (int k = 0; k < 7; k++) { const float4 v = __ldg(p + k); q[k].x = v.x; q[k].y = v.y; q[k].z = v.z; q[k].w = v.w; }
+    }
+    if (COUNT) wc.box += 4;
+    auto box = [&](float lox, float hix, float loy, float hiy, float loz, float hiz, float& e) -> bool {
+        if (!L.guard) return box_own(L, lox, hix, loy, hiy, loz, hiz, e);
+        e = box_guarded(L.o, L.inv, lox, hix, loy, hiy, loz, hiz);         // entry >= 0 on a hit, -1 on a miss
+        return e >= 0.0f && !(e > L.t_prune);
+    };
+    lane_wide_step<Lane, decltype(box), ANY>(L, stack, q, box, YUNE_STACK_BASE);
+}
+
+template <bool ANY, bool COUNT, int ACCEL>
+__device__ __forceinline__ void lane_node_step(Lane& L, int* stack, const DevScene& sc, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)
+{
+    if (ACCEL & 4) lane_inner_step_wide<ANY, COUNT>(L, stack, sc, s_box, wc);
+    else lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+}
+
 template <bool ANY, bool COUNT, int ACCEL>
 __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, WorkCount& wc)
 {
@@ -295,10 +328,10 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
             const int ni = __popc(bi), nt = __popc(bt);
             if (nt >= tri_min || nt > ni) { if (wt) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc); }
             else {
-                if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
                 #pragma unroll 1
                 for (int k = 0; k < inner_chain && __popc(__ballot_sync(0xffffffffu, L.cur >= 0)) >= inner_min; k++) {
-                    if (L.cur >= 0) lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                    if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
                 }
             }
             __syncwarp();
@@ -312,6 +345,9 @@ __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
     extern __shared__ float4 s_box[];                    // [3 * n_smem_pairs] boxes, then [n_smem_pairs] int2 child refs
     const DevScene& sc = A.sc;
     int2* s_ref = reinterpret_cast<int2*>(s_box + 3 * sc.n_smem_pairs);
+    if (ACCEL & 4) {                                     // wide records are staged as they are (7 float4 = 112 bytes each)
+        for (int i = threadIdx.x; i < sc.n_smem_pairs * 7; i += blockDim.x) s_box[i] = __ldg(sc.pairs + i);
+    } else
     for (int i = threadIdx.x; i < sc.n_smem_pairs * 4; i += blockDim.x) {
         const float4 v = __ldg(sc.pairs + i);
         const int node = i >> 2, k = i & 3;
@@ -789,7 +825,8 @@ static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
     const bool all_staged = a.sc.n_smem_pairs >= a.sc.n_inner;      // the whole tree is in shared memory: variant without the global node path
-    if (a.sc.accel == 1 && all_staged && !count) k_trace<false, 3><<<grid, block, smem_bytes, st>>>(a);
+    if (a.sc.accel == 2) { if (count) k_trace<true, 5><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 5><<<grid, block, smem_bytes, st>>>(a); }
+    else if (a.sc.accel == 1 && all_staged && !count) k_trace<false, 3><<<grid, block, smem_bytes, st>>>(a);
     else if (a.sc.accel == 1) { if (count) k_trace<true, 1><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 1><<<grid, block, smem_bytes, st>>>(a); }
     else                 { if (count) k_trace<true, 0><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 0><<<grid, block, smem_bytes, st>>>(a); }
     return cudaGetLastError();
@@ -801,6 +838,8 @@ cudaError_t trace_set_smem(size_t smem_bytes)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     return e;
 }
 int trace_blocks_per_sm(int block, size_t smem_bytes)

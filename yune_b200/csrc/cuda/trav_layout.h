@@ -62,8 +62,8 @@ struct TravLayoutHost {
 //
 //        2 = accel 1's tree collapsed into nodes of up to FOUR children (`quads`; half the steps per ray at the same number of
 //            box tests).  Host-verified groundwork for the next trace kernel: the layout and the walk in
-//            trace_core.h are pinned against the oracle by tests/test_traversal_hostcheck.py; the device does not use it yet
-//            (the C ABI's "accel" option accepts 0 and 1 only).
+//            trace_core.h are pinned against the oracle by tests/test_traversal_hostcheck.py.  The device kernel variant that
+//            calls the same step (k_trace<., 5>, option "accel" = 2) compiles but has not been run on a GPU yet.
 //
 // n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
 //        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.

@@ -433,35 +433,6 @@ def test_ragged_image_sizes_match_oracle(gpu_manager, oracle, W, H):
     assert (r.readSum()[..., 3] == 4).all()
 
 
-@pytest.mark.parametrize("kind,n,seed", [("uniform", 1500, 31), ("clustered", 1200, 32), ("flats", 1000, 33), ("mixed", 1800, 34)])
-def test_random_soups_bit_exact(gpu_manager, oracle, kind, n, seed):
-    """Random triangle soups (tests/helpers.random_soup: overlapping boxes, padded flats, slivers over four decades, empty
-    children) -- the same scenes and rays tests/test_traversal_hostcheck.py walks on the CPU -- through the device kernels:
-    closest hits bit-exact against the oracle's breadth-first walk, same occlusion answers, for the own-tree walk (default)
-    and the walk over the reference tree."""
-    from tests.helpers import random_soup, soup_rays
-    m = gpu_manager
-    rng = np.random.default_rng(seed)
-    T = random_soup(rng, n, kind)
-    sc = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
-    od, tm = soup_rays(rng, T, 200000)
-    cfg = Oracle.config("udpt", heap_size=0)
-    otri, olight, ot = oracle.trace(cfg, od, None, 0, sc.vert_data, sc.bvh)
-    stri, slight, _ = oracle.trace(cfg, od, tm, 1, sc.vert_data, sc.bvh)
-    assert (otri >= 0).mean() > 0.3
-    try:
-        for accel in (1, 0):
-            m.setOption("accel", accel)
-            r = yb.RendererCore(m, 32, 32)
-            assert m.createRenderProgram("udpt.cl") and r.setup(sc), m.last_message
-            tri, light, t = r.traceRays(od)
-            assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all(), accel
-            atri, _, _ = r.traceRays(od, tm, any_hit=True)
-            assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all(), accel
-    finally:
-        m.setOption("accel", 1)
-
-
 @pytest.mark.parametrize("scene", ["cornellbox", "teapot"])
 def test_brute_force_mode_bvh_size_zero(gpu_manager, oracle, scene):
     """Kernel arg 6 bvh_size == 0 (udpt.cl:280-284: every triangle in index order, no box tests): hit records equal to the
@@ -530,3 +501,32 @@ def test_headless_cli_writes_png_and_jpg(gpu_manager, tmp_path):
     want3 = (np.clip(np.nan_to_num(r.readLDR()[::-1, :, :3]), 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8)
     got3 = np.asarray(Image.open(shot).convert("RGB"))
     assert np.abs(got3.astype(int) - want3.astype(int)).max() <= 1 and np.abs(got3.astype(int) - want.astype(int)).max() > 1
+
+
+@pytest.mark.parametrize("kind,n,seed", [("uniform", 1500, 31), ("clustered", 1200, 32), ("flats", 1000, 33), ("mixed", 1800, 34)])
+def test_random_soups_bit_exact(gpu_manager, oracle, kind, n, seed):
+    """Random triangle soups (tests/helpers.random_soup: overlapping boxes, padded flats, slivers over four decades, empty
+    children) -- the same scenes and rays tests/test_traversal_hostcheck.py walks on the CPU -- through the device kernels:
+    closest hits bit-exact against the oracle's breadth-first walk, same occlusion answers, for the own-tree walk (default)
+    and the walk over the reference tree."""
+    from tests.helpers import random_soup, soup_rays
+    m = gpu_manager
+    rng = np.random.default_rng(seed)
+    T = random_soup(rng, n, kind)
+    sc = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
+    od, tm = soup_rays(rng, T, 200000)
+    cfg = Oracle.config("udpt", heap_size=0)
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, sc.vert_data, sc.bvh)
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, sc.vert_data, sc.bvh)
+    assert (otri >= 0).mean() > 0.3
+    try:
+        for accel in (1, 0):
+            m.setOption("accel", accel)
+            r = yb.RendererCore(m, 32, 32)
+            assert m.createRenderProgram("udpt.cl") and r.setup(sc), m.last_message
+            tri, light, t = r.traceRays(od)
+            assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all(), accel
+            atri, _, _ = r.traceRays(od, tm, any_hit=True)
+            assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all(), accel
+    finally:
+        m.setOption("accel", 1)

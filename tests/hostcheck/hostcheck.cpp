@@ -153,8 +153,21 @@ void sim_inner_wide(SimLane& L, const SimScene& S, bool any_q)
 {
     F4 q[7]; S.qf(L.cur, q);
     auto box = [&](float lox, float hix, float loy, float hiy, float loz, float hiz, float& e) { return box_hit_own(L.r, lox, hix, loy, hiy, loz, hiz, L.t_prune, e); };
-    if (any_q) lane_wide_step<SimLane, decltype(box), true>(L, L.stack, q, box, STACK_BASE);
-    else lane_wide_step<SimLane, decltype(box), false>(L, L.stack, q, box, STACK_BASE);
+    if (std::getenv("YUNE_SIM_WIDE_V1")) {          // the first form of the step (pushes through memory, record order for shadow queries)
+        if (any_q) lane_wide_step<SimLane, decltype(box), true>(L, L.stack, q, box, STACK_BASE);
+        else lane_wide_step<SimLane, decltype(box), false>(L, L.stack, q, box, STACK_BASE);
+        return;
+    }
+    // the device form (kernels.cu lane_inner_step_wide): keys + lane_wide_finish, distance order for both query kinds
+    const int top1 = L.stack[L.sp - 1], top2 = L.stack[L.sp - 2];
+    const float* f = &q[0].x;
+    int k[4], r[4] = {YF_ASINT(q[6].x), YF_ASINT(q[6].y), YF_ASINT(q[6].z), YF_ASINT(q[6].w)};
+    for (int i = 0; i < 4; i++) {
+        float e = 0.0f;
+        const bool hit = r[i] != YUNE_REF_EMPTY && box(f[i], f[4 + i], f[8 + i], f[12 + i], f[16 + i], f[20 + i], e);
+        k[i] = hit ? YF_ASINT(e) : YUNE_KEY_MISS;
+    }
+    lane_wide_finish(L, L.stack, top1, top2, k[0], k[1], k[2], k[3], r[0], r[1], r[2], r[3]);
 }
 void sim_tri(SimLane& L, const SimScene& S, bool any_q)
 {

@@ -84,6 +84,8 @@ struct yune_ctx {
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
+    int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache
+
     yune_stats stats{};
 };
 
@@ -191,22 +193,31 @@ static int ensure_scene(yune_ctx* c)
 }
 
 struct TraceLaunch { int grid, block; size_t smem; };
-static int trace_config(yune_ctx* c, TraceLaunch& tl)
+static int trace_config(yune_ctx* c, TraceLaunch& tl, bool count)
 {
     // "smem_nodes" < 0 (default): the whole tree if it fits (the kernel variant without a global node path, +3.5 % on C2), else
     // the first 2340 records -- a bigger staging area would take the L1 capacity that triangles and stacks need (measured).
-    const bool wide = c->sc.accel == 2;                       // 4-wide records: 112 B each, half as many (experimental)
-    const int rec_bytes = wide ? 112 : 56, rec_max = wide ? 1950 : 3900, rec_part = wide ? 1170 : 2340;
+    const bool wide = c->sc.accel == 2;                       // 4-wide records: 112 B each, half as many
+    tl.block = c->opt_trace_block;
+    const int ray_bytes = wide ? 32 * tl.block : 0;           // the wide kernel keeps (o, d, u, v) of every lane in shared memory
+    const int rec_bytes = wide ? 112 : 56, rec_max = wide ? (232448 - 1024 - ray_bytes) / 112 : 3900, rec_part = wide ? 1170 : 2340;
     int want = c->opt_smem_nodes;
     if (want < 0) want = c->sc.n_inner <= rec_max ? c->sc.n_inner : rec_part;
     int n_smem = want < c->sc.n_inner ? want : c->sc.n_inner;
     if (n_smem > rec_max) n_smem = rec_max;                   // 3900 * 56 B = 1950 * 112 B = 213 KB < 227 KB
     c->sc.n_smem_pairs = n_smem;
-    tl.smem = (size_t)n_smem * rec_bytes;                     // 48 B of boxes + 8 B of child refs per staged record
-    Y_CUDA(c, trace_set_smem(tl.smem > 0 ? tl.smem : 16));
-    tl.block = c->opt_trace_block;
-    int per_sm = trace_blocks_per_sm(tl.block, tl.smem);
-    if (per_sm < 1) Y_FAIL(c, YUNE_ERR_CUDA, "trace kernel does not fit on an SM with %zu bytes of shared memory", tl.smem);
+    tl.smem = (size_t)n_smem * rec_bytes + ray_bytes;         // 48 B of boxes + 8 B of child refs per staged record
+    if (tl.smem < 16) tl.smem = 16;
+    // the attribute and the occupancy belong to ONE instantiation, block size and staging size: asked once per combination and
+    // kept in the context (not in function statics: contexts live on different devices)
+    const int variant = trace_variant_id(c->sc, count);
+    if (c->tc_variant != variant || c->tc_block != tl.block || c->tc_smem != tl.smem) {
+        int per_sm = 0;
+        Y_CUDA(c, trace_prepare(c->sc, count, tl.block, tl.smem, &per_sm));
+        if (per_sm < 1) Y_FAIL(c, YUNE_ERR_CUDA, "trace kernel does not fit on an SM with %zu bytes of shared memory", tl.smem);
+        c->tc_variant = variant; c->tc_block = tl.block; c->tc_smem = tl.smem; c->tc_per_sm = per_sm;
+    }
+    int per_sm = c->tc_per_sm;
     if (c->opt_trace_blocks_per_sm > 0 && per_sm > c->opt_trace_blocks_per_sm) per_sm = c->opt_trace_blocks_per_sm;
     tl.grid = c->sm_count * per_sm;
     return YUNE_OK;
@@ -430,7 +441,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
     if ((rc = ensure_pool(c, (unsigned long long)c->W * c->H * (unsigned long long)spp_count)) != YUNE_OK) return rc;
     TraceLaunch tl;
-    if ((rc = trace_config(c, tl)) != YUNE_OK) return rc;
+    if ((rc = trace_config(c, tl, c->opt_count_work != 0)) != YUNE_OK) return rc;
 
     const size_t n_pix = (size_t)c->W * c->H;
     if (reset) Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n_pix * 16, c->stream));
@@ -619,7 +630,7 @@ static int ensure_hook(yune_ctx* c, int n)
 static int hook_trace(yune_ctx* c, int n, int any)
 {
     TraceLaunch tl; int rc;
-    if ((rc = trace_config(c, tl)) != YUNE_OK) return rc;
+    if ((rc = trace_config(c, tl, false)) != YUNE_OK) return rc;
     int h_cnt[4] = {any ? 0 : n, 0, any ? n : 0, 0};       // n_extend, fetch_extend, n_shadow, fetch_shadow
     Y_CUDA(c, cudaMemcpyAsync(c->hk_cnt, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, c->stream));
     TraceArgs t{};

@@ -38,6 +38,7 @@ struct Lane {
     V3 o, d, inv, oi;       // oi = o * inv: fused slab test of our own tree (ACCEL 1)
     float t_best, t_prune, u, v;
     int tri, best_pos, cur, pend_pos, pend_end, sp;
+    int sgn;                // ACCEL bit 2: byte k = 16 when d[k] < 0 (which of a wide record's lo / hi vectors holds the NEAR planes)
     bool guard;
 };
 
@@ -51,6 +52,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128v(uint32_t addr)       // ordered against the stores above (a lane re-reads what it wrote)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ int2 lds64(uint32_t addr)
@@ -92,23 +104,31 @@ __device__ __forceinline__ bool box_own(const Lane& L, float lox, float hix, flo
     return YF_MUL(t_max, 1.0000021f) >= t_min;        // (t_min >= 0) at least as wide as t_max (1 + 1e-6) >= t_min (1 - 1e-6)
 }
 
+// ACCEL bit 2 keeps the part of a ray that node steps never touch -- origin, direction, the barycentrics of the best hit -- in
+// SHARED memory next to the staged records (two float4 per thread: (o.xyz, u) at s_ray, (d.xyz, v) at s_ray + 16 * blockDim.x;
+// a warp's LDS.128 / STS.128 are conflict-free).  The wide step holds 24 plane values + 4 refs + 4 keys at once; with the whole
+// ray in registers ptxas spilled the walk's own state (sp, the parked range, the loop counter) around every step.
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o, float4 d, WorkCount& wc)
+__device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o, float4 d, WorkCount& wc, const uint32_t s_ray)
 {
-    L.o = xyz(o); L.d = xyz(d);
+    if (ACCEL & 4) { sts128(s_ray, make_float4(o.x, o.y, o.z, 0.0f)); sts128(s_ray + 16u * blockDim.x, make_float4(d.x, d.y, d.z, 0.0f)); }
+    else { L.o = xyz(o); L.d = xyz(d); L.u = 0.0f; L.v = 0.0f; }
     L.inv = v3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));       // correctly rounded 1/x == '1 / ray->dir' (udpt.cl:395)
     L.guard = !(fabsf(L.inv.x) < INFINITY && fabsf(L.inv.y) < INFINITY && fabsf(L.inv.z) < INFINITY);
     L.t_best = o.w; L.t_prune = o.w * 1.00001f;
-    L.u = 0.0f; L.v = 0.0f; L.tri = -1; L.best_pos = -1; L.sp = YUNE_STACK_BASE;
-    L.oi = v3(YF_MUL(L.o.x, L.inv.x), YF_MUL(L.o.y, L.inv.y), YF_MUL(L.o.z, L.inv.z));
+    L.tri = -1; L.best_pos = -1; L.sp = YUNE_STACK_BASE;
+    L.oi = v3(YF_MUL(o.x, L.inv.x), YF_MUL(o.y, L.inv.y), YF_MUL(o.z, L.inv.z));
+    if (ACCEL & 1)      // o * (1/d) can overflow although 1/d is finite: lo * inv - oi would then be -inf for both planes (box lost)
+        L.guard = L.guard || !(fabsf(L.oi.x) < INFINITY && fabsf(L.oi.y) < INFINITY && fabsf(L.oi.z) < INFINITY);
+    if (ACCEL & 4) L.sgn = (L.inv.x < 0.0f ? 16 : 0) | (L.inv.y < 0.0f ? 16 << 8 : 0) | (L.inv.z < 0.0f ? 16 << 16 : 0);
     bool hit = sc.root_ref != YUNE_REF_EMPTY;
     if ((ACCEL & 1) == 0 && hit) {
         // the reference tests the root box first (udpt.cl:295-296).  With ACCEL 1 the boxes of our own tree only prune -- what the
         // reference would have reached is decided per triangle by the leaf-box filter -- so the root test is skipped there.
         float entry;
         if (COUNT) wc.box++;
-        if (L.guard) { entry = box_guarded(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]); hit = entry >= 0.0f; }
-        else hit = box_fast(L.o, L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
+        if (L.guard) { entry = box_guarded(xyz(o), L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2]); hit = entry >= 0.0f; }
+        else hit = box_fast(xyz(o), L.inv, sc.root_lo[0], sc.root_hi[0], sc.root_lo[1], sc.root_hi[1], sc.root_lo[2], sc.root_hi[2], entry);
     }
     const int ref = hit ? sc.root_ref : YUNE_REF_DONE;
     const int x = ~ref;                                                 // a root that is a leaf is parked at once
@@ -166,43 +186,86 @@ __device__ __forceinline__ void lane_inner_step(Lane& L, int* stack, const DevSc
     L.pend_end = park ? (x >> 4) + (x & 15) : L.pend_end;
 }
 
-// ACCEL bit 2 (value 4; accel option 2): the own tree collapsed into 4-wide records (trav_layout.h `quads`: 7 float4 per record;
-// sc.pairs points at them, sc.n_inner counts them, the first sc.n_smem_pairs are staged at a 112-byte stride).  The step itself
-// is trace_core.h's lane_wide_step, the function tests/hostcheck runs for simulated warps.  EXPERIMENTAL: verified on the host
-// (bit-exact hit records for every scheduling), not yet run or measured on a device -- DESIGN.md section 10.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void lane_inner_step_wide(Lane& L, int* stack, const DevScene& sc, const uint32_t s_quad, WorkCount& wc)
+// ACCEL bit 2 (value 4; accel option 2): the own tree collapsed into 4-wide records (trav_layout.h `quads`: 7 float4 per record
+// = lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4]; sc.pairs points at them, sc.n_inner counts them, the first
+// sc.n_smem_pairs are staged at a 112-byte stride).  Half the steps of the binary walk for the same number of box tests.
+// The NEAR planes of an axis are the lo vector when d > 0 and the hi vector when d < 0, so the fetch address picks them
+// (Lane::sgn) and a box costs 6 FFMA + 2 three-input min / max instead of 6 FFMA + 6 min / max + 2; an unused slot (lo = 3e38,
+// hi = -3e38) misses by itself.  What the walk does next is trace_core.h's lane_wide_finish (selects only).
+struct WideKeys { int k0, k1, k2, k3; };
+__device__ __noinline__ WideKeys wide_keys_guarded(V3 o, V3 inv, float t_prune, const float4* q)     // rare: some 1/d (or o/d) is not finite
 {
-    F4 q[7];
-    if (L.cur < sc.n_smem_pairs) {
-        const uint32_t p = s_quad + 112u * (uint32_t)L.cur;
-        #pragma unroll
-        for (int k = 0; k < 7; k++) { const float4 v = lds128(p + 16u * k); q[k].x = v.x; q[k].y = v.y; q[k].z = v.z; q[k].w = v.w; }
-    } else {
-        const float4* p = sc.pairs + 7 * (size_t)L.cur;
-        #pragma unroll
-        for (int k = 0; k < 7; k++) { const float4 v = __ldg(p + k); q[k].x = v.x; q[k].y = v.y; q[k].z = v.z; q[k].w = v.w; }
-    }
+    const float4 lx = q[0], hx = q[1], ly = q[2], hy = q[3], lz = q[4], hz = q[5];
+    const int4 rf = *reinterpret_cast<const int4*>(q + 6);
+    const float e0 = box_guarded(o, inv, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x), e1 = box_guarded(o, inv, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y);
+    const float e2 = box_guarded(o, inv, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z), e3 = box_guarded(o, inv, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w);
+    WideKeys K;
+    K.k0 = (rf.x != YUNE_REF_EMPTY && e0 >= 0.0f && !(e0 > t_prune)) ? __float_as_int(e0) : YUNE_KEY_MISS;
+    K.k1 = (rf.y != YUNE_REF_EMPTY && e1 >= 0.0f && !(e1 > t_prune)) ? __float_as_int(e1) : YUNE_KEY_MISS;
+    K.k2 = (rf.z != YUNE_REF_EMPTY && e2 >= 0.0f && !(e2 > t_prune)) ? __float_as_int(e2) : YUNE_KEY_MISS;
+    K.k3 = (rf.w != YUNE_REF_EMPTY && e3 >= 0.0f && !(e3 > t_prune)) ? __float_as_int(e3) : YUNE_KEY_MISS;
+    return K;
+}
+// The fetches of the wide step are `volatile` asm so that ptxas keeps them in this order: x and y planes first, their partial
+// intervals folded into 8 registers, then the z planes, then the refs and the two stack tops.  Left to itself it hoists all seven
+// LDS.128 (28 registers) above the arithmetic and spills the walk's own state around every step (64 registers per thread).
+__device__ __forceinline__ float4 ld_plane(const bool smem, const uint32_t sa, const char* ga, const int off)
+{
+    float4 v;
+    if (smem) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa + off));
+    else asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ga + off));
+    return v;
+}
+template <bool ANY, bool COUNT, bool ALL_STAGED>
+__device__ __forceinline__ void lane_inner_step_wide(Lane& L, int* stack, const DevScene& sc, const uint32_t s_quad, const uint32_t s_ray, WorkCount& wc)
+{
     if (COUNT) wc.box += 4;
-    auto box = [&](float lox, float hix, float loy, float hiy, float loz, float hiz, float& e) -> bool {
-        if (!L.guard) return box_own(L, lox, hix, loy, hiy, loz, hiz, e);
-        e = box_guarded(L.o, L.inv, lox, hix, loy, hiy, loz, hiz);         // entry >= 0 on a hit, -1 on a miss
-        return e >= 0.0f && !(e > L.t_prune);
-    };
-    lane_wide_step<Lane, decltype(box), ANY>(L, stack, q, box, YUNE_STACK_BASE);
+    const bool smem = ALL_STAGED || L.cur < sc.n_smem_pairs;
+    const uint32_t sa = s_quad + 112u * (uint32_t)L.cur;
+    const char* ga = ALL_STAGED ? nullptr : reinterpret_cast<const char*>(sc.pairs + 7 * (size_t)L.cur);
+    WideKeys K;
+    if (!L.guard) {
+        const int sx = L.sgn & 0xff, sy = (L.sgn >> 8) & 0xff, sz = L.sgn >> 16;
+        const float4 nx = ld_plane(smem, sa, ga, sx), fx = ld_plane(smem, sa, ga, 16 - sx);
+        const float4 ny = ld_plane(smem, sa, ga, 32 + sy), fy = ld_plane(smem, sa, ga, 48 - sy);
+        // per child: t_min = max(near planes, 0), t_max = min(far planes, pruning distance); one FFMA per plane
+        float lo0 = fmaxf(__fmaf_rn(nx.x, L.inv.x, -L.oi.x), __fmaf_rn(ny.x, L.inv.y, -L.oi.y)), hi0 = fminf(__fmaf_rn(fx.x, L.inv.x, -L.oi.x), __fmaf_rn(fy.x, L.inv.y, -L.oi.y));
+        float lo1 = fmaxf(__fmaf_rn(nx.y, L.inv.x, -L.oi.x), __fmaf_rn(ny.y, L.inv.y, -L.oi.y)), hi1 = fminf(__fmaf_rn(fx.y, L.inv.x, -L.oi.x), __fmaf_rn(fy.y, L.inv.y, -L.oi.y));
+        float lo2 = fmaxf(__fmaf_rn(nx.z, L.inv.x, -L.oi.x), __fmaf_rn(ny.z, L.inv.y, -L.oi.y)), hi2 = fminf(__fmaf_rn(fx.z, L.inv.x, -L.oi.x), __fmaf_rn(fy.z, L.inv.y, -L.oi.y));
+        float lo3 = fmaxf(__fmaf_rn(nx.w, L.inv.x, -L.oi.x), __fmaf_rn(ny.w, L.inv.y, -L.oi.y)), hi3 = fminf(__fmaf_rn(fx.w, L.inv.x, -L.oi.x), __fmaf_rn(fy.w, L.inv.y, -L.oi.y));
+        const float4 nz = ld_plane(smem, sa, ga, 64 + sz), fz = ld_plane(smem, sa, ga, 80 - sz);
+        lo0 = fmaxf(lo0, fmaxf(__fmaf_rn(nz.x, L.inv.z, -L.oi.z), 0.0f)); hi0 = fminf(hi0, fminf(__fmaf_rn(fz.x, L.inv.z, -L.oi.z), L.t_prune));
+        lo1 = fmaxf(lo1, fmaxf(__fmaf_rn(nz.y, L.inv.z, -L.oi.z), 0.0f)); hi1 = fminf(hi1, fminf(__fmaf_rn(fz.y, L.inv.z, -L.oi.z), L.t_prune));
+        lo2 = fmaxf(lo2, fmaxf(__fmaf_rn(nz.z, L.inv.z, -L.oi.z), 0.0f)); hi2 = fminf(hi2, fminf(__fmaf_rn(fz.z, L.inv.z, -L.oi.z), L.t_prune));
+        lo3 = fmaxf(lo3, fmaxf(__fmaf_rn(nz.w, L.inv.z, -L.oi.z), 0.0f)); hi3 = fminf(hi3, fminf(__fmaf_rn(fz.w, L.inv.z, -L.oi.z), L.t_prune));
+        // box_own's predicate and entry distance: (t_min >= 0) at least as wide as t_max (1 + 1e-6) >= t_min (1 - 1e-6)
+        K.k0 = YF_MUL(hi0, 1.0000021f) >= lo0 ? __float_as_int(lo0) : YUNE_KEY_MISS;
+        K.k1 = YF_MUL(hi1, 1.0000021f) >= lo1 ? __float_as_int(lo1) : YUNE_KEY_MISS;
+        K.k2 = YF_MUL(hi2, 1.0000021f) >= lo2 ? __float_as_int(lo2) : YUNE_KEY_MISS;
+        K.k3 = YF_MUL(hi3, 1.0000021f) >= lo3 ? __float_as_int(lo3) : YUNE_KEY_MISS;
+    } else {
+        const float4* q = smem ? reinterpret_cast<const float4*>(__cvta_shared_to_generic(sa)) : reinterpret_cast<const float4*>(ga);
+        K = wide_keys_guarded(xyz(lds128v(s_ray)), L.inv, L.t_prune, q);
+    }
+    const float4 r4 = ld_plane(smem, sa, ga, 96);
+    const int top1 = stack[L.sp - 1], top2 = stack[L.sp - 2];       // cur >= 0 implies sp >= YUNE_STACK_BASE
+    lane_wide_finish(L, stack, top1, top2, K.k0, K.k1, K.k2, K.k3, __float_as_int(r4.x), __float_as_int(r4.y), __float_as_int(r4.z), __float_as_int(r4.w));
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void lane_node_step(Lane& L, int* stack, const DevScene& sc, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)
+__device__ __forceinline__ void lane_node_step(Lane& L, int* stack, const DevScene& sc, const uint32_t s_box, const uint32_t s_ref, const uint32_t s_ray, WorkCount& wc)
 {
-    if (ACCEL & 4) lane_inner_step_wide<ANY, COUNT>(L, stack, sc, s_box, wc);
+    if (ACCEL & 4) lane_inner_step_wide<ANY, COUNT, (ACCEL & 2) != 0>(L, stack, sc, s_box, s_ray, wc);
     else lane_inner_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
 }
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, WorkCount& wc)
+__device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const DevScene& sc, const uint32_t s_ray, WorkCount& wc)
 {
     const int top1 = stack[max(L.sp - 1, 0)];
+    V3 ro, rd;
+    if (ACCEL & 4) { ro = xyz(lds128v(s_ray)); rd = xyz(lds128v(s_ray + 16u * blockDim.x)); }
+    else { ro = L.o; rd = L.d; }
     const int pos = L.pend_pos++;
     const float4* p = sc.tris + 3 * (size_t)pos;
     const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -210,13 +273,13 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     // rayTriangleIntersection (udpt.cl:326-373), evaluated without early exits: the rejected lanes would idle anyway, and
     // NaNs (det == 0) fall through the comparisons exactly as in the sequential form.
     const V3 e1 = xyz(b), e2 = xyz(c);
-    const V3 pvec = vcross(L.d, e2);
+    const V3 pvec = vcross(rd, e2);
     const float det = vdot(e1, pvec);
     const float inv_det = __frcp_rn(det);
-    const V3 dist = vsub(L.o, xyz(a));
+    const V3 dist = vsub(ro, xyz(a));
     const float u = YF_MUL(vdot(pvec, dist), inv_det);
     const V3 qvec = vcross(dist, e1);
-    const float v = YF_MUL(vdot(qvec, L.d), inv_det);
+    const float v = YF_MUL(vdot(qvec, rd), inv_det);
     const float t = YF_MUL(vdot(e2, qvec), inv_det);
     bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
     if ((ACCEL & 1) == 1) {
@@ -230,8 +293,8 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
             const float4 lo = __ldg(lb), hi = __ldg(lb + 1);
             float entry; bool reach;
             if (COUNT) wc.box++;
-            if (!L.guard) reach = box_fast(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
-            else reach = box_guarded(L.o, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) >= 0.0f;
+            if (!L.guard) reach = box_fast(ro, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
+            else reach = box_guarded(ro, L.inv, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) >= 0.0f;
             inside = reach;
         }
     }
@@ -242,7 +305,9 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     } else {
         const int rank = __float_as_int(b.w);
         const bool accept = inside && t > 0.0f && (t < L.t_best || (t == L.t_best && L.best_pos >= 0 && rank < L.best_pos));
-        L.t_best = accept ? t : L.t_best; L.u = accept ? u : L.u; L.v = accept ? v : L.v;
+        L.t_best = accept ? t : L.t_best;
+        if (ACCEL & 4) { if (accept) { sts32(s_ray + 12u, u); sts32(s_ray + 16u * blockDim.x + 12u, v); } }
+        else { L.u = accept ? u : L.u; L.v = accept ? v : L.v; }
         L.tri = accept ? __float_as_int(a.w) : L.tri; L.best_pos = accept ? rank : L.best_pos;
         L.t_prune = accept ? t * 1.00001f : L.t_prune;
     }
@@ -266,7 +331,7 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
 #endif
 
 template <bool ANY, bool COUNT, int ACCEL>
-__device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s_box, const uint32_t s_ref, WorkCount& wc)
+__device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s_box, const uint32_t s_ref, const uint32_t s_ray, WorkCount& wc)
 {
     const DevScene& sc = A.sc;
     const int lane = threadIdx.x & 31;
@@ -293,7 +358,8 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
             if (ANY) {
                 const unsigned char vis = L.tri >= 0 ? 0 : 1;
                 if (where >= 0) A.vis_a[where] = vis; else A.vis_b[~where] = vis;
-            } else A.hit[where] = make_float4(L.t_best, L.u, L.v, __int_as_float(L.tri));
+            } else if (ACCEL & 4) A.hit[where] = make_float4(L.t_best, lds128v(s_ray).w, lds128v(s_ray + 16u * blockDim.x).w, __int_as_float(L.tri));
+            else A.hit[where] = make_float4(L.t_best, L.u, L.v, __int_as_float(L.tri));
             have = false;
         }
         // ---- refill: lanes take rays from the warp's private chunk; a new chunk costs one atomic per YUNE_FETCH_CHUNK rays ----
@@ -312,7 +378,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
                 float4 o, d;
                 if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
                 else { where = A.eq ? A.eq[q] : q; const size_t k = (size_t)where * A.ray_stride; o = A.ray_o[k]; d = A.ray_d[k]; }
-                lane_init<ANY, COUNT, ACCEL>(L, sc, o, d, wc);
+                lane_init<ANY, COUNT, ACCEL>(L, sc, o, d, wc, s_ray);
                 have = true;
             }
             chunk_next = min(chunk_next + __popc(idle), chunk_end);
@@ -326,12 +392,12 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
             const unsigned bi = __ballot_sync(0xffffffffu, L.cur >= 0), bt = __ballot_sync(0xffffffffu, wt);
             if (__popc(bi | bt) < busy_min) break;
             const int ni = __popc(bi), nt = __popc(bt);
-            if (nt >= tri_min || nt > ni) { if (wt) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, wc); }
+            if (nt >= tri_min || nt > ni) { if (wt) lane_tri_step<ANY, COUNT, ACCEL>(L, stack, sc, s_ray, wc); }
             else {
-                if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, s_ray, wc);
                 #pragma unroll 1
                 for (int k = 0; k < inner_chain && __popc(__ballot_sync(0xffffffffu, L.cur >= 0)) >= inner_min; k++) {
-                    if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, wc);
+                    if (L.cur >= 0) lane_node_step<ANY, COUNT, ACCEL>(L, stack, sc, s_box, s_ref, s_ray, wc);
                 }
             }
             __syncwarp();
@@ -358,8 +424,9 @@ __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
 
     WorkCount wc; wc.box = 0; wc.tri = 0;
     const uint32_t a_box = (uint32_t)__cvta_generic_to_shared(s_box), a_ref = (uint32_t)__cvta_generic_to_shared(s_ref);
-    trace_queue<true, COUNT, ACCEL>(A, a_box, a_ref, wc);      // shadow rays: any hit
-    trace_queue<false, COUNT, ACCEL>(A, a_box, a_ref, wc);     // extension rays: closest hit
+    const uint32_t a_ray = a_box + 112u * (uint32_t)sc.n_smem_pairs + 16u * threadIdx.x;      // ACCEL bit 2: this thread's (o, u) record
+    trace_queue<true, COUNT, ACCEL>(A, a_box, a_ref, a_ray, wc);      // shadow rays: any hit
+    trace_queue<false, COUNT, ACCEL>(A, a_box, a_ref, a_ray, wc);     // extension rays: closest hit
     if (COUNT) {
         const int lane = threadIdx.x & 31;
         unsigned long long b = wc.box, t = wc.tri;
@@ -426,7 +493,14 @@ __device__ __forceinline__ bool classify_slot(const RenderArgs& A, const int s, 
     bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
     if (state == YS_TRACE || state == YS_DRAIN) {
         const int tri = state == YS_TRACE ? __float_as_int(hit_w) : -1;
-        if (tri >= 0) { to_s = A.sc.tri_class[tri] != 0; to_d = !to_s; }
+        if (tri >= 0) {
+            to_s = A.sc.tri_class[tri] != 0; to_d = !to_s;
+#ifdef YUNE_PREFETCH_RAY
+            // the surface round of this slot runs a chunk or two later and reads the ray record, which classify does not touch:
+            // request it into L2 now so that the round's loads are L2 hits instead of a DRAM round trip
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(P.ray_o.p + 2 * (size_t)s));
+#endif
+        }
         const bool pend = (meta.w & (YF_PEND_EVT | YF_PEND_L)) != 0;
         if (pend || tri < 0) {
             if (!spec) { spec_col = P.col[s]; spec_thr = P.thr[s]; if (meta.w & YF_PEND_L) spec_pend = P.pend_l[s]; }
@@ -822,31 +896,33 @@ __global__ void k_capture(PathPool P, const IterCounters* c, int max_rays, float
 // ------------------------------------------------------------------------------------------------------------
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
 
+// Which instantiation serves a scene: ACCEL bit 0 = own tree + leaf-box filter, bit 1 = every node record is staged in shared
+// memory (no global node path compiled in), bit 2 = 4-wide records.
+typedef void (*TraceKernel)(TraceArgs);
+static TraceKernel trace_kernel(const DevScene& sc, bool count)
+{
+    const bool all_staged = sc.n_smem_pairs >= sc.n_inner;
+    if (sc.accel == 2) return count ? k_trace<true, 5> : (all_staged ? k_trace<false, 7> : k_trace<false, 5>);
+    if (sc.accel == 1) return count ? k_trace<true, 1> : (all_staged ? k_trace<false, 3> : k_trace<false, 1>);
+    return count ? k_trace<true, 0> : k_trace<false, 0>;
+}
+int trace_variant_id(const DevScene& sc, bool count)
+{
+    return sc.accel | (sc.n_smem_pairs >= sc.n_inner ? 4 : 0) | (count ? 8 : 0);
+}
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
-    const bool all_staged = a.sc.n_smem_pairs >= a.sc.n_inner;      // the whole tree is in shared memory: variant without the global node path
-    if (a.sc.accel == 2) { if (count) k_trace<true, 5><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 5><<<grid, block, smem_bytes, st>>>(a); }
-    else if (a.sc.accel == 1 && all_staged && !count) k_trace<false, 3><<<grid, block, smem_bytes, st>>>(a);
-    else if (a.sc.accel == 1) { if (count) k_trace<true, 1><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 1><<<grid, block, smem_bytes, st>>>(a); }
-    else                 { if (count) k_trace<true, 0><<<grid, block, smem_bytes, st>>>(a); else k_trace<false, 0><<<grid, block, smem_bytes, st>>>(a); }
+    trace_kernel(a.sc, count)<<<grid, block, smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t trace_set_smem(size_t smem_bytes)
+// Shared-memory opt-in and resident blocks per SM of the instantiation that will be launched (the caller caches the answer per
+// (variant, block, smem) and per context).
+cudaError_t trace_prepare(const DevScene& sc, bool count, int block, size_t smem_bytes, int* blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    return e;
-}
-int trace_blocks_per_sm(int block, size_t smem_bytes)
-{
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, 1>, block, smem_bytes) != cudaSuccess) return 0;
-    return n;
+    TraceKernel k = trace_kernel(sc, count);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, block, smem_bytes);
 }
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st)
 {

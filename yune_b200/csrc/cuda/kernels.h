@@ -32,8 +32,8 @@ struct TraceArgs {
 };
 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st);
-cudaError_t trace_set_smem(size_t smem_bytes);
-int         trace_blocks_per_sm(int block, size_t smem_bytes);
+cudaError_t trace_prepare(const DevScene& sc, bool count, int block, size_t smem_bytes, int* blocks_per_sm);
+int         trace_variant_id(const DevScene& sc, bool count);
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
 cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st);   // persistent, in-block sorted (default)
 cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, cudaStream_t st);

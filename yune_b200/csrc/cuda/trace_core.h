@@ -354,6 +354,43 @@ YUNE_HD void lane_wide_step(LaneT& L, int* stack, const F4* q, const BoxTest& bo
     L.cur = c0;
 }
 
+// The wide step as the device kernel runs it (accel 2), in two halves so that host and device share everything but the fetch:
+//   keys    k_i = int bits of child i's entry distance (>= 0, so the integer order is the float order), YUNE_KEY_MISS for a miss;
+//           the device computes them from near / far planes picked by the ray's direction signs (one FFMA per plane, no
+//           per-axis min / max: for lo <= hi and a finite 1/d the fused product-difference is monotone, so near <= far and the
+//           values are those of box_hit_own), the host calls box_hit_own;
+//   finish  sorts the four (key, ref) pairs with the 5-comparator network and updates the walk with selects only: the two
+//           places the walk visits next are c0 / c1 (a hit, or the entries read from the top of the stack up front), at most
+//           three refs are stored, each at a position that only depends on the hit count.  Same rules as lane_wide_step.
+#define YUNE_KEY_MISS 0x7f800000
+YUNE_HD void key_cswap(int& ka, int& ra, int& kb, int& rb)
+{
+    const bool sw = kb < ka;
+    const int k_lo = sw ? kb : ka, k_hi = sw ? ka : kb, r_lo = sw ? rb : ra, r_hi = sw ? ra : rb;
+    ka = k_lo; kb = k_hi; ra = r_lo; rb = r_hi;
+}
+template <class LaneT>
+YUNE_HD void lane_wide_finish(LaneT& L, int* stack, int top1, int top2, int k0, int k1, int k2, int k3, int r0, int r1, int r2, int r3)
+{
+    key_cswap(k0, r0, k1, r1); key_cswap(k2, r2, k3, r3);
+    key_cswap(k0, r0, k2, r2); key_cswap(k1, r1, k3, r3);
+    key_cswap(k1, r1, k2, r2);
+    const bool h1 = k0 < YUNE_KEY_MISS, h2 = k1 < YUNE_KEY_MISS, h3 = k2 < YUNE_KEY_MISS, h4 = k3 < YUNE_KEY_MISS;   // at least 1 / 2 / 3 / 4 hits
+    const int n = (h1 ? 1 : 0) + (h2 ? 1 : 0) + (h3 ? 1 : 0) + (h4 ? 1 : 0);
+    const int c0 = h1 ? r0 : top1;
+    const int c1 = h2 ? r1 : (h1 ? top1 : top2);
+    const bool park = c0 < 0 && !(L.pend_pos < L.pend_end);      // c0 is a leaf (or the sentinel: an empty leaf) and nothing is parked
+    const int x = ~c0;
+    int* s = stack + L.sp;
+    if (h4) s[0] = r3;                                            // far to near: r3 (only with four hits) lands lowest
+    if (h3) s[n - 3] = r2;
+    if (h2 && !park) s[n - 2] = r1;                               // with a parked c0 the walk continues at r1 itself
+    L.sp += n - 1 - (park ? 1 : 0);
+    L.cur = park ? c1 : c0;
+    L.pend_pos = park ? (x >> 4) : L.pend_pos;
+    L.pend_end = park ? (x >> 4) + (x & 15) : L.pend_end;
+}
+
 template <class QuadFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
 YUNE_HD void trace_wide(const QuadFetch& fetch_quad, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, int root_ref,
                         const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)

@@ -1,3 +1,3 @@
-for a in 1 2; do for l in 2 3 4; do for b in 1024 768; do
-echo "accel=$a leaf_split=$l trace_block=$b: $(python tools/ab.py --spp 256 --opt accel=$a --opt leaf_split=$l --opt trace_block=$b default)"
-done; done; done
+for l in 2 3; do for n in 900 1100 1300 1500; do
+echo "accel=2 leaf_split=$l smem_nodes=$n: $(python tools/ab.py --spp 256 --opt accel=2 --opt leaf_split=$l --opt smem_nodes=$n default)"
+done; done

@@ -67,8 +67,8 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   and engine knobs: "pool_slots" (path slots in flight; 0 = sized per job as 512*sqrt(samples), default;
  *   "pool_slots_in_use" reads back the size of the last render), "smem_nodes" (pair records staged in shared memory; < 0 = all if they fit, else 2340, default),
  *   "accel" (1 = walk our own SAH tree and filter candidates with the exact box test of their reference leaf, default;
- *   0 = walk the reference tree itself; 2 = EXPERIMENTAL: the own tree collapsed into 4-wide records -- verified on the host build,
- *   not yet run on a device, not covered by the GPU tests), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
+ *   0 = walk the reference tree itself; 2 = the own tree collapsed into 4-wide records: half the node steps, bit-exact like the others,
+ *   measured SLOWER than 1 on B200 because its staging area leaves the L1 2 KB -- DESIGN.md section 5), "leaf_split" (accel 0: refine reference leaves holding more than N triangles; 0 = off),
  *   "trace_block", "trace_blocks_per_sm" (trace-kernel launch shape), "refill_idle" (refill a warp once this many lanes are
  *   idle), "phase_min" (run a triangle step once this many lanes hold postponed triangles), "inner_min" / "inner_chain"
  *   (chain up to inner_chain further node steps without a new vote while inner_min lanes can take one),
@@ -141,6 +141,42 @@ typedef struct yune_stats {
     uint64_t slot_visits;      /* pool slots x shade launches (every launch classifies every slot)        */
 } yune_stats;
 int yune_get_stats(yune_ctx* ctx, yune_stats* out);
+
+/* ---- multi-GPU: the reference is single-device; a drop-in that scales needs this surface ----
+ * The path shards by SAMPLE INDEX: rank r of G renders all pixels for its slice of the sample range into its own fp32
+ * sum buffer (no traffic while rendering), one ncclReduce(sum) over NVLink merges the buffers on the root, the root
+ * tonemaps (yune_tonemap on yune_group_ctx(g, root)).  One process drives every device (ncclCommInitAll; NCCL is bound
+ * at run time with dlopen, so the library has no link-time dependency on it).  A group of one needs no NCCL.
+ * yune_shard_samples is the split rule: contiguous, balanced, the first (count mod n) ranks take one sample more. */
+typedef struct yune_group yune_group;
+typedef struct yune_group_stats {
+    int      n_devices;
+    double   render_ms_max, render_ms_min;   /* slowest / fastest rank of the last yune_group_render (device time) */
+    double   reduce_ms;                      /* last yune_group_reduce, CUDA events on the root's stream            */
+    uint64_t samples, extend_rays, shadow_rays;   /* summed over ranks                                             */
+} yune_group_stats;
+void yune_shard_samples(int spp_begin, int spp_count, int rank, int n_ranks, int* begin, int* count);
+/* devices = NULL: devices 0 .. n-1; n_devices <= 0: every device of the node. */
+int  yune_group_create(int n_devices, const int* devices, yune_group** out_group);
+void yune_group_destroy(yune_group* g);
+int  yune_group_size(const yune_group* g);
+yune_ctx* yune_group_ctx(yune_group* g, int rank);              /* the rank's context, e.g. for read-backs and hooks */
+const char* yune_group_last_error(const yune_group* g);          /* g may be NULL for a failed yune_group_create      */
+/* the set-up calls above, applied to every rank (the scene is replicated) */
+int yune_group_create_render_program(yune_group* g, const char* kernel, const char* compiler_opts);
+int yune_group_create_postproc_program(yune_group* g, const char* kernel, const char* compiler_opts);
+int yune_group_setup_vertex_buffer(yune_group* g, const yune_triangle* tris, int n_triangles);
+int yune_group_setup_mat_buffer(yune_group* g, const yune_material* mats, int n_materials);
+int yune_group_setup_bvh_buffer(yune_group* g, const yune_bvh_node* nodes, int n_nodes);
+int yune_group_setup_camera_buffer(yune_group* g, const yune_cam* cam);
+int yune_group_setup_image_buffers(yune_group* g, int width, int height);
+int yune_group_set_light_sources(yune_group* g, const yune_quad_light* lights, int n_lights);
+int yune_group_set_option(yune_group* g, const char* key, double value);
+/* Every rank renders its shard of [spp_begin, spp_begin + spp_count) concurrently (yune_render semantics per rank). */
+int yune_group_render(yune_group* g, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset);
+/* SUM-reduce the ranks' accumulation buffers into the root's (in place); the other ranks' buffers are unchanged. */
+int yune_group_reduce(yune_group* g, int root);
+int yune_group_get_stats(yune_group* g, yune_group_stats* out);
 
 #ifdef __cplusplus
 }

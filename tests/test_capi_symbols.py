@@ -64,3 +64,28 @@ def test_argument_errors_do_not_crash():
     assert lib.yune_setup(0, None) == -1
     assert lib.yune_render(None, 0, 1, 1, 0, 1) == -1
     assert lib.yune_get_stats(None, None) == -1
+
+
+def test_group_api_without_a_device_and_shard_rule():
+    """yune_group_* (SURVEY.md 8b): argument errors and the no-device answer do not need a GPU; the split rule is the one the
+    torch.distributed path uses (yune_b200/dist.py) -- contiguous, balanced, disjoint, covering."""
+    import torch
+    from yune_b200.dist import shard_samples as py_shard
+    import yune_b200 as yb
+    lib = _native.load()
+    assert lib.yune_group_create(2, None, None) == -1
+    assert lib.yune_group_size(None) == 0 and lib.yune_group_ctx(None, 0) is None
+    assert lib.yune_group_render(None, 0, 1, 1, 0, 1) == -1 and lib.yune_group_reduce(None, 0) == -1
+    if not torch.cuda.is_available():
+        g = C.c_void_p()
+        assert lib.yune_group_create(2, None, C.byref(g)) == -5 and b"no CPU fallback" in lib.yune_group_last_error(None)
+        with pytest.raises(yb.YuneError):
+            yb.CUDAGroup(2)
+    for total, begin in ((16384, 0), (1024, 512), (7, 3), (0, 0), (5, 0)):
+        for n in (1, 2, 3, 4, 8):
+            got = [yb.shard_samples(begin, total, r, n) for r in range(n)]
+            want = [py_shard(total, r, n) for r in range(n)]
+            assert [(b - begin, c) for b, c in got] == want
+            assert sum(c for _, c in got) == total and got[0][0] == begin
+            assert all(got[r][0] + got[r][1] == got[r + 1][0] for r in range(n - 1))
+            assert max(c for _, c in got) - min(c for _, c in got) <= 1

@@ -710,3 +710,74 @@ def test_synthetic_c4_at_full_size_hits_bit_exact(gpu_manager, oracle):
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (_bits(a[2]) == _bits(b[2])).all()
     sa = r.traceRays(od6, tm, any_hit=True); sb = oracle.trace(cfg, od6, tm, 1, sc.vert_data, sc.bvh)
     assert (((sb[0] >= 0) | (sb[1] >= 0)) == (sa[0] >= 0)).all()
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("n_dev", [2, 4])
+def test_group_reduced_image_equals_single_gpu(oracle, n_dev):
+    """The multi-GPU rule on hardware, through the C ABI (yune_group_*): n devices render disjoint sample ranges, ncclReduce(sum)
+    to the root -- the reduced buffer must equal what ONE device renders for the whole range (fp32 summation order only), and
+    every pixel must have been counted exactly spp times.  Needs >= n_dev GPUs (gpurun --gpus N); skipped on a single-GPU box."""
+    if _device_count() < n_dev:
+        pytest.skip("needs %d GPUs" % n_dev)
+    sc = golden_scene_object("teapot", transmissive_teapot=True)
+    W, H, spp, seed = 160, 96, 37, 4321                       # 37 samples: uneven shards
+    one = yb.CUDAGroup(1).setup(sc, W, H, compiler_opts="-DMIS")
+    try:
+        one.render(0, spp, seed=seed); one.reduce(0)
+        ref = one.readSum(0)
+    finally:
+        one.close()
+    g = yb.CUDAGroup(n_dev).setup(sc, W, H, compiler_opts="-DMIS")
+    try:
+        st = g.render(0, spp, seed=seed)
+        assert st.n_devices == n_dev and st.samples == W * H * spp
+        parts = [g.readSum(r) for r in range(n_dev)]
+        for r in range(n_dev):
+            assert (parts[r][..., 3] == yb.shard_samples(0, spp, r, n_dev)[1]).all()
+        st = g.reduce(0)
+        assert st.reduce_ms > 0
+        total = g.readSum(0)
+        assert (total[..., 3] == spp).all()
+        np.testing.assert_allclose(total, np.sum(parts, axis=0, dtype=np.float32), rtol=1e-6, atol=1e-6)      # NCCL summed exactly these buffers
+        np.testing.assert_allclose(total, ref, rtol=2e-5, atol=1e-5)                                         # == the single-device image
+        for r in range(1, n_dev):
+            np.testing.assert_array_equal(g.readSum(r), parts[r])                                            # non-root buffers untouched
+        # a second, accumulating pass continues the sample range on every rank
+        g.render(spp, 3, seed=seed, reset=False)
+        assert sum(float(g.readSum(r)[0, 0, 3]) for r in range(1, n_dev)) + float(g.readSum(0)[0, 0, 3]) == spp + sum(yb.shard_samples(0, spp, r, n_dev)[1] for r in range(1, n_dev)) + 3
+    finally:
+        g.close()
+
+
+def test_group_of_one_and_headless_cli_multi_gpu(tmp_path):
+    """A group of one needs no NCCL and equals the plain context; `yune_headless --gpus N` (C++ host over yune_group_*) writes
+    the same picture as --gpus 1."""
+    import subprocess
+    from tests.helpers import write_obj, ROOT
+    sc = golden_scene_object("cornellbox")
+    g = yb.CUDAGroup(1).setup(sc, 64, 48)
+    try:
+        g.render(0, 8, seed=5); g.reduce(0)
+        img = g.readSum(0)
+        assert (img[..., 3] == 8).all() and g.stats().reduce_ms == 0.0
+    finally:
+        g.close()
+    if _device_count() < 2:
+        return
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    obj = str(tmp_path / "cb.obj"); write_obj(obj, tris, mats)
+    exe = os.path.join(ROOT, "yune_b200", "yune_headless")
+    outs = []
+    for n in (1, 2):
+        out = str(tmp_path / ("cb%d.pfm" % n))
+        p = subprocess.run([exe, "--obj", obj, "--width", "64", "--height", "48", "--spp", "9", "--seed", "5", "--gpus", str(n), "--out", out], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        with open(out, "rb") as f:
+            f.readline(); f.readline(); f.readline()
+            outs.append(np.frombuffer(f.read(), "<f4").reshape(48, 64, 3))
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-4, atol=1e-5)

@@ -20,6 +20,11 @@ class Stats(C.Structure):
                 ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64)]
 
 
+class GroupStats(C.Structure):
+    _fields_ = [("n_devices", C.c_int), ("render_ms_max", C.c_double), ("render_ms_min", C.c_double), ("reduce_ms", C.c_double),
+                ("samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/*.h declares is listed here (tests check the export table against it)
 CUDA_API = {
     "yune_setup": (C.c_int, [C.c_int, c_void_pp]),
@@ -49,6 +54,24 @@ CUDA_API = {
     "yune_debug_capture_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "yune_debug_read_captured": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "yune_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "yune_shard_samples": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "yune_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), c_void_pp]),
+    "yune_group_destroy": (None, [C.c_void_p]),
+    "yune_group_size": (C.c_int, [C.c_void_p]),
+    "yune_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "yune_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "yune_group_create_render_program": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "yune_group_create_postproc_program": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "yune_group_setup_vertex_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_group_setup_mat_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_group_setup_bvh_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_group_setup_camera_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "yune_group_setup_image_buffers": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "yune_group_set_light_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_group_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "yune_group_render": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]),
+    "yune_group_reduce": (C.c_int, [C.c_void_p, C.c_int]),
+    "yune_group_get_stats": (C.c_int, [C.c_void_p, C.POINTER(GroupStats)]),
 }
 HOST_API = {
     "yune_scene_create": (C.c_void_p, []),

@@ -254,6 +254,87 @@ class CUDAManager:
         return v.value
 
 
+class CUDAGroup:
+    """Several devices of one node behind one object (include/yune_cuda.h: yune_group_*): the scene is replicated, a render is
+    sharded by SAMPLE INDEX, one NCCL sum-reduce merges the accumulation buffers on the root."""
+
+    def __init__(self, n_devices=0, devices=None):
+        self._lib = _native.load()
+        self._g = C.c_void_p()
+        arr = None
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices); n_devices = len(devices)
+        rc = self._lib.yune_group_create(int(n_devices), arr, C.byref(self._g))
+        if rc != 0:
+            raise YuneError(self._lib.yune_group_last_error(None).decode())
+        self.size = self._lib.yune_group_size(self._g)
+
+    def close(self):
+        if self._g:
+            self._lib.yune_group_destroy(self._g); self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise YuneError(self._lib.yune_group_last_error(self._g).decode())
+
+    def manager(self, rank):
+        """A CUDAManager view of one rank's context (owned by the group: do not close it)."""
+        m = CUDAManager.__new__(CUDAManager)
+        m._lib = self._lib; m._ctx = C.c_void_p(self._lib.yune_group_ctx(self._g, int(rank)))
+        m.last_message = ""; m.rk_file = m.rk_compiler_opts = m.ppk_file = ""
+        m.close = lambda: None
+        return m
+
+    def setup(self, scene, width, height, kernel="udpt.cl", compiler_opts="", cam=None):
+        L, g = self._lib, self._g
+        self.width, self.height = int(width), int(height)
+        v, mt, b = np.ascontiguousarray(scene.vert_data), np.ascontiguousarray(scene.mat_data), np.ascontiguousarray(scene.bvh)
+        cam = np.ascontiguousarray(cam if cam is not None else scene.main_camera)
+        self.check(L.yune_group_create_render_program(g, kernel.encode(), compiler_opts.encode()))
+        self.check(L.yune_group_create_postproc_program(g, b"tonemap.cl", b""))
+        self.check(L.yune_group_setup_vertex_buffer(g, _ptr(v), int(v.size)))
+        self.check(L.yune_group_setup_mat_buffer(g, _ptr(mt), int(mt.size)))
+        self.check(L.yune_group_setup_bvh_buffer(g, _ptr(b), int(b.size)))
+        self.check(L.yune_group_setup_image_buffers(g, self.width, self.height))
+        self.check(L.yune_group_setup_camera_buffer(g, _ptr(cam)))
+        return self
+
+    def setOption(self, key, value):
+        self.check(self._lib.yune_group_set_option(self._g, key.encode(), float(value)))
+
+    def render(self, spp_begin, spp_count, seed=12345, gi_check=True, reset=True):
+        self.check(self._lib.yune_group_render(self._g, int(spp_begin), int(spp_count), int(bool(gi_check)), int(seed) & 0xffffffff, int(bool(reset))))
+        return self.stats()
+
+    def reduce(self, root=0):
+        self.check(self._lib.yune_group_reduce(self._g, int(root)))
+        return self.stats()
+
+    def stats(self):
+        st = _native.GroupStats()
+        self._lib.yune_group_get_stats(self._g, C.byref(st))
+        return st
+
+    def readSum(self, rank=0):
+        img = np.zeros((self.height, self.width, 4), np.float32)
+        m = self.manager(rank)
+        m.check(self._lib.yune_read_sum(m._ctx, _ptr(img)))
+        return img
+
+
+def shard_samples(spp_begin, spp_count, rank, n_ranks):
+    """yune_shard_samples: (begin, count) of `rank`'s contiguous, balanced slice."""
+    b, c = C.c_int(), C.c_int()
+    _native.load().yune_shard_samples(int(spp_begin), int(spp_count), int(rank), int(n_ranks), C.byref(b), C.byref(c))
+    return b.value, c.value
+
+
 class RendererCore:
     """Headless counterpart of yune::RendererCore: uploads the scene (setup) and renders frames (enqueueKernels)."""
 

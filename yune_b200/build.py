@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "yune_b200", "csrc")
 LIB = os.path.join(ROOT, "yune_b200", "libyune_b200.so")
 
-CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu"]
+CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu", "cuda/group.cu"]
 HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/RendererCore.cpp", "host/ImageIO.cpp", "host/host_capi.cpp"]
 APP = os.path.join(ROOT, "yune_b200", "yune_headless")
 
@@ -46,7 +46,7 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build yune_b200/libyune_b200.so (and there is no CPU fallback)")
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
     cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CSRC, "cuda"),
-                                 "-I", os.path.join(CSRC, "host"), "-o", LIB] + srcs
+                                 "-I", os.path.join(CSRC, "host"), "-o", LIB] + srcs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -557,9 +557,8 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, 2) k_shade_bdpt(RenderArgs A
     }
 }
 
-cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, cudaStream_t st)
-{
-    static int occ[2] = { 0, 0 };
+cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, int* occ, cudaStream_t st)
+{      // occ[2]: resident blocks per SM of the two instantiations, cached by the caller per context (0 = not asked yet)
     const int v = a.mis ? 1 : 0;
     if (occ[v] == 0) {
         cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_bdpt<true>, YUNE_SHADE_BLOCK, 0)

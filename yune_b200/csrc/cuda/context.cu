@@ -84,6 +84,7 @@ struct yune_ctx {
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
 
+    int occ_dense[2] = {0, 0}, occ_bdpt[2] = {0, 0};                           // shade-kernel occupancy caches
     int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache
 
     yune_stats stats{};
@@ -415,7 +416,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
-    if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (experimental: own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
+    if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     *p = v;
     return YUNE_OK;
@@ -433,6 +434,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
 {
     if (!c) return YUNE_ERR_INVALID;
     if (spp_begin < 0 || spp_count < 0) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: negative sample range");
+    if ((long long)spp_begin + (long long)spp_count > 2147483647ll) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: spp_begin + spp_count exceeds INT_MAX");
     if (c->integrator != INTEGRATOR_UDPT && c->integrator != INTEGRATOR_BDPT) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: no render program selected");
     if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: image buffers not set up");
     if (!c->have_cam) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: camera buffer not set up");
@@ -482,8 +484,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
             const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
-            if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->sm_count, c->stream));
-            else Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->stream));
+            if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->sm_count, c->occ_bdpt, c->stream));
+            else Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->occ_dense, c->stream));
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));

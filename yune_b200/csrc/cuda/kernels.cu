@@ -929,9 +929,8 @@ cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStre
     k_iter_end<<<1, 1, 0, st>>>(ctr, tot, parity);
     return cudaGetLastError();
 }
-cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st)
-{
-    static int occ[2] = { 0, 0 };                   // resident blocks per SM of the two instantiations (asked once)
+cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, int* occ, cudaStream_t st)
+{      // occ[2]: resident blocks per SM of the two instantiations, cached by the caller per context (0 = not asked yet)
     const int v = a.mis ? 1 : 0;
     if (occ[v] == 0) {
         cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_dense<true>, YUNE_SHADE_BLOCK, 0)

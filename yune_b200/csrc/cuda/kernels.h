@@ -35,8 +35,8 @@ cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_by
 cudaError_t trace_prepare(const DevScene& sc, bool count, int block, size_t smem_bytes, int* blocks_per_sm);
 int         trace_variant_id(const DevScene& sc, bool count);
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
-cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, cudaStream_t st);   // persistent, in-block sorted (default)
-cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, cudaStream_t st);
+cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, int* occ_cache, cudaStream_t st);   // persistent, in-block sorted (default)
+cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, int* occ_cache, cudaStream_t st);
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);

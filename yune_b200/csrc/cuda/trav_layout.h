@@ -61,9 +61,8 @@ struct TravLayoutHost {
 //            Same hit records, roughly half the box tests and a third of the triangle tests.
 //
 //        2 = accel 1's tree collapsed into nodes of up to FOUR children (`quads`; half the steps per ray at the same number of
-//            box tests).  Host-verified groundwork for the next trace kernel: the layout and the walk in
-//            trace_core.h are pinned against the oracle by tests/test_traversal_hostcheck.py.  The device kernel variant that
-//            calls the same step (k_trace<., 5>, option "accel" = 2) compiles but has not been run on a GPU yet.
+//            box tests).  Layout and walk are pinned against the oracle on the host (tests/test_traversal_hostcheck.py) and on the
+//            B200 (tests/test_gpu_parity.py); kernel variant k_trace<., 5 / 7>.  Measured slower than accel 1.
 //
 // n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
 //        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.

@@ -17,7 +17,7 @@ struct DevScene {
     const unsigned char* tri_class; // 1 byte per original triangle: 1 = specular material
     const float4* leaf_boxes;// accel 1: 2 x float4 per REFERENCE leaf (its uploaded box), indexed by triangle record t2.w
     int   accel;             // 0 = walk the reference tree, 1 = walk our own tree + exact leaf-box filter (trav_layout.h),
-                             // 2 = experimental: as 1 over 4-wide records (`pairs` then holds 7 x float4 per record, n_inner counts them)
+                             // 2 = as 1 over 4-wide records (`pairs` then holds 7 x float4 per record, n_inner counts them)
     int   n_inner, n_tris, n_mats, root_ref;
     float root_lo[3], root_hi[3];
     int   n_smem_pairs;      // pair records [0, n_smem_pairs) are staged in shared memory by the trace kernel

@@ -139,6 +139,11 @@ typedef struct yune_stats {
     uint64_t specular_visits;  /* slot visits shaded as a mirror/glass surface hit                         */
     uint64_t regenerations;    /* slot visits that started a fresh sample                                  */
     uint64_t slot_visits;      /* pool slots x shade launches (every launch classifies every slot)        */
+    /* steady state = host-sync windows in which the pool was full throughout (past the first 8 iterations, samples still left
+     * to hand out afterwards): rays traced in them and the TIMED launches that fell into them -- like divided by like      */
+    uint32_t steady_iterations, steady_timed_iterations;
+    uint64_t steady_extend_rays, steady_shadow_rays;
+    double   steady_trace_ms, steady_shade_ms;
 } yune_stats;
 int yune_get_stats(yune_ctx* ctx, yune_stats* out);
 

@@ -17,7 +17,9 @@ class Stats(C.Structure):
                 ("samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("timed_iterations", C.c_uint32),
-                ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64)]
+                ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64),
+                ("steady_iterations", C.c_uint32), ("steady_timed_iterations", C.c_uint32), ("steady_extend_rays", C.c_uint64),
+                ("steady_shadow_rays", C.c_uint64), ("steady_trace_ms", C.c_double), ("steady_shade_ms", C.c_double)]
 
 
 class GroupStats(C.Structure):

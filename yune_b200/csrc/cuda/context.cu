@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace yune;
@@ -476,7 +477,14 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     int it = 0;
     bool done = spp_count == 0;
+    // Steady state = the windows between two host syncs in which the pool was full throughout: past the first iterations (the
+    // path mix has settled) and with samples still left to hand out after the window (every finished slot was regenerated).
+    // Their rays and timed launches are reported separately so that a roofline can divide like by like.
+    std::vector<int> timed_it; timed_it.reserve(kMaxTimed);
+    std::vector<std::pair<int, int>> steady_windows;
+    unsigned long long prev_ext = 0, prev_sh = 0;
     while (!done) {
+        const int window_begin = it;
         for (int b = 0; b < c->opt_sync_every && it < c->opt_max_iterations; b++, it++) {
             const int p = it & 1;
             a.parity = p;
@@ -490,13 +498,19 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));
             Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, c->opt_count_work != 0, c->stream));
-            if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 2], c->stream)); n_timed++; }
+            if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 2], c->stream)); n_timed++; timed_it.push_back(it); }
             Y_CUDA(c, launch_iter_end(c->d_ctr, c->d_tot, p, c->stream));
             st.kernel_launches += 3; st.trace_launches += 1;
         }
         Y_CUDA(c, cudaMemcpyAsync(c->h_tot, c->d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
         Y_CUDA(c, cudaStreamSynchronize(c->stream));
         a.tail = c->h_tot->next_sample >= c->h_tot->n_samples ? 1 : 0;      // the pool only drains from here on
+        if (!a.tail && window_begin >= 8) {
+            steady_windows.push_back({window_begin, it});
+            st.steady_iterations += (uint32_t)(it - window_begin);
+            st.steady_extend_rays += c->h_tot->extend_rays - prev_ext; st.steady_shadow_rays += c->h_tot->shadow_rays - prev_sh;
+        }
+        prev_ext = c->h_tot->extend_rays; prev_sh = c->h_tot->shadow_rays;
         if (c->h_tot->live_last == 0) done = true;
         else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
     }
@@ -506,6 +520,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
         cudaEventElapsedTime(&m1, c->ev_pool[3 * i], c->ev_pool[3 * i + 1]);
         cudaEventElapsedTime(&m2, c->ev_pool[3 * i + 1], c->ev_pool[3 * i + 2]);
         shade_ms += m1; trace_ms += m2;
+        for (const auto& w : steady_windows)
+            if (timed_it[i] >= w.first && timed_it[i] < w.second) { st.steady_shade_ms += m1; st.steady_trace_ms += m2; st.steady_timed_iterations++; break; }
     }
     st.timed_iterations = (uint32_t)n_timed;
     Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));

@@ -368,8 +368,10 @@ def run_ours(args, cfg):
     bytes_per_launch = ext_per_launch * work["extend"]["bytes"] + sh_per_launch * work["shadow"]["bytes"]
     achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
     resident = cfg["scene"] != "c4"
+    traffic = prof.get("dram_bytes_per_launch") if prof.get("pool_slots", pool_in_use) == pool_in_use else None      # same pool size = same kind of launch
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "bytes_per_launch": bytes_per_launch,
+                "traffic": traffic,
+                "hbm_frac_measured": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic and avg_launch_ms > 0 else None, "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "bytes_per_launch": bytes_per_launch,
                 "launches": which, "rays_per_launch": {"extend": ext_per_launch, "shadow": sh_per_launch}, "work_model": work,
                 "traffic_source": prof.get("source"),
                 "trace_share_of_step": agg["trace_ms"] / max(agg["trace_ms"] + agg["shade_ms"], 1e-9),

@@ -73,7 +73,7 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   idle), "phase_min" (run a triangle step once this many lanes hold postponed triangles), "inner_min" / "inner_chain"
  *   (chain up to inner_chain further node steps without a new vote while inner_min lanes can take one),
  *   "shade_blocks_per_sm" (persistent shade grid; 0 = what the occupancy query returns),
- *   "isect" (0 = reference Moller-Trumbore), "max_iterations", "sync_every", "time_stages", "count_work".
+ *   "isect" (0 = reference Moller-Trumbore), "deterministic" (0/1, below), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);
 int yune_get_option(yune_ctx* ctx, const char* key, double* value);
@@ -96,6 +96,15 @@ int yune_read_sum(yune_ctx* ctx, float* rgba);
 int yune_read_ldr(yune_ctx* ctx, float* rgba);
 /* Load a (e.g. all-reduced) sum buffer back from the host. */
 int yune_write_sum(yune_ctx* ctx, const float* rgba);
+
+/* Option "deterministic" = 1: samples are accumulated in 64-bit FIXED POINT (unit 2^-24, 4 x int64 per pixel: r, g, b, count)
+ * instead of with fp32 atomics.  Integer addition is associative, so the accumulated image is bit-for-bit the same from run to
+ * run, for any pool size, any split of the sample range into calls, and any number of GPUs (yune_group_reduce then reduces
+ * the integer buffers).  The float sum buffer (yune_read_sum, yune_sum_device_ptr, tonemap input) is derived from it at the
+ * end of every yune_render.  Off (default) = the reference-like float accumulation, order-dependent in the last bits. */
+int yune_read_sum_fixed(yune_ctx* ctx, int64_t* rgba);                          /* W*H*4 int64; needs "deterministic" */
+int yune_sum_fixed_device_ptr(yune_ctx* ctx, void** dptr, size_t* n_bytes);     /* for an external (NCCL) int64 sum-reduce */
+int yune_sum_refresh(yune_ctx* ctx);       /* re-derive the float sum buffer after the fixed-point one was reduced externally */
 
 /* Device pointer of the fp32 RGBA sum buffer (width*height*4 floats) so a collective library can reduce it
  * in place across GPUs; and the CUDA stream the context launches on. */

@@ -781,3 +781,65 @@ def test_group_of_one_and_headless_cli_multi_gpu(tmp_path):
             f.readline(); f.readline(); f.readline()
             outs.append(np.frombuffer(f.read(), "<f4").reshape(48, 64, 3))
     np.testing.assert_allclose(outs[0], outs[1], rtol=1e-4, atol=1e-5)
+
+
+def test_deterministic_accumulation_is_bit_exact(gpu_manager):
+    """Option "deterministic": fixed-point (2^-24) integer accumulation.  Same bits from run to run, for any pool size, and for
+    any split of the sample range into calls: [0,4) then [4,8) on top == [0,8), and the integer buffers of two separate shards
+    ADD UP exactly to the unsharded one (the multi-GPU rule; test_group_reduced_image... does it with real devices).  Against
+    the default float accumulation the image agrees to summation-order tolerance."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 96, 64, opts="-DMIS", transmissive_teapot=True)
+    r.seed = 31
+    m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1)); float_mode = r.readSum()
+    old_pool = m.getOption("pool_slots")
+    try:
+        m.setOption("deterministic", 1)
+        m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1)); full, full_fix = r.readSum(), r.readSumFixed()
+        assert (full_fix[..., 3] == 8).all() and (full[..., 3] == 8).all()
+        np.testing.assert_allclose(full, float_mode, rtol=2e-5, atol=1e-5)
+        np.testing.assert_array_equal(full[..., :3], (full_fix[..., :3].astype(np.float32) * np.float32(2.0 ** -24)))     # the float view is derived
+        for rep in range(2):                                                     # run to run
+            m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1))
+            np.testing.assert_array_equal(r.readSumFixed(), full_fix); np.testing.assert_array_equal(r.readSum(), full)
+        m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); a_fix = r.readSumFixed()
+        m.check(r._lib.yune_render(r._ctx, 4, 4, 1, r.seed, 0))                  # accumulate the second half on top
+        np.testing.assert_array_equal(r.readSumFixed(), full_fix); np.testing.assert_array_equal(r.readSum(), full)
+        m.check(r._lib.yune_render(r._ctx, 4, 4, 1, r.seed, 1)); b_fix = r.readSumFixed()
+        np.testing.assert_array_equal(a_fix + b_fix, full_fix)                   # shards over sample index sum exactly
+        for pool in (2048, 5000, 1 << 20):                                       # scheduling
+            m.setOption("pool_slots", pool)
+            m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1))
+            np.testing.assert_array_equal(r.readSumFixed(), full_fix)
+        # tonemap reads the derived buffer
+        r.postProcess()
+        assert np.isfinite(r.readLDR()).all()
+        # switching the mode off keeps the image; switching it on again rebuilds the integers from it
+        m.setOption("deterministic", 0)
+        np.testing.assert_array_equal(r.readSum(), full)
+        with pytest.raises(yb.YuneError):
+            r.readSumFixed()
+    finally:
+        m.setOption("deterministic", 0); m.setOption("pool_slots", old_pool)
+
+
+@pytest.mark.parametrize("n_dev", [2, 4])
+def test_group_deterministic_image_is_identical_for_any_gpu_count(n_dev):
+    """north_star: "runs are reproducible".  With "deterministic" = 1 the group reduces the INTEGER buffers (ncclInt64 sum): the
+    image of n devices equals the image of one device bit for bit."""
+    if _device_count() < n_dev:
+        pytest.skip("needs %d GPUs" % n_dev)
+    sc = golden_scene_object("teapot", transmissive_teapot=True)
+    W, H, spp, seed = 128, 80, 21, 99
+    imgs = []
+    for n in (1, n_dev):
+        g = yb.CUDAGroup(n).setup(sc, W, H, compiler_opts="-DMIS")
+        try:
+            g.setOption("deterministic", 1)
+            g.render(0, spp, seed=seed); g.reduce(0)
+            imgs.append((g.readSum(0), g.readSumFixed(0)))
+        finally:
+            g.close()
+    np.testing.assert_array_equal(imgs[0][1], imgs[1][1])
+    np.testing.assert_array_equal(imgs[0][0], imgs[1][0])
+    assert (imgs[1][1][..., 3] == spp).all()

@@ -10,16 +10,22 @@ if os.environ.get("YUNE_AB_CHILD"):
     sys.path.insert(0, ROOT)
     import numpy as np
     import yune_b200 as yb
-    from bench import load_scene
+    from bench import build_scene, CONFIGS
     spp, size = int(sys.argv[1]), int(sys.argv[2])
-    tris, mats, nodes = load_scene()
+    opts = dict(kv.split("=") for kv in sys.argv[3:])
+    cfg = CONFIGS[opts.pop("config", "c2")]
+    tris, mats, nodes, lights = build_scene(cfg)
     m = yb.CUDAManager().setup(0)
-    for kv in sys.argv[3:]:
-        k, v = kv.split("="); m.setOption(k, float(v))
-    r = yb.RendererCore(m, size, size)
-    assert m.createRenderProgram("udpt.cl", compiler_opts="-DMIS")
+    for k, v in opts.items():
+        m.setOption(k, float(v))
+    W, H = (size, size) if cfg["W"] == cfg["H"] else (size, size * cfg["H"] // cfg["W"])
+    r = yb.RendererCore(m, W, H)
+    assert m.createRenderProgram(cfg["kernel"], compiler_opts=cfg["opts"])
     sc = yb.Scene(); sc.vert_data, sc.mat_data, sc.bvh = tris, mats, nodes
     assert r.setup(sc), m.last_message
+    if lights is not None:
+        assert m.setLightSources(lights)
+    m.setOption("oren_nayar", 1 if cfg.get("oren_nayar") else 0)
     r.enqueueKernels(8)
     m.setOption("time_stages", 4)
     best = None

@@ -49,6 +49,9 @@ CUDA_API = {
     "yune_read_ldr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yune_write_sum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yune_sum_device_ptr": (C.c_int, [C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
+    "yune_read_sum_fixed": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "yune_sum_fixed_device_ptr": (C.c_int, [C.c_void_p, c_void_pp, C.POINTER(C.c_size_t)]),
+    "yune_sum_refresh": (C.c_int, [C.c_void_p]),
     "yune_stream": (C.c_int, [C.c_void_p, c_void_pp]),
     "yune_synchronize": (C.c_int, [C.c_void_p]),
     "yune_trace_primary": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

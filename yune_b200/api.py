@@ -328,6 +328,16 @@ class CUDAGroup:
         return img
 
 
+def _group_read_sum_fixed(self, rank=0):
+    img = np.zeros((self.height, self.width, 4), np.int64)
+    m = self.manager(rank)
+    m.check(self._lib.yune_read_sum_fixed(m._ctx, _ptr(img)))
+    return img
+
+
+CUDAGroup.readSumFixed = _group_read_sum_fixed
+
+
 def shard_samples(spp_begin, spp_count, rank, n_ranks):
     """yune_shard_samples: (begin, count) of `rank`'s contiguous, balanced slice."""
     b, c = C.c_int(), C.c_int()
@@ -404,6 +414,12 @@ class RendererCore:
 
     def readSum(self):
         return self._read(self._lib.yune_read_sum)
+
+    def readSumFixed(self):
+        """Option "deterministic": the fixed-point accumulation buffer (H, W, 4) int64, unit 2^-24 (r, g, b) and sample count."""
+        img = np.zeros((self.height, self.width, 4), np.int64)
+        self.cl_manager.check(self._lib.yune_read_sum_fixed(self._ctx, _ptr(img)))
+        return img
 
     def readLDR(self):
         return self._read(self._lib.yune_read_ldr)

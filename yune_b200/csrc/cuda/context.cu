@@ -65,6 +65,7 @@ struct yune_ctx {
 
     int W = 0, H = 0;
     float4 *d_sum = nullptr, *d_hdr = nullptr, *d_ldr = nullptr;
+    long long* d_fix = nullptr;                 // option "deterministic": fixed-point accumulation buffer (4 x int64 per pixel); d_sum is derived from it
 
     PathPool pool{}; int pool_alloc = 0; int pool_integrator = 0;
     BdptPool bdpt{};
@@ -83,7 +84,7 @@ struct yune_ctx {
     int opt_pool_slots = 0, opt_smem_nodes = -1, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 12, opt_phase_min = 24, opt_inner_min = 16, opt_inner_chain = 8;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
-    int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0;
+    int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0, opt_deterministic = 0;
 
     int occ_dense[2] = {0, 0}, occ_bdpt[2] = {0, 0};                           // shade-kernel occupancy caches
     int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache
@@ -278,7 +279,7 @@ void yune_destroy(yune_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_pool(c);
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
-    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_ctr); dfree(c->d_tot);
+    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_fix); dfree(c->d_ctr); dfree(c->d_tot);
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
     dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
     if (c->h_tot) cudaFreeHost(c->h_tot);
@@ -367,10 +368,11 @@ int yune_setup_image_buffers(yune_ctx* c, int W, int H)
     const size_t n = (size_t)W * H;
     if (c->d_sum && c->W == W && c->H == H) {          // same size: keep the allocation (and any pointer handed out), just clear
         Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n * 16, c->stream));
+        if (c->d_fix) Y_CUDA(c, cudaMemsetAsync(c->d_fix, 0, n * 32, c->stream));
         Y_CUDA(c, cudaStreamSynchronize(c->stream));
         return YUNE_OK;
     }
-    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr);
+    dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_fix);
     Y_CUDA(c, cudaMalloc(&c->d_sum, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_hdr, n * 16)); Y_CUDA(c, cudaMalloc(&c->d_ldr, n * 16));
     Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n * 16, c->stream));
     Y_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, n * 16, c->stream));
@@ -399,7 +401,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -419,6 +421,16 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
+    if (p == &c->opt_deterministic && (v != 0) != (*p != 0) && c->d_sum) {
+        // switching modes carries the image over: the fixed-point buffer is (re)built from the float sums, or dropped
+        Y_CUDA(c, cudaSetDevice(c->device));
+        const size_t n = (size_t)c->W * c->H;
+        if (v != 0) {
+            if (!c->d_fix) Y_CUDA(c, cudaMalloc(&c->d_fix, n * 32));
+            Y_CUDA(c, launch_sum_to_fix(c->d_sum, c->d_fix, n, c->stream));
+            Y_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
     *p = v;
     return YUNE_OK;
 }
@@ -447,7 +459,15 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     if ((rc = trace_config(c, tl, c->opt_count_work != 0)) != YUNE_OK) return rc;
 
     const size_t n_pix = (size_t)c->W * c->H;
-    if (reset) Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n_pix * 16, c->stream));
+    const bool det = c->opt_deterministic != 0;
+    if (det && !c->d_fix) {
+        Y_CUDA(c, cudaMalloc(&c->d_fix, n_pix * 32));
+        Y_CUDA(c, launch_sum_to_fix(c->d_sum, c->d_fix, n_pix, c->stream));
+    }
+    if (reset) {
+        Y_CUDA(c, cudaMemsetAsync(c->d_sum, 0, n_pix * 16, c->stream));
+        if (det) Y_CUDA(c, cudaMemsetAsync(c->d_fix, 0, n_pix * 32, c->stream));
+    }
     std::memset(c->h_tot, 0, sizeof(Totals));
     c->h_tot->n_samples = (unsigned long long)n_pix * (unsigned long long)spp_count;
     c->h_tot->live_last = 1;
@@ -457,7 +477,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
     RenderArgs a = make_args(c);
-    a.tail = 0; a.chunk_live = c->d_chunk_live;
+    a.tail = 0; a.chunk_live = c->d_chunk_live; a.fix = det ? c->d_fix : nullptr;
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
     c->bdpt.bounces = c->opt_bdpt_bounces;
     TraceArgs t{};
@@ -524,6 +544,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
             if (timed_it[i] >= w.first && timed_it[i] < w.second) { st.steady_shade_ms += m1; st.steady_trace_ms += m2; st.steady_timed_iterations++; break; }
     }
     st.timed_iterations = (uint32_t)n_timed;
+    if (det) Y_CUDA(c, launch_fix_to_sum(c->d_fix, c->d_sum, n_pix, c->stream));      // inside the timed region: part of the mode's cost
     Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     Y_CUDA(c, cudaEventSynchronize(c->ev1));
     float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -577,7 +598,33 @@ int yune_write_sum(yune_ctx* c, const float* rgba)
     if (!c->d_sum) Y_FAIL(c, YUNE_ERR_STATE, "yune_write_sum: image buffers not set up");
     Y_CUDA(c, cudaSetDevice(c->device));
     Y_CUDA(c, cudaMemcpyAsync(c->d_sum, rgba, (size_t)c->W * c->H * 16, cudaMemcpyHostToDevice, c->stream));
+    if (c->opt_deterministic && c->d_fix) Y_CUDA(c, launch_sum_to_fix(c->d_sum, c->d_fix, (size_t)c->W * c->H, c->stream));
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YUNE_OK;
+}
+int yune_read_sum_fixed(yune_ctx* c, int64_t* rgba)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!rgba) Y_FAIL(c, YUNE_ERR_INVALID, "yune_read_sum_fixed: destination is NULL");
+    if (!c->opt_deterministic || !c->d_fix) Y_FAIL(c, YUNE_ERR_STATE, "yune_read_sum_fixed: option \"deterministic\" is off (no fixed-point buffer)");
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, cudaMemcpyAsync(rgba, c->d_fix, (size_t)c->W * c->H * 32, cudaMemcpyDeviceToHost, c->stream));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YUNE_OK;
+}
+int yune_sum_fixed_device_ptr(yune_ctx* c, void** dptr, size_t* n_bytes)
+{
+    if (!c || !dptr) return YUNE_ERR_INVALID;
+    if (!c->opt_deterministic || !c->d_fix) Y_FAIL(c, YUNE_ERR_STATE, "option \"deterministic\" is off (no fixed-point buffer)");
+    *dptr = c->d_fix; if (n_bytes) *n_bytes = (size_t)c->W * c->H * 32;
+    return YUNE_OK;
+}
+int yune_sum_refresh(yune_ctx* c)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->opt_deterministic || !c->d_fix) return YUNE_OK;           // nothing to derive: the float buffer is the accumulator
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, launch_fix_to_sum(c->d_fix, c->d_sum, (size_t)c->W * c->H, c->stream));
     return YUNE_OK;
 }
 int yune_sum_device_ptr(yune_ctx* c, void** dptr, size_t* n_bytes)

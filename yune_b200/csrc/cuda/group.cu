@@ -173,8 +173,10 @@ int yune_group_reduce(yune_group* g, int root)
     g->stats.reduce_ms = 0.0;
     if (n == 1) return YUNE_OK;
     std::vector<void*> buf(n); std::vector<size_t> bytes(n); std::vector<void*> stream(n);
+    double det = 0.0;
+    yune_get_option(g->ctx[root], "deterministic", &det);       // fixed-point accumulation: reduce the integer buffers (exact, order-free)
     for (int r = 0; r < n; r++) {
-        int rc = yune_sum_device_ptr(g->ctx[r], &buf[r], &bytes[r]);
+        int rc = det != 0.0 ? yune_sum_fixed_device_ptr(g->ctx[r], &buf[r], &bytes[r]) : yune_sum_device_ptr(g->ctx[r], &buf[r], &bytes[r]);
         if (rc == YUNE_OK) rc = yune_stream(g->ctx[r], &stream[r]);
         if (rc != YUNE_OK) { g->err = "rank " + std::to_string(r) + ": " + yune_last_error(g->ctx[r]); return rc; }
         if (bytes[r] != bytes[0]) G_FAIL(g, YUNE_ERR_STATE, "yune_group_reduce: image sizes differ between ranks");
@@ -183,9 +185,11 @@ int yune_group_reduce(yune_group* g, int root)
     cudaEventRecord(g->ev[0], (cudaStream_t)stream[root]);
     ncclResult_t res = g_nccl.GroupStart();
     for (int r = 0; r < n && res == ncclSuccess; r++)      // in place on the root; the other ranks' buffers stay as they are
-        res = g_nccl.Reduce(buf[r], buf[root], bytes[r] / sizeof(float), ncclFloat32, ncclSum, root, g->comm[r], (cudaStream_t)stream[r]);
+        res = det != 0.0 ? g_nccl.Reduce(buf[r], buf[root], bytes[r] / sizeof(long long), ncclInt64, ncclSum, root, g->comm[r], (cudaStream_t)stream[r])
+                         : g_nccl.Reduce(buf[r], buf[root], bytes[r] / sizeof(float), ncclFloat32, ncclSum, root, g->comm[r], (cudaStream_t)stream[r]);
     if (res == ncclSuccess) res = g_nccl.GroupEnd(); else g_nccl.GroupEnd();
     if (res != ncclSuccess) G_FAIL(g, YUNE_ERR_CUDA, "ncclReduce: %s", g_nccl.GetErrorString(res));
+    if (det != 0.0 && yune_sum_refresh(g->ctx[root]) != YUNE_OK) { g->err = yune_last_error(g->ctx[root]); return YUNE_ERR_CUDA; }
     cudaSetDevice(g->devices[root]);
     cudaEventRecord(g->ev[1], (cudaStream_t)stream[root]);
     for (int r = 0; r < n; r++) {

@@ -83,10 +83,25 @@ __device__ __forceinline__ void list_push_u16(unsigned short* list, int* count, 
     if (want) list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
+#define YUNE_FIX_SCALE 16777216.0f            /* 2^24 */
+__device__ __forceinline__ long long to_fixed(float x)
+{
+    return __float2ll_rn(fminf(fmaxf(x, -2.7487791e11f), 2.7487791e11f) * YUNE_FIX_SCALE);      // clamp to +-2^38, round to nearest even
+}
+
 // a finished sample goes to the fp32 accumulation buffer (udpt.cl:193-210; sum instead of running mean)
 __device__ __forceinline__ void finish_sample(const RenderArgs& A, unsigned pixel, V3 col)
 {
     if (col.x != col.x || col.y != col.y || col.z != col.z) col = v3(0.988f, 0.0588f, 0.7529f);     // PINK (udpt.cl:193-194)
+    if (A.fix) {
+        // Deterministic accumulation: integer addition is associative, so the sum does not depend on the order in which samples
+        // finish, on the pool size, on how a sample range is split into calls or over GPUs.  One unit = 2^-24 (a sample is
+        // quantised to ~6e-8 absolute, below the fp32 resolution of any pixel mean >= 1); |x| is clamped to 2^38.
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.fix) + 4 * (size_t)pixel;
+        atomicAdd(dst + 0, (unsigned long long)to_fixed(col.x)); atomicAdd(dst + 1, (unsigned long long)to_fixed(col.y));
+        atomicAdd(dst + 2, (unsigned long long)to_fixed(col.z)); atomicAdd(dst + 3, 1ull);
+        return;
+    }
     float* dst = reinterpret_cast<float*>(A.sum + pixel);
     atomicAdd(dst + 0, col.x); atomicAdd(dst + 1, col.y); atomicAdd(dst + 2, col.z); atomicAdd(dst + 3, 1.0f);
 }

@@ -797,6 +797,23 @@ __global__ void k_fill_f4(float4* p, size_t n, float4 v)
     if (i < n) p[i] = v;
 }
 
+// option "deterministic": the float sum buffer is a view of the fixed-point one (rgb * 2^-24, a = count), and back
+__global__ void k_fix_to_sum(const long long* fix, float4* sum, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const longlong2 a = reinterpret_cast<const longlong2*>(fix)[2 * i], b = reinterpret_cast<const longlong2*>(fix)[2 * i + 1];
+    const float inv = 1.0f / YUNE_FIX_SCALE;
+    sum[i] = make_float4(__ll2float_rn(a.x) * inv, __ll2float_rn(a.y) * inv, __ll2float_rn(b.x) * inv, __ll2float_rn(b.y));
+}
+__global__ void k_sum_to_fix(const float4* sum, long long* fix, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = sum[i];
+    fix[4 * i + 0] = to_fixed(v.x); fix[4 * i + 1] = to_fixed(v.y); fix[4 * i + 2] = to_fixed(v.z); fix[4 * i + 3] = __float2ll_rn(v.w);
+}
+
 // tonemap.cl:14-47 on mean = sum / count.  Output keeps the reference's "gamma on all four channels".
 __global__ void k_tonemap(const float4* sum, float4* hdr, float4* ldr, int n)
 {
@@ -960,6 +977,16 @@ cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     k_fill_f4<<<ceil_div((long long)n, 256), 256, 0, st>>>(p, n, v);
+    return cudaGetLastError();
+}
+cudaError_t launch_fix_to_sum(const long long* fix, float4* sum, size_t n, cudaStream_t st)
+{
+    if (n) k_fix_to_sum<<<ceil_div((long long)n, 256), 256, 0, st>>>(fix, sum, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_to_fix(const float4* sum, long long* fix, size_t n, cudaStream_t st)
+{
+    if (n) k_sum_to_fix<<<ceil_div((long long)n, 256), 256, 0, st>>>(sum, fix, n);
     return cudaGetLastError();
 }
 cudaError_t launch_tonemap(const float4* sum, float4* hdr, float4* ldr, int n, cudaStream_t st)

@@ -40,6 +40,8 @@ cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_cou
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);
+cudaError_t launch_fix_to_sum(const long long* fix, float4* sum, size_t n, cudaStream_t st);
+cudaError_t launch_sum_to_fix(const float4* sum, long long* fix, size_t n, cudaStream_t st);
 cudaError_t launch_tonemap(const float4* sum, float4* hdr, float4* ldr, int n, cudaStream_t st);
 cudaError_t launch_hook_primary(const RenderArgs& a, int jitter_mode, uint32_t rand, float4* ray_o, float4* ray_d, cudaStream_t st);
 cudaError_t launch_hook_prepare(const LightSet& L, int n, const float* od6, const float* tmax, int any_hit,

@@ -107,6 +107,7 @@ struct RenderArgs {
     LightSet  lights;
     PathPool  pool;
     float4*   sum;            // W*H fp32 RGBA accumulation buffer (rgb sums, a = sample count)
+    long long* fix;           // option "deterministic": W*H x 4 fixed-point (2^-24) sums instead; `sum` is derived from it after the render
     IterCounters* ctr;        // [2]
     Totals*   tot;
     float     cam[20];        // the 80-byte Cam record

@@ -268,7 +268,9 @@ def run_ours(args, cfg):
     else:
         spp_begin, spp_rank = rank * SPP, SPP                           # every rank renders the full workload on its own range
     warm_spp = min(spp_rank, 64) if SPP > 2048 else spp_rank           # a 16 k-spp step is minutes long: warm up on the same scene at 64 spp
-    sum_t = sum_buffer_as_tensor(r) if world > 1 else None
+    if world > 1:                  # the fixed-point buffer exists after the first render of this size
+        m.check(r._lib.yune_render(r._ctx, spp_begin, 1, 1, SEED, 1))
+    sum_t = sum_buffer_as_tensor(r) if world > 1 else None          # int64 fixed point (option "deterministic", default): exact, order-free reduce
     lib, ctx = r._lib, r._ctx
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -277,7 +279,10 @@ def run_ours(args, cfg):
         st = yb._native.Stats(); lib.yune_get_stats(ctx, C.byref(st))
         extra_ms, reduce_ms = 0.0, 0.0
         if world > 1:                      # the path's single exchange step: SUM-reduce the fp32 accumulation buffers over NVLink
-            ev0.record(); reduce_sum_to_root(sum_t); ev1.record(); torch.cuda.synchronize()
+            ev0.record(); reduce_sum_to_root(sum_t); torch.cuda.synchronize()      # the context's stream does not order itself against torch's
+            if rank == 0:
+                m.check(lib.yune_sum_refresh(ctx)); m.check(lib.yune_synchronize(ctx))      # float view of the reduced integers
+            ev1.record(); torch.cuda.synchronize()
             reduce_ms = ev0.elapsed_time(ev1); extra_ms += reduce_ms
         if rank == 0:
             m.check(lib.yune_tonemap(ctx))

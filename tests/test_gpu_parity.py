@@ -261,13 +261,22 @@ def test_sample_ranges_add_up_and_pool_size_is_invisible(gpu_manager):
     m.check(r._lib.yune_render(r._ctx, 4, 4, 1, r.seed, 0)); ab = r.readSum()      # accumulate on top: a-range then b-range twice
     np.testing.assert_allclose(a + b, full, rtol=2e-5, atol=1e-5)
     np.testing.assert_allclose(b + b, ab, rtol=2e-5, atol=1e-5)
+    # default accumulation is fixed point (option "deterministic"): in the integer domain the shards add up EXACTLY
+    m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1)); full_fix = r.readSumFixed()
+    m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); a_fix = r.readSumFixed()
+    m.check(r._lib.yune_render(r._ctx, 4, 4, 1, r.seed, 1)); b_fix = r.readSumFixed()
+    np.testing.assert_array_equal(a_fix + b_fix, full_fix)
+    m.check(r._lib.yune_render(r._ctx, 4, 4, 1, r.seed, 0))
+    np.testing.assert_array_equal(r.readSumFixed(), b_fix + b_fix)
+    m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1))
+    np.testing.assert_array_equal(r.readSum(), full)                             # and a repeated render is bit-identical
     old = m.getOption("pool_slots")
     try:
         m.setOption("pool_slots", 2048)
         m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1)); small = r.readSum()
     finally:
         m.setOption("pool_slots", old)
-    np.testing.assert_allclose(small, full, rtol=2e-5, atol=1e-5)
+    np.testing.assert_array_equal(small, full)                                   # the pool size is invisible, bit for bit
     assert (full[..., 3] == 8).all()
     # zero samples is a no-op that still succeeds
     m.check(r._lib.yune_render(r._ctx, 0, 0, 1, r.seed, 0))
@@ -728,12 +737,14 @@ def test_group_reduced_image_equals_single_gpu(oracle, n_dev):
     W, H, spp, seed = 160, 96, 37, 4321                       # 37 samples: uneven shards
     one = yb.CUDAGroup(1).setup(sc, W, H, compiler_opts="-DMIS")
     try:
+        one.setOption("deterministic", 0)                      # this test pins the FLOAT reduce; the integer one has its own below
         one.render(0, spp, seed=seed); one.reduce(0)
         ref = one.readSum(0)
     finally:
         one.close()
     g = yb.CUDAGroup(n_dev).setup(sc, W, H, compiler_opts="-DMIS")
     try:
+        g.setOption("deterministic", 0)
         st = g.render(0, spp, seed=seed)
         assert st.n_devices == n_dev and st.samples == W * H * spp
         parts = [g.readSum(r) for r in range(n_dev)]
@@ -791,6 +802,8 @@ def test_deterministic_accumulation_is_bit_exact(gpu_manager):
     m = gpu_manager
     r, sc = _renderer(m, "teapot", 96, 64, opts="-DMIS", transmissive_teapot=True)
     r.seed = 31
+    assert m.getOption("deterministic") == 1                                    # the default
+    m.setOption("deterministic", 0)
     m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1)); float_mode = r.readSum()
     old_pool = m.getOption("pool_slots")
     try:
@@ -820,7 +833,7 @@ def test_deterministic_accumulation_is_bit_exact(gpu_manager):
         with pytest.raises(yb.YuneError):
             r.readSumFixed()
     finally:
-        m.setOption("deterministic", 0); m.setOption("pool_slots", old_pool)
+        m.setOption("deterministic", 1); m.setOption("pool_slots", old_pool)
 
 
 @pytest.mark.parametrize("n_dev", [2, 4])
@@ -835,8 +848,7 @@ def test_group_deterministic_image_is_identical_for_any_gpu_count(n_dev):
     for n in (1, n_dev):
         g = yb.CUDAGroup(n).setup(sc, W, H, compiler_opts="-DMIS")
         try:
-            g.setOption("deterministic", 1)
-            g.render(0, spp, seed=seed); g.reduce(0)
+            g.render(0, spp, seed=seed); g.reduce(0)            # "deterministic" = 1 is the default
             imgs.append((g.readSum(0), g.readSumFixed(0)))
         finally:
             g.close()

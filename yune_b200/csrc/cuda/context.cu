@@ -84,7 +84,7 @@ struct yune_ctx {
     int opt_pool_slots = 0, opt_smem_nodes = -1, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
     int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 12, opt_phase_min = 24, opt_inner_min = 16, opt_inner_chain = 8;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
-    int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0, opt_deterministic = 0;
+    int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0, opt_deterministic = 1;
 
     int occ_dense[2] = {0, 0}, occ_bdpt[2] = {0, 0};                           // shade-kernel occupancy caches
     int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache

@@ -28,13 +28,17 @@ def reduce_sum_to_root(sum_tensor, root=0):
 class _DevicePointer:
     """Expose a raw device pointer (from yune_sum_device_ptr) to torch through __cuda_array_interface__."""
 
-    def __init__(self, ptr, n_floats):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 3, "strides": None}
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
 
 
 def sum_buffer_as_tensor(renderer):
-    """Zero-copy torch view of a RendererCore's device-resident sum buffer (for NCCL)."""
+    """Zero-copy torch view of a RendererCore's device-resident accumulation buffer (for NCCL): the int64 fixed-point buffer when
+    the context accumulates deterministically (default; after the reduce call yune_sum_refresh on the root), else the fp32 sums."""
     import ctypes as C
     p, n = C.c_void_p(), C.c_size_t()
+    if renderer.cl_manager.getOption("deterministic"):
+        renderer.cl_manager.check(renderer._lib.yune_sum_fixed_device_ptr(renderer._ctx, C.byref(p), C.byref(n)))
+        return torch.as_tensor(_DevicePointer(p.value, n.value // 8, "<i8"), device="cuda")
     renderer.cl_manager.check(renderer._lib.yune_sum_device_ptr(renderer._ctx, C.byref(p), C.byref(n)))
     return torch.as_tensor(_DevicePointer(p.value, n.value // 4), device="cuda")

@@ -379,3 +379,11 @@ extern "C" int hc_wide_stats(int n, const float* od6, const float* tmax, int any
     out[0] = visits; out[1] = boxes; out[2] = tests; out[3] = hits;
     return 0;
 }
+
+// which walk a layout ended up with (accel 1 / 2 fall back to 0 when the uploaded boxes do not nest; bvh_size == 0 forces 1)
+extern "C" int hc_layout_accel(const yune_triangle* tris, int ntri, const yune_bvh_node* nodes, int nnodes, int leaf_split, int accel)
+{
+    TravLayoutHost lay; std::string err;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    return lay.accel;
+}

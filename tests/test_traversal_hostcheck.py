@@ -265,3 +265,71 @@ def test_wide_layout_shape(hc):
     assert b[0] == w[0] and b[1] == w[1] == tris.size           # same binary tree underneath, every triangle in a leaf
     assert 0.4 * b[0] < w[3] < 0.55 * b[0] and w[2] <= 0.7 * b[2] and 3 * w[2] + 2 <= 64
     assert w[3] * 112 <= 3900 * 56
+
+
+def _soup_with_duplicates(seed, n):
+    """A soup in which every triangle exists twice (indices i and i + n): every hit is an exact tie in t, so the hit index
+    says which copy the walk kept -- the reference keeps the one its breadth-first queue reaches first (udpt.cl:373)."""
+    import yune_b200 as yb
+    from tests.helpers import random_soup, soup_rays
+    rng = np.random.default_rng(seed)
+    T = random_soup(rng, n, "uniform")
+    T2 = np.concatenate([T, T])
+    sc = yb.Scene().setGeometry(T2, load_golden_scene("cornellbox")[1])
+    od, tm = soup_rays(rng, T, 20000)
+    return sc.vert_data, sc.bvh.copy(), od, tm
+
+
+def test_hand_made_tree_whose_boxes_do_not_nest_falls_back_to_the_reference_walk(hc, oracle):
+    """accel 1 decides 'the reference would have reached this triangle' from the leaf box alone, which needs every box
+    to contain its children's boxes.  A tree that does not nest (here: inner boxes shrunk, so the reference prunes subtrees whose
+    leaves a ray would pass) must be walked as uploaded: the layout reports accel 0 and the hits are the oracle's."""
+    tris, nodes, od, tm = _soup_with_duplicates(5, 1500)
+    inner = np.nonzero(nodes["child_idx"] > 0)[0]
+    victims = inner[(inner > 0)][::3]
+    mid = 0.5 * (nodes["p_min"][victims] + nodes["p_max"][victims])
+    nodes["p_min"][victims] = mid - 0.25 * (mid - nodes["p_min"][victims])
+    nodes["p_max"][victims] = mid + 0.25 * (nodes["p_max"][victims] - mid)
+    for accel in (1, 2):
+        assert hc.hc_layout_accel(ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), 0, accel) == 0
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    for accel in (0, 1, 2):
+        tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, 0, accel)
+        assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), accel
+
+
+def test_tie_rank_follows_the_breadth_first_queue_not_the_node_index(hc, oracle):
+    """the visiting rank that breaks exact ties must be the position in the reference's breadth-first queue.  Here
+    two DIFFERENT reference-built trees over the same triangles (copy i in tree A, copy i + n in tree B) hang under one root, A's
+    nodes stored before B's: child indices are after their parents but the array is not in breadth-first order.  Every hit is an
+    exact tie between the two copies; the queue reaches the shallower leaf first, the node index always says A."""
+    import yune_b200 as yb
+    from tests.helpers import random_soup, soup_rays
+    rng = np.random.default_rng(6)
+    n = 1500
+    T = random_soup(rng, n, "uniform")
+    mats = load_golden_scene("cornellbox")[1]
+    A = yb.Scene().setGeometry(T, mats, bvh_bins=20).bvh.copy()
+    B = yb.Scene().setGeometry(T, mats, bvh_bins=3).bvh.copy()
+    na, nb = A.size, B.size
+    nodes = np.zeros(1 + na + nb, NODE_DTYPE)
+    a_inner, b_inner = A["child_idx"] > 0, B["child_idx"] > 0
+    A["child_idx"][a_inner] += 2
+    B["child_idx"][b_inner] += na + 1
+    b_leaf = (B["child_idx"] == -1) & (B["vert_len"] > 0)
+    for j in range(10):
+        m = b_leaf & (B["vert_len"] > j)
+        B["vert_list"][m, j] += n
+    nodes[1], nodes[2], nodes[3:2 + na], nodes[2 + na:] = A[0], B[0], A[1:], B[1:]
+    nodes["p_min"][0] = np.minimum(A["p_min"][0], B["p_min"][0]); nodes["p_max"][0] = np.maximum(A["p_max"][0], B["p_max"][0])
+    nodes["child_idx"][0] = 1; nodes["vert_len"][0] = 0
+    tris = np.concatenate([T, T])
+    od, tm = soup_rays(rng, T, 20000)
+    assert hc.hc_layout_accel(ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), 0, 1) == 1       # boxes nest
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    assert ((otri >= n).sum() > 100) and ((otri >= 0) & (otri < n)).sum() > 100                         # both copies win somewhere
+    for leaf_split, accel in ((0, 0), (2, 0), (0, 1), (0, 2)):
+        tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
+        assert (tri == otri).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)

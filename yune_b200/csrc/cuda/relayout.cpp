@@ -175,12 +175,21 @@ struct OwnBuilder {
     }
 };
 
-// Structural checks shared by both layouts: child indices in range and breadth-first, leaves sane, every leaf linked from the root
-// (accel 1 decides reachability from the leaf boxes alone, so an orphan leaf must be an error, not silently visible).
-static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n_tris, std::string& err)
+// Structural checks shared by both layouts: child indices in range and after their parent, leaves sane, every leaf linked from the
+// root (accel 1 decides reachability from the leaf boxes alone, so an orphan leaf must be an error, not silently visible).
+// Also reports
+//   bfs_leaves  the linked leaves in the order the reference's breadth-first queue (udpt.cl:288-320) can reach them: a leaf's
+//               position in this list is the visiting rank that breaks exact ties in t.  For an array in breadth-first order (what
+//               the reference builder emits) this is node-index order; for a hand-made or deserialised array whose child indices
+//               do not increase with the parent index it is not, and the ranks must follow the queue, not the index.
+//   nested      every linked inner node's box contains the boxes of its non-empty children exactly.  The reference builder
+//               guarantees it (getExtent / resizeBvh, src/BVH.cpp:218-278); accel 1 / 2 RELY on it ("the leaf's box passes" implies
+//               "every ancestor's box passes"), so the caller walks the reference tree itself (accel 0) when it does not hold.
+static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n_tris, std::string& err, std::vector<int>* bfs_leaves = nullptr, bool* nested = nullptr)
 {
     std::vector<char> linked(n_nodes, 0);
     linked[0] = 1;
+    bool nest = true;
     for (int i = 0; i < n_nodes; i++) {
         const yune_bvh_node& nd = nodes[i];
         const bool is_leaf = nd.child_idx == -1 && nd.vert_len > 0;
@@ -193,7 +202,26 @@ static bool validateReferenceTree(const yune_bvh_node* nodes, int n_nodes, int n
         } else if (is_inner) {
             if (nd.child_idx + 1 >= n_nodes) { err = "child index out of range"; return false; }
             if (nd.child_idx <= i) { err = "BVH is not in breadth-first order (child index <= parent index)"; return false; }
-            if (linked[i]) linked[nd.child_idx] = linked[nd.child_idx + 1] = 1;
+            if (!linked[i]) continue;
+            for (int c = nd.child_idx; c <= nd.child_idx + 1; c++) {
+                if (linked[c]) { err = "node has two parents"; return false; }
+                linked[c] = 1;
+                const yune_bvh_node& ch = nodes[c];
+                if (!(ch.vert_len > 0 || ch.child_idx > 0)) continue;          // the reference's "empty" node: never visited (udpt.cl:316)
+                for (int k = 0; k < 3; k++)
+                    if (!(ch.aabb.p_min.s[k] >= nd.aabb.p_min.s[k] && ch.aabb.p_max.s[k] <= nd.aabb.p_max.s[k])) nest = false;
+            }
+        }
+    }
+    if (nested) *nested = nest;
+    if (bfs_leaves) {
+        bfs_leaves->clear();
+        std::vector<int> queue; queue.reserve(n_nodes);
+        if (n_nodes > 0) queue.push_back(0);
+        for (size_t h = 0; h < queue.size(); h++) {
+            const yune_bvh_node& nd = nodes[queue[h]];
+            if (nd.child_idx == -1 && nd.vert_len > 0) { bfs_leaves->push_back(queue[h]); continue; }
+            if (nd.child_idx > 0) { queue.push_back(nd.child_idx); queue.push_back(nd.child_idx + 1); }
         }
     }
     return true;
@@ -204,7 +232,8 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (std::getenv("YUNE_BVH_TIMING")) { auto T1 = std::chrono::steady_clock::now(); std::fprintf(stderr, "  relayout %s: %.2f s\n", what, std::chrono::duration<double>(T1 - T0).count()); T0 = T1; } };
     const bool brute = n_nodes == 0;       // no reference tree: the reference tests every triangle in index order (udpt.cl:280-284)
-    if (!brute && !validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    std::vector<int> bfs_leaves;
+    if (!brute && !validateReferenceTree(nodes, n_nodes, n_tris, err, &bfs_leaves)) return false;
     lap("validate");
     // reference leaves: id, box, visiting rank of every triangle slot
     std::vector<OwnTri> t; t.reserve(n_tris);
@@ -231,10 +260,8 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
         parallel_for((size_t)n_tris, [&](size_t i) { OwnTri& x = t[i]; x.tri = (int)i; x.rank = (int)i; x.leaf = 0; padded_bounds(x); });
         n_leaves = 1;
     }
-    for (int i = 0; i < n_nodes; i++) {
+    for (const int i : bfs_leaves) {
         const yune_bvh_node& nd = nodes[i];
-        if (!(nd.child_idx == -1 && nd.vert_len > 0)) continue;
-        if (nd.vert_len > 10) { err = "leaf with more than 10 triangles"; return false; }
         out.leaf_boxes.push_back({nd.aabb.p_min.s[0], nd.aabb.p_min.s[1], nd.aabb.p_min.s[2], 0.0f});
         out.leaf_boxes.push_back({nd.aabb.p_max.s[0], nd.aabb.p_max.s[1], nd.aabb.p_max.s[2], 0.0f});
         for (int j = 0; j < nd.vert_len; j++) {
@@ -247,6 +274,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
         n_leaves++;
     }
     lap("gather leaves");
+    if (t.size() >= ((size_t)1 << 27)) { err = "more than 2^27 triangle slots in the leaves (a leaf reference holds 27 bits)"; return false; }
     out.n_leaf_tris = (int)t.size();
     if (t.empty()) { out.root_ref = YUNE_REF_EMPTY; out.n_inner = out.n_inner_ref = 0; out.max_depth = 0; return true; }
     OwnBuilder B(t, leaf_max < 1 ? 2 : (leaf_max > 8 ? 8 : leaf_max));
@@ -357,7 +385,12 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     if (accel < 0 || accel > 2) { err = "accel must be 0, 1 or 2"; return false; }
     out.n_tris = n_tris; out.accel = accel;
 
-    if (n_nodes > 0 && !validateReferenceTree(nodes, n_nodes, n_tris, err)) return false;
+    std::vector<int> bfs_leaves; bool nested = true;
+    if (n_nodes > 0 && !validateReferenceTree(nodes, n_nodes, n_tris, err, &bfs_leaves, &nested)) return false;
+    // accel 1 / 2 answer "would the reference have reached this triangle?" from the leaf box alone, which is only right when every
+    // box contains its children's boxes.  A tree that was not built by the reference builder (hand-made, refitted, deserialised)
+    // may not nest: walk that tree itself, under the reference's own predicates.
+    if (accel >= 1 && n_nodes > 0 && !nested) { accel = 0; out.accel = 0; }
     if (accel >= 1) {
         if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err, leaf_split)) return false;
         goto shade_records;
@@ -366,7 +399,7 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     // classify nodes; inner nodes get their pair index in node-index (= breadth-first) order
     std::vector<int> ref(n_nodes, YUNE_REF_EMPTY);
     std::vector<char> kind(n_nodes, 0);      // 0 empty, 1 inner, 2 leaf
-    int n_inner = 0, n_slots = 0;
+    int n_inner = 0; long long n_slots = 0;
     for (int i = 0; i < n_nodes; i++) {
         const yune_bvh_node& nd = nodes[i];
         const bool is_leaf = nd.child_idx == -1 && nd.vert_len > 0;      // udpt.cl:301
@@ -383,17 +416,18 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
         }
         // anything else is the reference's "empty" node: vert_len <= 0 and child_idx <= 0 -> never visited (udpt.cl:316)
     }
-    out.n_inner_ref = n_inner; out.n_leaf_tris = n_slots;
+    if (n_slots >= (1ll << 27)) { err = "more than 2^27 triangle slots in the leaves (a leaf reference holds 27 bits)"; return false; }
+    out.n_inner_ref = n_inner; out.n_leaf_tris = (int)n_slots;
     for (int k = 0; k < 3; k++) { out.root_lo[k] = nodes[0].aabb.p_min.s[k]; out.root_hi[k] = nodes[0].aabb.p_max.s[k]; }
 
-    // leaves, in node-index order: rank = the reference's breadth-first visiting order of the triangle slots
+    // leaves, in the order of the reference's breadth-first queue (= node-index order for a reference-built array): rank = the
+    // reference's visiting order of the triangle slots
     out.pairs.resize((size_t)n_inner * 4);
     out.tris.reserve((size_t)n_slots * 3);
     Refiner refiner(tris, out, leaf_split > 0 ? leaf_split : 16);
     int rank = 0, sub_depth = 0;
     std::vector<SubTri> work;
-    for (int i = 0; i < n_nodes; i++) {
-        if (kind[i] != 2) continue;
+    for (const int i : bfs_leaves) {
         const yune_bvh_node& nd = nodes[i];
         work.clear();
         for (int j = 0; j < nd.vert_len; j++) {

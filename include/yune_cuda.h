@@ -73,7 +73,9 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   idle), "phase_min" (run a triangle step once this many lanes hold postponed triangles), "inner_min" / "inner_chain"
  *   (chain up to inner_chain further node steps without a new vote while inner_min lanes can take one),
  *   "shade_blocks_per_sm" (persistent shade grid; 0 = what the occupancy query returns),
- *   "isect" (0 = reference Moller-Trumbore), "deterministic" (0/1, below), "max_iterations", "sync_every", "time_stages", "count_work".
+ *   "isect" (0 = the reference's Moller-Trumbore behind the exact leaf-box filter: hit records bit-identical to udpt.cl:326-431, default;
+ *   1 = PERF MODE: watertight edge-function test on the raw vertices, no filter -- needs accel 1; differs from 0 only for rays within rounding distance
+ *   of an edge, a vertex or a reference box face), "deterministic" (0/1, below), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);
 int yune_get_option(yune_ctx* ctx, const char* key, double* value);

@@ -33,7 +33,9 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
                         int* tri_id, int* light_id, float* t_hit, unsigned long long* work2, int leaf_split, int accel)
 {
     TravLayoutHost lay; std::string err;
-    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
+    const int isect = (accel >> 8) & 1;              // bit 8 of `accel`: perf-mode (watertight) intersection, own tree only
+    accel &= 0xff;
+    if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel, isect)) return -1;
     accel = lay.accel;                               // bvh_size == 0 (brute-force mode) always walks the own tree
     HostLeafFetch lf{lay.leaf_boxes.data()};
     HostPairFetch pf{lay.pairs.data()}; HostTriFetch tf{lay.tris.data()}; HostQuadFetch qf{lay.quads.data()};
@@ -50,6 +52,7 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
             bool occ = lid >= 0;
             if (!occ) {
                 if (accel == 2) { HitRec h; trace_wide<HostQuadFetch, HostTriFetch, HostLeafFetch, true, true>(qf, tf, lf, lay.root_wide_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
+                else if (accel == 1 && isect) { HitRec h; trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, true, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
                 else if (accel == 1) { HitRec h; trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc); occ = h.tri >= 0; }
                 else occ = any_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, &wc);
             }
@@ -57,6 +60,7 @@ extern "C" int hc_trace(int n, const float* od6, const float* tmax, int any, con
         } else {
             HitRec h;
             if (accel == 2) trace_wide<HostQuadFetch, HostTriFetch, HostLeafFetch, false, true>(qf, tf, lf, lay.root_wide_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
+            else if (accel == 1 && isect) trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, false, true, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             else if (accel == 1) trace_own<HostPairFetch, HostTriFetch, HostLeafFetch, false, true>(pf, tf, lf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             else closest_hit<HostPairFetch, HostTriFetch, true>(pf, tf, lay.root_ref, lay.root_lo, lay.root_hi, o, d, t, h, &wc);
             tri_id[i] = h.tri; light_id[i] = h.tri >= 0 ? -1 : lid; if (t_hit) t_hit[i] = h.t;

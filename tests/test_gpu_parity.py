@@ -855,3 +855,63 @@ def test_group_deterministic_image_is_identical_for_any_gpu_count(n_dev):
     np.testing.assert_array_equal(imgs[0][1], imgs[1][1])
     np.testing.assert_array_equal(imgs[0][0], imgs[1][0])
     assert (imgs[1][1][..., 3] == spp).all()
+
+
+def test_watertight_perf_mode_on_device(gpu_manager):
+    """Option "isect" = 1 (north star: a watertight ray-triangle test; SURVEY 7: ship a parity mode and a perf mode).
+    (a) the device walk returns what the host build of the same headers returns, bit for bit (tests/test_traversal_hostcheck.py
+    pins that one: <= 1e-5 of the rays differ from parity mode, no ray leaks through shared edges / vertices of a closed mesh);
+    (b) against parity mode ON THE DEVICE: hit ids differ for <= 1e-5 of the rays; (c) no leak through the icosphere's edges and
+    vertices; (d) a render in perf mode is the render in parity mode except for the handful of pixels whose paths grazed an edge."""
+    import ctypes as C
+    from tests.helpers import ROOT
+    from tests.refbind import ptr
+    from tests.test_traversal_hostcheck import _trace, _icosphere, WT
+    from tests.refbind import TRI_DTYPE
+    hc = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libyune_hostcheck.so"))
+    m = gpu_manager
+    assert m.getOption("accel") == 1
+    try:
+        r, sc = _renderer(m, "teapot", 64, 64)
+        rng = np.random.RandomState(41); n = 300000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:1000, 0] = 0; d[1000:2000, 1] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od = np.concatenate([o, d], 1).astype(np.float32)
+        tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
+        p_tri, p_light, p_t = r.traceRays(od)
+        m.setOption("isect", 1)
+        w_tri, w_light, w_t = r.traceRays(od)
+        h_tri, h_light, h_t, _ = _trace(hc, od, None, 0, sc.vert_data, sc.bvh, 0, WT)
+        assert (w_tri == h_tri).all() and (w_light == h_light).all() and (_bits(w_t) == _bits(h_t)).all()          # (a)
+        assert (w_tri != p_tri).mean() <= 1e-5                                                                      # (b)
+        wa = r.traceRays(od, tm, any_hit=True); ha = _trace(hc, od, tm, 1, sc.vert_data, sc.bvh, 0, WT)
+        assert ((wa[0] >= 0) == (ha[0] >= 0)).all()
+        # (c) closed mesh, rays aimed exactly at vertices and edge points
+        V, F = _icosphere(4)
+        T = np.zeros(F.shape[0], TRI_DTYPE)
+        for k, name in enumerate(("v1", "v2", "v3")):
+            T[name][:, :3] = V[F[:, k]]; T[name][:, 3] = 1.0; T["vn" + name[1]][:, :3] = V[F[:, k]]
+        ball = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
+        r2 = yb.RendererCore(m, 32, 32)
+        assert r2.setup(ball), m.last_message
+        e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+        targets = np.concatenate([V, 0.5 * (V[e[:, 0]] + V[e[:, 1]])]).astype(np.float32)
+        o2 = np.float32([0.1, -0.2, 0.05])
+        d2 = targets - o2; d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+        od2 = np.concatenate([np.broadcast_to(o2, d2.shape), d2], 1).astype(np.float32)
+        tri2, light2, _ = r2.traceRays(od2)
+        assert (tri2 >= 0).all()
+        # (d) images
+        r3, _ = _renderer(m, "teapot", 96, 96, opts="-DMIS", transmissive_teapot=True)
+        r3.seed = 5
+        m.check(r3._lib.yune_render(r3._ctx, 0, 16, 1, r3.seed, 1)); img_w = r3.readSum()
+        m.setOption("isect", 0)
+        m.check(r3._lib.yune_render(r3._ctx, 0, 16, 1, r3.seed, 1)); img_p = r3.readSum()
+        same = (img_w == img_p).all(-1).mean()
+        assert same >= 0.995, same
+        assert abs(luminance(img_w).mean() / luminance(img_p).mean() - 1) < 2e-3
+        # the perf mode needs the own tree
+        m.setOption("accel", 0); m.setOption("isect", 1)
+        assert not m._ok(r3._lib.yune_render(r3._ctx, 0, 1, 1, 1, 1)) and "accel 1" in m.last_message
+    finally:
+        m.setOption("accel", 1); m.setOption("isect", 0)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from tests.helpers import ROOT, GOLDEN, load_golden_scene
-from tests.refbind import NODE_DTYPE, Oracle, default_cam_array, ptr
+from tests.refbind import NODE_DTYPE, TRI_DTYPE as TRI_DTYPE_, Oracle, default_cam_array, ptr
 
 LIGHT_UDPT = np.zeros(32, np.float32)
 LIGHT_UDPT[0:4] = [-0.1979, 0.92, -3.1972, 1]; LIGHT_UDPT[4:8] = [0, -1, 0, 0]; LIGHT_UDPT[8:12] = [16, 16, 16, 0]
@@ -333,3 +333,88 @@ def test_tie_rank_follows_the_breadth_first_queue_not_the_node_index(hc, oracle)
     for leaf_split, accel in ((0, 0), (2, 0), (0, 1), (0, 2)):
         tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
         assert (tri == otri).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)
+
+
+# ---- option "isect" = 1: the watertight perf-mode intersection (north star; SURVEY 7 "ship both") ----
+WT = 1 | 256        # hc_trace's accel argument: own tree, bit 8 = watertight
+
+
+def _icosphere(level, radius=1.0, centre=(0.0, 0.0, 0.0)):
+    t = (1 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(level):
+        cache, nf = {}, []
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]; v.append(m / np.linalg.norm(m)); cache[k] = len(v) - 1
+            return cache[k]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    V = (np.array(v) * radius + np.array(centre)).astype(np.float32)       # ONE float32 position per vertex, shared by its triangles
+    return V, np.array(f, np.int32)
+
+
+def test_watertight_mode_matches_parity_mode_except_at_edges(hc):
+    """isect 1 against isect 0 on the shipped scenes: the hit triangle may differ only for rays within rounding distance of an
+    edge / vertex (or of a reference box face, where the reference itself drops the hit), at most 1e-5 of the rays (SURVEY 7);
+    t agrees to 4e-6 absolute + 2e-6 relative (both tests are accurate to a few ulps of the vertex coordinates)."""
+    for scene in ("cornellbox", "teapot"):
+        tris, mats, nodes = load_golden_scene(scene)
+        rng = np.random.RandomState(11); n = 300000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od = np.concatenate([o, d], 1).astype(np.float32)
+        t0, l0, tt0, _ = _trace(hc, od, None, 0, tris, nodes, 0, 1)
+        t1, l1, tt1, _ = _trace(hc, od, None, 0, tris, nodes, 0, WT)
+        assert (t0 != t1).mean() <= 1e-5, scene
+        same = (t0 == t1) & (t0 >= 0)
+        assert (np.abs(tt0[same] - tt1[same]) <= 4e-6 + 2e-6 * np.abs(tt0[same])).all()
+        tm = rng.uniform(0.01, 2.5, n).astype(np.float32)
+        a0, _, _, _ = _trace(hc, od, tm, 1, tris, nodes, 0, 1)
+        a1, _, _, _ = _trace(hc, od, tm, 1, tris, nodes, 0, WT)
+        assert ((a0 >= 0) != (a1 >= 0)).mean() <= 1e-4        # a segment that ends within rounding distance of a surface may flip
+
+
+def test_watertight_mode_leaks_no_ray_through_shared_edges_and_vertices(hc):
+    """The property that names the mode: rays from inside a closed mesh aimed EXACTLY at its vertices and at points on its edges
+    (float32 positions, float32 directions) all hit something in isect 1.  (The reference's Moller-Trumbore decides u, v >= 0 and
+    u + v <= 1 per triangle with differently rounded edge vectors and lets some of these rays through; that count is only
+    reported, it is the reference's behaviour.)"""
+    import yune_b200 as yb
+    V, F = _icosphere(4)                                         # 5120 triangles, 2562 shared vertices
+    T = np.zeros(F.shape[0], TRI_DTYPE_)
+    for k, name in enumerate(("v1", "v2", "v3")):
+        T[name][:, :3] = V[F[:, k]]; T[name][:, 3] = 1.0
+        T["vn" + name[1]][:, :3] = V[F[:, k]]
+    sc = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
+    tris, nodes = sc.vert_data, sc.bvh
+    rng = np.random.default_rng(3)
+    origins = rng.uniform(-0.3, 0.3, (8, 3)).astype(np.float32)
+    e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+    w = rng.uniform(0, 1, (e.shape[0], 1)).astype(np.float32)
+    targets = np.concatenate([V, (V[e[:, 0]] * w + V[e[:, 1]] * (1 - w)).astype(np.float32), 0.5 * (V[e[:, 0]] + V[e[:, 1]])]).astype(np.float32)
+    leaks_wt = leaks_mt = total = 0
+    for o in origins:
+        d = targets - o
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        od = np.concatenate([np.broadcast_to(o, d.shape), d], 1).astype(np.float32)
+        t1, _, _, _ = _trace(hc, od, None, 0, tris, nodes, 0, WT)
+        t0, _, _, _ = _trace(hc, od, None, 0, tris, nodes, 0, 1)
+        leaks_wt += int((t1 < 0).sum()); leaks_mt += int((t0 < 0).sum()); total += od.shape[0]
+    print("rays at vertices / edges: %d, leaked in parity mode (reference behaviour): %d, in watertight mode: %d" % (total, leaks_mt, leaks_wt))
+    assert total > 100000 and leaks_wt == 0
+
+
+def test_watertight_mode_needs_the_own_tree(hc):
+    tris, mats, nodes = load_golden_scene("cornellbox")
+    od = np.zeros((1, 6), np.float32); od[0, 5] = -1
+    tri = np.zeros(1, np.int32); light = np.zeros(1, np.int32); t = np.zeros(1, np.float32); work = np.zeros(2, np.uint64)
+    for accel in (0, 2):
+        assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(LIGHT_UDPT), 1,
+                           ptr(tri), ptr(light), ptr(t), ptr(work), 0, accel | 256) == -1

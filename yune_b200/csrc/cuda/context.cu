@@ -171,7 +171,7 @@ static int ensure_scene(yune_ctx* c)
     }
     if (!c->layout_dirty) return YUNE_OK;
     std::string err;
-    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel))
+    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
     const TravLayoutHost& L = c->lay;
@@ -187,7 +187,7 @@ static int ensure_scene(yune_ctx* c)
     if (!L.shade.empty()) Y_CUDA(c, cudaMemcpyAsync(c->d_shade, L.shade.data(), L.shade.size() * 16, cudaMemcpyHostToDevice, c->stream));
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
     DevScene& s = c->sc;
-    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats; s.leaf_boxes = c->d_leaf_boxes; s.accel = L.accel;
+    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats; s.leaf_boxes = c->d_leaf_boxes; s.accel = L.accel; s.isect = L.isect;
     s.n_inner = L.n_inner; s.n_tris = L.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = L.root_ref;
     if (L.accel == 2) { s.n_inner = L.n_wide; s.root_ref = L.root_wide_ref; }
     for (int k = 0; k < 3; k++) { s.root_lo[k] = L.root_lo[k]; s.root_hi[k] = L.root_hi[k]; }
@@ -418,7 +418,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32) || (p == &c->opt_inner_min && (v < 1 || v > 33)) || (p == &c->opt_inner_chain && (v < 0 || v > 64))) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
-    if (p == &c->opt_isect && v != 0) Y_FAIL(c, YUNE_ERR_INVALID, "isect: only 0 (reference Moller-Trumbore) is built into this revision");
+    if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_deterministic && (v != 0) != (*p != 0) && c->d_sum) {

@@ -121,6 +121,7 @@ __device__ __forceinline__ void lane_init(Lane& L, const DevScene& sc, float4 o,
     if (ACCEL & 1)      // o * (1/d) can overflow although 1/d is finite: lo * inv - oi would then be -inf for both planes (box lost)
         L.guard = L.guard || !(fabsf(L.oi.x) < INFINITY && fabsf(L.oi.y) < INFINITY && fabsf(L.oi.z) < INFINITY);
     if (ACCEL & 4) L.sgn = (L.inv.x < 0.0f ? 16 : 0) | (L.inv.y < 0.0f ? 16 << 8 : 0) | (L.inv.z < 0.0f ? 16 << 16 : 0);
+    if (ACCEL & 8) { const WtRay w = wt_setup(xyz(d)); L.d = w.S; L.sgn = w.kz; }      // isect 1: node steps never read the direction itself
     bool hit = sc.root_ref != YUNE_REF_EMPTY;
     if ((ACCEL & 1) == 0 && hit) {
         // the reference tests the root box first (udpt.cl:295-296).  With ACCEL 1 the boxes of our own tree only prune -- what the
@@ -272,17 +273,24 @@ __device__ __forceinline__ void lane_tri_step(Lane& L, const int* stack, const D
     if (COUNT) wc.tri++;
     // rayTriangleIntersection (udpt.cl:326-373), evaluated without early exits: the rejected lanes would idle anyway, and
     // NaNs (det == 0) fall through the comparisons exactly as in the sequential form.
-    const V3 e1 = xyz(b), e2 = xyz(c);
-    const V3 pvec = vcross(rd, e2);
-    const float det = vdot(e1, pvec);
-    const float inv_det = __frcp_rn(det);
-    const V3 dist = vsub(ro, xyz(a));
-    const float u = YF_MUL(vdot(pvec, dist), inv_det);
-    const V3 qvec = vcross(dist, e1);
-    const float v = YF_MUL(vdot(qvec, rd), inv_det);
-    const float t = YF_MUL(vdot(e2, qvec), inv_det);
-    bool inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
-    if ((ACCEL & 1) == 1) {
+    float t, u, v; bool inside;
+    if (ACCEL & 8) {
+        // isect 1 (perf mode): watertight test on the raw vertices (trace_core.h), no leaf-box filter
+        WtRay w; w.S = rd; w.kz = L.sgn;
+        inside = tri_test_watertight(ro, w, xyz(a), xyz(b), xyz(c), t, u, v);
+    } else {
+        const V3 e1 = xyz(b), e2 = xyz(c);
+        const V3 pvec = vcross(rd, e2);
+        const float det = vdot(e1, pvec);
+        const float inv_det = __frcp_rn(det);
+        const V3 dist = vsub(ro, xyz(a));
+        u = YF_MUL(vdot(pvec, dist), inv_det);
+        const V3 qvec = vcross(dist, e1);
+        v = YF_MUL(vdot(qvec, rd), inv_det);
+        t = YF_MUL(vdot(e2, qvec), inv_det);
+        inside = !(u < 0.0f || u > 1.0f) && !(v < 0.0f || YF_ADD(u, v) > 1.0f);
+    }
+    if ((ACCEL & 9) == 1) {
         // Would the reference have reached this triangle?  <=> the uploaded box of its reference leaf passes the reference's
         // own predicate (its ancestors' boxes contain it exactly, so they pass too).  Geometrically a ray that hits the
         // triangle always crosses that box, so the test can only ever reject in last-bit grazing cases; it is evaluated just
@@ -914,18 +922,20 @@ __global__ void k_capture(PathPool P, const IterCounters* c, int max_rays, float
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
 
 // Which instantiation serves a scene: ACCEL bit 0 = own tree + leaf-box filter, bit 1 = every node record is staged in shared
-// memory (no global node path compiled in), bit 2 = 4-wide records.
+// memory (no global node path compiled in), bit 2 = 4-wide records, bit 3 = watertight intersection instead of the filter + the
+// reference's Moller-Trumbore (isect 1, own binary tree only).
 typedef void (*TraceKernel)(TraceArgs);
 static TraceKernel trace_kernel(const DevScene& sc, bool count)
 {
     const bool all_staged = sc.n_smem_pairs >= sc.n_inner;
+    if (sc.isect == 1) return count ? k_trace<true, 9> : (all_staged ? k_trace<false, 11> : k_trace<false, 9>);
     if (sc.accel == 2) return count ? k_trace<true, 5> : (all_staged ? k_trace<false, 7> : k_trace<false, 5>);
     if (sc.accel == 1) return count ? k_trace<true, 1> : (all_staged ? k_trace<false, 3> : k_trace<false, 1>);
     return count ? k_trace<true, 0> : k_trace<false, 0>;
 }
 int trace_variant_id(const DevScene& sc, bool count)
 {
-    return sc.accel | (sc.n_smem_pairs >= sc.n_inner ? 4 : 0) | (count ? 8 : 0);
+    return sc.accel | (sc.n_smem_pairs >= sc.n_inner ? 4 : 0) | (count ? 8 : 0) | (sc.isect ? 16 : 0);
 }
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {

@@ -294,6 +294,7 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
         V3 v1 = v3(T.v1.s[0], T.v1.s[1], T.v1.s[2]);
         V3 e1 = vsub(v3(T.v2.s[0], T.v2.s[1], T.v2.s[2]), v1);
         V3 e2 = vsub(v3(T.v3.s[0], T.v3.s[1], T.v3.s[2]), v1);
+        if (out.isect == 1) { e1 = v3(T.v2.s[0], T.v2.s[1], T.v2.s[2]); e2 = v3(T.v3.s[0], T.v3.s[1], T.v3.s[2]); }   // raw vertices
         out.tris[3 * i + 0] = {v1.x, v1.y, v1.z, bits(t[i].tri)};
         out.tris[3 * i + 1] = {e1.x, e1.y, e1.z, bits(t[i].rank)};
         out.tris[3 * i + 2] = {e2.x, e2.y, e2.z, bits(t[i].leaf)};
@@ -373,9 +374,10 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
 } // namespace
 
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err, int leaf_split, int accel)
+                     TravLayoutHost& out, std::string& err, int leaf_split, int accel, int isect)
 {
     out = TravLayoutHost();
+    if (isect != 0 && isect != 1) { err = "isect must be 0 (reference Moller-Trumbore) or 1 (watertight)"; return false; }
     if (n_nodes < 0 || (n_nodes > 0 && !nodes)) { err = "bad BVH buffer"; return false; }
     if (n_tris < 0 || (n_tris > 0 && !tris)) { err = "bad triangle buffer"; return false; }
     if (n_tris >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
@@ -391,6 +393,8 @@ bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node*
     // box contains its children's boxes.  A tree that was not built by the reference builder (hand-made, refitted, deserialised)
     // may not nest: walk that tree itself, under the reference's own predicates.
     if (accel >= 1 && n_nodes > 0 && !nested) { accel = 0; out.accel = 0; }
+    if (isect == 1 && accel != 1) { err = "isect 1 (watertight) walks the own tree: it needs accel 1 and a tree whose boxes nest"; return false; }
+    out.isect = isect;
     if (accel >= 1) {
         if (!buildOwnLayout(tris, n_tris, nodes, n_nodes, out, err, leaf_split)) return false;
         goto shade_records;

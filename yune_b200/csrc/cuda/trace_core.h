@@ -111,6 +111,48 @@ YUNE_HD bool tri_test(const RayPre& r, V3 v1, V3 e1, V3 e2, float& t, float& u, 
     return true;
 }
 
+// PERF-MODE intersection (option "isect" = 1; north star: "a watertight ray-triangle test"; replaces rayTriangleIntersection,
+// udpt.cl:326-390, whose edge decisions are not consistent between the two triangles that share an edge).  Woop / Benthin / Wald's
+// formulation: vertices relative to the ray origin, axes permuted so that z is the ray's major axis, sheared so that the ray
+// becomes the z axis; then 2-D edge functions
+//     U = C'x B'y - C'y B'x    V = A'x C'y - A'y C'x    W = B'x A'y - B'y A'x        inside <=> no two of them have opposite signs
+//     det = U + V + W,   t = (U A'z + V B'z + W C'z) / det,   (u, v) = (V, W) / det   (the reference's barycentrics of v2 / v3)
+// The sheared coordinates are offsets from the RAY (small near the hit), so the products do not cancel the way origin-relative
+// triple products do.  Watertight along edges WITHOUT the paper's double-precision fallback because nothing here is contracted
+// into an FMA: a sheared vertex is a function of (ray, vertex bits) only -- the same for every triangle that uses the vertex --
+// and (a*b) - (c*d) is exactly antisymmetric, so the two triangles of an edge (P, Q) see edge values that are exact negatives of
+// each other: a ray cannot be outside of both, and a ray on the edge (value 0) is inside both.  Borders included, two-sided, like
+// the reference's test.  Needs the three RAW vertices (trav_layout.h, isect 1): v1 + (v2 - v1) would not reproduce v2's bits.
+struct WtRay { V3 S; int kz; };        // S = (d[kx] / d[kz], d[ky] / d[kz], 1 / d[kz]); (kx, ky, kz) cyclic, kz = major axis of d
+YUNE_HD V3 wt_perm(V3 p, int kz) { return kz == 2 ? p : (kz == 0 ? v3(p.y, p.z, p.x) : v3(p.z, p.x, p.y)); }
+YUNE_HD WtRay wt_setup(V3 d)
+{
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    WtRay w;
+    w.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    const V3 pd = wt_perm(d, w.kz);
+    const float sz = YF_DIV(1.0f, pd.z);
+    w.S = v3(YF_MUL(pd.x, sz), YF_MUL(pd.y, sz), sz);
+    return w;
+}
+YUNE_HD bool tri_test_watertight(V3 o, const WtRay& w, V3 v1, V3 v2, V3 v3_, float& t, float& u, float& v)
+{
+    const V3 A = wt_perm(vsub(v1, o), w.kz), B = wt_perm(vsub(v2, o), w.kz), C = wt_perm(vsub(v3_, o), w.kz);
+    const float Ax = YF_SUB(A.x, YF_MUL(w.S.x, A.z)), Ay = YF_SUB(A.y, YF_MUL(w.S.y, A.z));
+    const float Bx = YF_SUB(B.x, YF_MUL(w.S.x, B.z)), By = YF_SUB(B.y, YF_MUL(w.S.y, B.z));
+    const float Cx = YF_SUB(C.x, YF_MUL(w.S.x, C.z)), Cy = YF_SUB(C.y, YF_MUL(w.S.y, C.z));
+    const float U = YF_SUB(YF_MUL(Cx, By), YF_MUL(Cy, Bx));
+    const float V = YF_SUB(YF_MUL(Ax, Cy), YF_MUL(Ay, Cx));
+    const float W = YF_SUB(YF_MUL(Bx, Ay), YF_MUL(By, Ax));
+    const bool neg = (U < 0.0f) || (V < 0.0f) || (W < 0.0f), pos = (U > 0.0f) || (V > 0.0f) || (W > 0.0f);
+    const float det = YF_ADD(YF_ADD(U, V), W);
+    const float inv_det = YF_DIV(1.0f, det);
+    const float T = YF_ADD(YF_ADD(YF_MUL(U, YF_MUL(w.S.z, A.z)), YF_MUL(V, YF_MUL(w.S.z, B.z))), YF_MUL(W, YF_MUL(w.S.z, C.z)));
+    t = YF_MUL(T, inv_det);
+    u = YF_MUL(V, inv_det); v = YF_MUL(W, inv_det);
+    return !(neg && pos) && det != 0.0f;           // a NaN passes here and fails the caller's 't > 0'
+}
+
 struct HitRec { float t, u, v; int tri; };   // tri = original triangle index, -1 = nothing closer than t_in
 
 struct WorkCount { unsigned box, tri; };
@@ -230,18 +272,26 @@ YUNE_HD void ts_inner_step_own(TraceState& s, int* stack, const PairFetch& fetch
     else ts_pop(s, stack);
 }
 // fetch_leaf_box(id, lo, hi) returns the uploaded box of reference leaf `id`
-template <class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
+// WT: perf-mode intersection (isect 1): raw vertices, tri_test_watertight, no leaf-box filter (that filter reproduces the
+// reference's misses at grazing boxes, which is exactly what a watertight walk must not do).
+template <class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT, bool WT = false>
 YUNE_HD void ts_tri_step_own(TraceState& s, const int* stack, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, WorkCount* wc)
 {
     const int pos = s.leaf_pos++;
     F4 a, b, c, lo, hi;
     fetch_tri(pos, a, b, c);
-    fetch_leaf_box(YF_ASINT(c.w), lo, hi);
     float t, u, v, entry;
-    if (COUNT) { wc->tri++; wc->box++; }
-    // would the reference have reached this triangle?  <=> the box of its leaf passes the reference's predicate (udpt.cl:392-431)
-    const bool reachable = box_hit(s.r, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry);
-    if (reachable && tri_test(s.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+    bool inside;
+    if (WT) {
+        if (COUNT) wc->tri++;
+        inside = tri_test_watertight(s.r.o, wt_setup(s.r.d), v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v);
+    } else {
+        fetch_leaf_box(YF_ASINT(c.w), lo, hi);
+        if (COUNT) { wc->tri++; wc->box++; }
+        // would the reference have reached this triangle?  <=> the box of its leaf passes the reference's predicate (udpt.cl:392-431)
+        inside = box_hit(s.r, lo.x, hi.x, lo.y, hi.y, lo.z, hi.z, entry) && tri_test(s.r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v);
+    }
+    if (inside) {
         if (ANY) {
             if (t > 0.0f && t < s.t_best) { s.tri = 0; s.done = true; s.leaf_pos = s.leaf_end = 0; return; }
         } else if (t > 0.0f && (t < s.t_best || (t == s.t_best && s.best_pos >= 0 && YF_ASINT(b.w) < s.best_pos))) {
@@ -264,14 +314,14 @@ YUNE_HD void ts_init_own(TraceState& s, V3 o, V3 d, float t_in, int root_ref, co
     if (!box_hit_own(s.r, root_lo[0], root_hi[0], root_lo[1], root_hi[1], root_lo[2], root_hi[2], s.t_prune, entry)) { s.done = true; return; }
     ts_enter(s, root_ref);
 }
-template <class PairFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT>
+template <class PairFetch, class TriFetch, class LeafBoxFetch, bool ANY, bool COUNT, bool WT = false>
 YUNE_HD void trace_own(const PairFetch& fetch_pair, const TriFetch& fetch_tri, const LeafBoxFetch& fetch_leaf_box, int root_ref,
                        const float* root_lo, const float* root_hi, V3 o, V3 d, float t_in, HitRec& out, WorkCount* wc)
 {
     TraceState s; int stack[YUNE_STACK_SIZE];
     ts_init_own<COUNT>(s, o, d, t_in, root_ref, root_lo, root_hi, wc);
     while (!s.done) {
-        if (s.leaf_pos < s.leaf_end) ts_tri_step_own<TriFetch, LeafBoxFetch, ANY, COUNT>(s, stack, fetch_tri, fetch_leaf_box, wc);
+        if (s.leaf_pos < s.leaf_end) ts_tri_step_own<TriFetch, LeafBoxFetch, ANY, COUNT, WT>(s, stack, fetch_tri, fetch_leaf_box, wc);
         else ts_inner_step_own<PairFetch, ANY, COUNT>(s, stack, fetch_pair, wc);
     }
     out.t = s.t_best; out.u = s.u; out.v = s.v; out.tri = s.tri;

@@ -41,6 +41,7 @@ struct TravLayoutHost {
     std::vector<F4> quads;       // accel 2: 7 per wide node: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] refs[4]; unused slot = inverted box + YUNE_REF_EMPTY
     int   n_wide = 0, root_wide_ref = YUNE_REF_EMPTY, wide_depth = 0;
     int   accel = 0;
+    int   isect = 0;             // 1: `tris` holds the three RAW vertices (t0 = v1, t1 = v2, t2 = v3; same w fields) for the watertight test
     int   n_inner = 0, n_inner_ref = 0, n_leaf_tris = 0, n_tris = 0;   // n_inner counts refinement pairs too; n_inner_ref = reference inner nodes
     int   root_ref = YUNE_REF_EMPTY;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
@@ -66,8 +67,12 @@ struct TravLayoutHost {
 //
 // n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
 //        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.
+//
+// isect: 0 = the reference's Moller-Trumbore (parity mode: hit records bit-identical to the reference's);
+//        1 = watertight signed-volume test on the raw vertices, no leaf-box filter (perf mode, own tree only: accel 1).  Differs from
+//            mode 0 only for rays within rounding distance of an edge / vertex or of a reference box face (tests pin the rate).
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0);
+                     TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0, int isect = 0);
 
 } // namespace yune
 #endif

@@ -18,6 +18,7 @@ struct DevScene {
     const float4* leaf_boxes;// accel 1: 2 x float4 per REFERENCE leaf (its uploaded box), indexed by triangle record t2.w
     int   accel;             // 0 = walk the reference tree, 1 = walk our own tree + exact leaf-box filter (trav_layout.h),
                              // 2 = as 1 over 4-wide records (`pairs` then holds 7 x float4 per record, n_inner counts them)
+    int   isect;             // 0 = the reference's Moller-Trumbore + leaf-box filter (parity mode), 1 = watertight test on raw vertices (accel 1 only)
     int   n_inner, n_tris, n_mats, root_ref;
     float root_lo[3], root_hi[3];
     int   n_smem_pairs;      // pair records [0, n_smem_pairs) are staged in shared memory by the trace kernel

@@ -75,7 +75,7 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "shade_blocks_per_sm" (persistent shade grid; 0 = what the occupancy query returns),
  *   "isect" (0 = the reference's Moller-Trumbore behind the exact leaf-box filter: hit records bit-identical to udpt.cl:326-431, default;
  *   1 = PERF MODE: watertight edge-function test on the raw vertices, no filter -- needs accel 1; differs from 0 only for rays within rounding distance
- *   of an edge, a vertex or a reference box face), "deterministic" (0/1, below), "max_iterations", "sync_every", "time_stages", "count_work".
+ *   of an edge, a vertex or a reference box face), "deterministic" (0/1, below), "pipeline" (0/1, see yune_finish), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);
 int yune_get_option(yune_ctx* ctx, const char* key, double* value);
@@ -87,6 +87,15 @@ int yune_get_option(yune_ctx* ctx, const char* key, double* value);
  * `seed` keys the counter-based RNG (it replaces the per-frame `rand`, kernel arg 10): sample s of pixel p
  * always sees the same random numbers, whatever the spp split or GPU count. */
 int yune_render(yune_ctx* ctx, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset);
+/* Option "pipeline" = 1: the reference's interactive call pattern -- ONE sample per pixel per call
+ * (src/RendererCore.cpp:248-306, 483-486) -- without paying a full drain of the wavefront per call.  yune_render then returns
+ * as soon as every sample of the call has been handed out; the paths still in flight keep their slots and finish during the
+ * NEXT call (the pool stays full across calls), or in yune_finish.  Until then the image lacks those samples (each pixel's
+ * count `a` says how many it holds, so the running mean stays a mean of complete samples).  After yune_finish the image is
+ * bit-for-bit the image of one big call over the same sample range (tests pin that).  reset != 0, or any change of scene,
+ * camera, program, lights, image size or options, discards the paths in flight; a change of seed / gi_check finishes them
+ * first under the values they were started with.  0 (default): every call returns a complete image. */
+int yune_finish(yune_ctx* ctx);
 /* Post-processing launch (src/RendererCore.cpp:340-371): mean = sum/a, Reinhard + gamma of tonemap.cl:14-47. */
 int yune_tonemap(yune_ctx* ctx);
 
@@ -156,6 +165,9 @@ typedef struct yune_stats {
     uint32_t steady_iterations, steady_timed_iterations;
     uint64_t steady_extend_rays, steady_shadow_rays;
     double   steady_trace_ms, steady_shade_ms;
+    uint32_t carried_paths;    /* option "pipeline": paths the last yune_render left in flight (0 after yune_finish)        */
+    uint32_t reserved0;
+    double   finish_ms;        /* device time of the last yune_finish                                                       */
 } yune_stats;
 int yune_get_stats(yune_ctx* ctx, yune_stats* out);
 

@@ -915,3 +915,53 @@ def test_watertight_perf_mode_on_device(gpu_manager):
         assert not m._ok(r3._lib.yune_render(r3._ctx, 0, 1, 1, 1, 1)) and "accel 1" in m.last_message
     finally:
         m.setOption("accel", 1); m.setOption("isect", 0)
+
+
+def test_pipelined_frames_add_up_to_one_big_call(gpu_manager):
+    """Option "pipeline": the reference's call pattern (ONE sample per pixel per call, src/RendererCore.cpp:483-486) without a full
+    drain per call.  A call returns when its samples are handed out and leaves paths in flight; after yune_finish the image is,
+    bit for bit (fixed-point accumulation), the image of one call over the whole sample range.  A change of seed finishes the
+    carried paths under the old seed first; reset discards them."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 96, 96, opts="-DMIS", transmissive_teapot=True)
+    r.seed = 9
+    lib, ctx = r._lib, r._ctx
+    N = 12
+    m.check(lib.yune_render(ctx, 0, N, 1, r.seed, 1)); whole = r.readSumFixed()
+    m.check(lib.yune_render(ctx, 0, N, 1, 77, 1)); whole77 = r.readSumFixed()
+    try:
+        m.setOption("pipeline", 1)
+        carried = 0
+        for f in range(N):
+            m.check(lib.yune_render(ctx, f, 1, 1, r.seed, 1 if f == 0 else 0))
+            lib.yune_get_stats(ctx, __import__("ctypes").byref(r.stats)); carried = max(carried, r.stats.carried_paths)
+        assert carried > 0                                     # something really was left in flight
+        partial = r.readSumFixed()
+        assert (partial[..., 3] <= N).all() and (partial[..., 3] < N).any()
+        st = r.finish()
+        assert st.carried_paths == 0
+        np.testing.assert_array_equal(r.readSumFixed(), whole)
+        r.finish()                                             # nothing in flight: a no-op
+        np.testing.assert_array_equal(r.readSumFixed(), whole)
+        # seed change between pipelined calls: the carried paths finish under the seed they were started with
+        half = N // 2
+        for f in range(half):
+            m.check(lib.yune_render(ctx, f, 1, 1, r.seed, 1 if f == 0 else 0))
+        for f in range(half, N):
+            m.check(lib.yune_render(ctx, f, 1, 1, 77, 0))
+        r.finish()
+        m.check(lib.yune_render(ctx, 0, half, 1, r.seed, 1)); a = r.readSumFixed()
+        m.check(lib.yune_render(ctx, half, N - half, 1, 77, 0)); r.finish()
+        mixed = r.readSumFixed()
+        m.setOption("pipeline", 0)
+        m.check(lib.yune_render(ctx, 0, half, 1, r.seed, 1)); m.check(lib.yune_render(ctx, half, N - half, 1, 77, 0))
+        np.testing.assert_array_equal(mixed, r.readSumFixed())
+        # reset discards what is in flight; a non-pipelined call after pipelined ones completes everything
+        m.setOption("pipeline", 1)
+        m.check(lib.yune_render(ctx, 0, 1, 1, r.seed, 1))
+        m.check(lib.yune_render(ctx, 0, 1, 1, r.seed, 1))
+        m.setOption("pipeline", 0)
+        m.check(lib.yune_render(ctx, 1, N - 1, 1, r.seed, 0))
+        np.testing.assert_array_equal(r.readSumFixed(), whole)
+    finally:
+        m.setOption("pipeline", 0)

@@ -19,7 +19,8 @@ class Stats(C.Structure):
                 ("iterations", C.c_uint32), ("kernel_launches", C.c_uint32), ("trace_launches", C.c_uint32), ("timed_iterations", C.c_uint32),
                 ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64),
                 ("steady_iterations", C.c_uint32), ("steady_timed_iterations", C.c_uint32), ("steady_extend_rays", C.c_uint64),
-                ("steady_shadow_rays", C.c_uint64), ("steady_trace_ms", C.c_double), ("steady_shade_ms", C.c_double)]
+                ("steady_shadow_rays", C.c_uint64), ("steady_trace_ms", C.c_double), ("steady_shade_ms", C.c_double),
+                ("carried_paths", C.c_uint32), ("reserved0", C.c_uint32), ("finish_ms", C.c_double)]
 
 
 class GroupStats(C.Structure):
@@ -43,6 +44,7 @@ CUDA_API = {
     "yune_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "yune_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]),
     "yune_render": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int]),
+    "yune_finish": (C.c_int, [C.c_void_p]),
     "yune_tonemap": (C.c_int, [C.c_void_p]),
     "yune_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yune_read_sum": (C.c_int, [C.c_void_p, C.c_void_p]),

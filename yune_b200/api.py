@@ -400,6 +400,12 @@ class RendererCore:
         self._lib.yune_get_stats(self._ctx, C.byref(self.stats))
         return self.stats
 
+    def finish(self):
+        """Option "pipeline": complete the paths the last enqueueKernels left in flight (yune_finish)."""
+        self.cl_manager.check(self._lib.yune_finish(self._ctx))
+        self._lib.yune_get_stats(self._ctx, C.byref(self.stats))
+        return self.stats
+
     def postProcess(self):
         self.cl_manager.check(self._lib.yune_tonemap(self._ctx))
         self._lib.yune_get_stats(self._ctx, C.byref(self.stats))

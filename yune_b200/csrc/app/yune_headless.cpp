@@ -3,10 +3,13 @@
 //   yune_headless --obj scene.obj [--kernel udpt.cl|bdpt.cl] [--opts -DMIS] [--width 1024 --height 1024] [--spp 64]
 //                 [--seed 12345] [--no-gi] [--bins 20] [--fov 60] [--out image.hdr|.png|.jpg|.pfm|.ppm] [--device 0]
 //                 [--save-at N --save-at-out file [--save-at-ext .jpg|.png|.hdr]]     ("Save At Samples": image after N spp)
+//                 [--frame-by-frame [--pipeline]]   one yune_render per sample like the reference's viewer (src/RendererCore.cpp:483-486);
+//                                 --pipeline sets option "pipeline": a frame returns when its samples are handed out (yune_cuda.h)
 //                 [--gpus N]     N > 1 (0 = every device): the sample range is sharded over N devices (yune_group_*), one ncclReduce
 #include "RendererCore.h"
 #include "ImageIO.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,7 +22,7 @@ int main(int argc, char** argv)
     std::string obj, kernel = "udpt.cl", opts, out, save_at_out, save_at_ext;
     int save_at = 0;
     int width = 1024, height = 1024, spp = 64, bins = 20, device = 0, gpus = 1;
-    unsigned seed = 12345; bool gi = true; float fov = 60.0f;
+    unsigned seed = 12345; bool gi = true, frame_by_frame = false, pipeline = false; float fov = 60.0f;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { std::cerr << "missing value for " << a << "\n"; std::exit(2); } return argv[++i]; };
@@ -29,6 +32,7 @@ int main(int argc, char** argv)
         else if (a == "--bins") bins = std::atoi(next()); else if (a == "--device") device = std::atoi(next());
         else if (a == "--fov") fov = (float)std::atof(next()); else if (a == "--out") out = next(); else if (a == "--no-gi") gi = false;
         else if (a == "--gpus") gpus = std::atoi(next());
+        else if (a == "--frame-by-frame") frame_by_frame = true; else if (a == "--pipeline") pipeline = true;
         else if (a == "--save-at") save_at = std::atoi(next()); else if (a == "--save-at-out") save_at_out = next(); else if (a == "--save-at-ext") save_at_ext = next();
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
@@ -85,7 +89,18 @@ int main(int argc, char** argv)
         if (bins > 0 && bins != 20) core.render_scene.loadBVH(bins);
         core.render_scene.main_camera.y_FOV = fov; core.render_scene.main_camera.updateViewPlaneDist();
         std::cout << "Total Triangles Loaded: " << core.render_scene.vert_data.size() << "\nBVH Size: " << core.render_scene.bvh.gpu_node_list.size() << " Nodes\n";
-        if (!core.setup(gi) || !core.enqueueKernels(spp, gi)) { std::cerr << manager.last_message << "\n"; return 1; }
+        if (!core.setup(gi)) { std::cerr << manager.last_message << "\n"; return 1; }
+        if (frame_by_frame) {
+            if (pipeline && yune_set_option(manager.ctx, "pipeline", 1) != YUNE_OK) { std::cerr << yune_last_error(manager.ctx) << "\n"; return 1; }
+            if (!core.enqueueKernels(1, gi)) { std::cerr << manager.last_message << "\n"; return 1; }      // first frame: pool allocation
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int f = 1; f < spp; f++) if (!core.enqueueKernels(1, gi)) { std::cerr << manager.last_message << "\n"; return 1; }
+            const auto t1 = std::chrono::steady_clock::now();
+            if (!core.finish()) { std::cerr << manager.last_message << "\n"; return 1; }
+            const auto t2 = std::chrono::steady_clock::now();
+            std::printf("frame by frame%s: %d frames, %.3f ms/frame (wall clock, frames 2..%d), finish %.3f ms\n", pipeline ? " (pipelined)" : "", spp,
+                        spp > 1 ? std::chrono::duration<double, std::milli>(t1 - t0).count() / (spp - 1) : 0.0, spp, std::chrono::duration<double, std::milli>(t2 - t1).count());
+        } else if (!core.enqueueKernels(spp, gi)) { std::cerr << manager.last_message << "\n"; return 1; }
         std::printf("samples/pixel %d  ms/frame %.4f  render time %.3f s  %.1f Msamples/s  %.1f Mrays/s  wavefront iterations %u\n",
                     core.samples_taken, core.mspf_avg, core.time_passed, core.msamples_per_s, core.mrays_per_s, core.stats.iterations);
         if (!out.empty()) { if (!core.saveImage(out)) { std::cerr << manager.last_message << "\n"; return 1; } std::cout << "wrote " << out << "\n"; }

@@ -86,6 +86,15 @@ struct yune_ctx {
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0, opt_deterministic = 1;
 
+    // Option "pipeline" (the reference's interactive call pattern, one sample per pixel per call, src/RendererCore.cpp:248-306,
+    // 483-486): a call returns as soon as its samples have all been HANDED OUT; the paths still in flight keep their slots and are
+    // carried into the next call (or yune_finish), so the pool stays full across calls instead of draining ~130 nearly empty
+    // iterations per frame.  `epoch` counts everything that invalidates paths in flight (scene, camera, program, lights, image size,
+    // options): a carry from another epoch is discarded.
+    int opt_pipeline = 0;
+    bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
+    unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
+
     int occ_dense[2] = {0, 0}, occ_bdpt[2] = {0, 0};                           // shade-kernel occupancy caches
     int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache
 
@@ -113,9 +122,10 @@ static void free_pool(yune_ctx* c)
 // Pool size.  "pool_slots" = 0 (default) sizes the pool for the job: measured on C1 / C2 at 16.8 M ... 1.07 G samples the best
 // pool doubles when the job quadruples (2 M, 4 M, 8 M, 16 M slots): a bigger pool amortises the per-iteration costs (launches,
 // kernel tails), a smaller one shortens the ramp at both ends of the job.  Hence 512 * sqrt(samples), as a power of two.
-static int ensure_pool(yune_ctx* c, unsigned long long n_samples)
+static int ensure_pool(yune_ctx* c, unsigned long long n_samples, bool keep)
 {
     const bool bd = c->integrator == INTEGRATOR_BDPT;
+    if (keep && c->pool.n_slots > 0) return YUNE_OK;      // paths of the previous call are still in flight in these slots
     int n = c->opt_pool_slots;
     if (n <= 0) {
         const double want = 512.0 * std::sqrt((double)n_samples);
@@ -302,6 +312,7 @@ static bool name_is(const char* s, const char* base)
 int yune_create_render_program(yune_ctx* c, const char* kernel, const char* opts)
 {
     if (!c) return YUNE_ERR_INVALID;
+    c->epoch++;
     int integ = name_is(kernel, "udpt") ? INTEGRATOR_UDPT : name_is(kernel, "bdpt") ? INTEGRATOR_BDPT : INTEGRATOR_NONE;
     if (integ == INTEGRATOR_NONE) Y_FAIL(c, YUNE_ERR_INVALID, "unknown render kernel '%s' (built-in: udpt.cl, bdpt.cl)", kernel ? kernel : "(null)");
     int mis = 0;
@@ -326,6 +337,7 @@ int yune_create_postproc_program(yune_ctx* c, const char* kernel, const char* op
 int yune_setup_vertex_buffer(yune_ctx* c, const yune_triangle* tris, int n)
 {
     if (!c || n < 0 || (n > 0 && !tris)) { if (c) c->err = "yune_setup_vertex_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     c->h_tris.assign(tris, tris + n);
     c->have_tris = true; c->layout_dirty = true;
     return YUNE_OK;
@@ -334,6 +346,7 @@ int yune_setup_vertex_buffer(yune_ctx* c, const yune_triangle* tris, int n)
 int yune_setup_mat_buffer(yune_ctx* c, const yune_material* mats, int n)
 {
     if (!c || n <= 0 || !mats) { if (c) c->err = "yune_setup_mat_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     Y_CUDA(c, cudaSetDevice(c->device));
     c->h_mats.assign(mats, mats + n);
     dfree(c->d_mats);
@@ -348,6 +361,7 @@ int yune_setup_mat_buffer(yune_ctx* c, const yune_material* mats, int n)
 int yune_setup_bvh_buffer(yune_ctx* c, const yune_bvh_node* nodes, int n)
 {
     if (!c || n < 0 || (n > 0 && !nodes)) { if (c) c->err = "yune_setup_bvh_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     // n == 0: the reference's brute-force mode (kernel arg 6 bvh_size == 0, udpt.cl:280-284) -- same hits, see relayout.cpp
     if (n > 0) c->h_nodes.assign(nodes, nodes + n); else c->h_nodes.clear();
     c->have_nodes = true; c->layout_dirty = true;
@@ -357,6 +371,7 @@ int yune_setup_bvh_buffer(yune_ctx* c, const yune_bvh_node* nodes, int n)
 int yune_setup_camera_buffer(yune_ctx* c, const yune_cam* cam)
 {
     if (!c || !cam) { if (c) c->err = "yune_setup_camera_buffer: bad arguments"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     c->cam = *cam; c->have_cam = true;
     return YUNE_OK;
 }
@@ -364,6 +379,7 @@ int yune_setup_camera_buffer(yune_ctx* c, const yune_cam* cam)
 int yune_setup_image_buffers(yune_ctx* c, int W, int H)
 {
     if (!c || W <= 0 || H <= 0 || (long long)W * H > (1ll << 30)) { if (c) c->err = "yune_setup_image_buffers: bad size"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     Y_CUDA(c, cudaSetDevice(c->device));
     const size_t n = (size_t)W * H;
     if (c->d_sum && c->W == W && c->H == H) {          // same size: keep the allocation (and any pointer handed out), just clear
@@ -385,6 +401,7 @@ int yune_setup_image_buffers(yune_ctx* c, int W, int H)
 int yune_set_light_sources(yune_ctx* c, const yune_quad_light* lights, int n)
 {
     if (!c || n < 0 || (n > 0 && !lights)) { if (c) c->err = "yune_set_light_sources: bad arguments"; return YUNE_ERR_INVALID; }
+    c->epoch++;
     if (n > YUNE_MAX_LIGHTS) Y_FAIL(c, YUNE_ERR_LIMIT, "at most %d quad lights are supported", YUNE_MAX_LIGHTS);
     if (n == 0) { c->user_lights = false; set_builtin_lights(c); return YUNE_OK; }
     c->lights.n = n;
@@ -401,7 +418,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -431,6 +448,8 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
             Y_CUDA(c, cudaStreamSynchronize(c->stream));
         }
     }
+    // anything but the pure measurement / call-pattern knobs invalidates paths that a pipelined call left in flight
+    if (v != *p && p != &c->opt_pipeline && p != &c->opt_time_stages && p != &c->opt_max_iterations && p != &c->opt_sync_every) c->epoch++;
     *p = v;
     return YUNE_OK;
 }
@@ -443,9 +462,10 @@ int yune_get_option(yune_ctx* c, const char* key, double* value)
     return YUNE_OK;
 }
 
-int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset)
+// One call of the frame loop.  `wait_all`: return only when no path is in flight (the default contract); otherwise (option
+// "pipeline") return as soon as every sample of this call has been handed out -- the rest is carried (see yune_ctx::carry).
+static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset, bool wait_all)
 {
-    if (!c) return YUNE_ERR_INVALID;
     if (spp_begin < 0 || spp_count < 0) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: negative sample range");
     if ((long long)spp_begin + (long long)spp_count > 2147483647ll) Y_FAIL(c, YUNE_ERR_INVALID, "yune_render: spp_begin + spp_count exceeds INT_MAX");
     if (c->integrator != INTEGRATOR_UDPT && c->integrator != INTEGRATOR_BDPT) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: no render program selected");
@@ -453,8 +473,16 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     if (!c->have_cam) Y_FAIL(c, YUNE_ERR_STATE, "yune_render: camera buffer not set up");
     Y_CUDA(c, cudaSetDevice(c->device));
     int rc;
+    // paths a pipelined call left in flight continue in this call, unless the image is reset or anything they depend on changed
+    bool cont = c->carry && !reset && c->carry_epoch == c->epoch && c->pool_integrator == c->integrator;
+    if (cont && (seed != c->carry_seed || (gi_check != 0) != (c->carry_gi != 0))) {
+        // they were started under another seed / GI switch: finish them under those before this call's samples start
+        if ((rc = render_impl(c, 0, 0, c->carry_gi, c->carry_seed, 0, true)) != YUNE_OK) return rc;
+        cont = false;
+    }
+    c->carry = false;
     if ((rc = ensure_scene(c)) != YUNE_OK) return rc;
-    if ((rc = ensure_pool(c, (unsigned long long)c->W * c->H * (unsigned long long)spp_count)) != YUNE_OK) return rc;
+    if ((rc = ensure_pool(c, (unsigned long long)c->W * c->H * (unsigned long long)spp_count, cont)) != YUNE_OK) return rc;
     TraceLaunch tl;
     if ((rc = trace_config(c, tl, c->opt_count_work != 0)) != YUNE_OK) return rc;
 
@@ -472,8 +500,11 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     c->h_tot->n_samples = (unsigned long long)n_pix * (unsigned long long)spp_count;
     c->h_tot->live_last = 1;
     Y_CUDA(c, cudaMemcpyAsync(c->d_tot, c->h_tot, sizeof(Totals), cudaMemcpyHostToDevice, c->stream));
-    Y_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(IterCounters), c->stream));
-    Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
+    if (!cont) {
+        Y_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(IterCounters), c->stream));
+        Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
+        c->it_global = 0;
+    }
     Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
     RenderArgs a = make_args(c);
@@ -496,7 +527,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     }
     Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     int it = 0;
-    bool done = spp_count == 0;
+    bool done = spp_count == 0 && !cont;
+    const int sync_every = wait_all ? c->opt_sync_every : (c->opt_sync_every < 4 ? c->opt_sync_every : 4);
     // Steady state = the windows between two host syncs in which the pool was full throughout: past the first iterations (the
     // path mix has settled) and with samples still left to hand out after the window (every finished slot was regenerated).
     // Their rays and timed launches are reported separately so that a roofline can divide like by like.
@@ -505,8 +537,8 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     unsigned long long prev_ext = 0, prev_sh = 0;
     while (!done) {
         const int window_begin = it;
-        for (int b = 0; b < c->opt_sync_every && it < c->opt_max_iterations; b++, it++) {
-            const int p = it & 1;
+        for (int b = 0; b < sync_every && it < c->opt_max_iterations; b++, it++, c->it_global++) {
+            const int p = (int)(c->it_global & 1u);
             a.parity = p;
             t.n_extend = &c->d_ctr[p].n_extend; t.fetch_extend = &c->d_ctr[p].fetch_extend;
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
@@ -532,6 +564,7 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
         }
         prev_ext = c->h_tot->extend_rays; prev_sh = c->h_tot->shadow_rays;
         if (c->h_tot->live_last == 0) done = true;
+        else if (!wait_all && a.tail) { done = true; c->carry = true; c->carry_epoch = c->epoch; c->carry_seed = seed; c->carry_gi = gi_check; }
         else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
     }
     float shade_ms = 0.f, trace_ms = 0.f;
@@ -554,8 +587,26 @@ int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_
     st.slot_visits = (uint64_t)c->pool.n_slots * (uint64_t)it;
     st.box_tests = c->h_tot->box_tests; st.tri_tests = c->h_tot->tri_tests; st.iterations = (uint32_t)it;
     st.tonemap_ms = c->stats.tonemap_ms;
+    st.carried_paths = c->carry ? (uint32_t)c->h_tot->live_last : 0u;
     c->stats = st;
     return YUNE_OK;
+}
+
+int yune_render(yune_ctx* c, int spp_begin, int spp_count, int gi_check, uint32_t seed, int reset)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    return render_impl(c, spp_begin, spp_count, gi_check, seed, reset, c->opt_pipeline == 0);
+}
+
+int yune_finish(yune_ctx* c)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->carry) return YUNE_OK;
+    if (c->carry_epoch != c->epoch) { c->carry = false; return YUNE_OK; }      // what they depended on changed: discarded
+    const yune_stats before = c->stats;
+    const int rc = render_impl(c, 0, 0, c->carry_gi, c->carry_seed, 0, true);
+    if (rc == YUNE_OK) { const float ms = c->stats.render_ms; c->stats = before; c->stats.finish_ms = ms; c->stats.carried_paths = 0; }
+    return rc;
 }
 
 int yune_tonemap(yune_ctx* c)

@@ -133,7 +133,7 @@ namespace yune
             samples_taken += n; left -= n;
             yune_get_stats(cl_manager.ctx, &stats);
             ms += stats.render_ms; samples += (double)stats.samples; rays += (double)(stats.extend_rays + stats.shadow_rays);
-            if (reached) ok = saveImage(save_samples_fn, save_samples_ext) && ok;
+            if (reached) ok = saveImage(save_samples_fn, save_samples_ext) && ok;      // (finishes paths in flight first)
         } while (left > 0);
         // endFrame() metrics (:483-505): one frame = one sample per pixel
         mspf_avg = frames > 0 ? (float)(ms / frames) : 0.0f;
@@ -142,6 +142,14 @@ namespace yune
         msamples_per_s = ms > 0 ? samples / ms / 1e3 : 0;
         mrays_per_s = ms > 0 ? rays / ms / 1e3 : 0;
         return ok;
+    }
+
+    // Option "pipeline" (yune_cuda.h): complete the paths the last frames left in flight.  A no-op otherwise.
+    bool RendererCore::finish()
+    {
+        if (yune_finish(cl_manager.ctx) != YUNE_OK) { cl_manager.last_message = yune_last_error(cl_manager.ctx); return false; }
+        yune_get_stats(cl_manager.ctx, &stats);
+        return true;
     }
 
     bool RendererCore::postProcess()
@@ -161,6 +169,7 @@ namespace yune
         std::vector<float> img((size_t)width * height * 4);
         const bool ldr = imageIsLdr(save_ext);
         if (!ldr && !imageIsHdr(save_ext)) { cl_manager.last_message = "unsupported image extension (use .hdr, .png, .jpg, .pfm or .ppm)"; return false; }
+        if (!finish()) return false;                                     // a saved image holds complete samples only
         if (ldr && !postProcess()) return false;
         const int rc = ldr ? yune_read_ldr(cl_manager.ctx, img.data()) : yune_read_hdr(cl_manager.ctx, img.data());
         if (rc != YUNE_OK) { cl_manager.last_message = yune_last_error(cl_manager.ctx); return false; }

@@ -49,7 +49,8 @@ namespace yune
             bool loadScene(std::string path, std::string fn);                             /**< src/RendererCore.cpp:124-137 */
             bool setup(bool gi_check);                                                    /**< upload scene + camera, allocate images */
             bool enqueueKernels(int frames, bool new_gi_check);                           /**< `frames` more samples per pixel; blocks until done */
-            bool postProcess();
+            bool finish();                       // option "pipeline": complete the paths still in flight (yune_finish)
+        bool postProcess();
             bool reloadMatFile();                                                         /**< src/RendererCore.cpp:109-122 + the buffer update the GUI triggers (src/RendererGUI.cpp:203-220) */
             void resetValues();                                                           /**< src/RendererCore.cpp:77-86: counters and metrics back to zero; the next frame starts a new image */
             void stop();                                                                  /**< src/RendererCore.cpp:88-107: wait for the device, then resetValues() */

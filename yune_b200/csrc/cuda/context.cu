@@ -131,6 +131,7 @@ static int ensure_pool(yune_ctx* c, unsigned long long n_samples, bool keep)
         const double want = 512.0 * std::sqrt((double)n_samples);
         int e = (int)std::lround(std::log2(want > 1.0 ? want : 1.0));
         const int e_max = bd ? 23 : 24;                      // a BDPT slot carries 4 KB of path vertices: 8 M slots = 35 GB of the 180 GB
+        if (c->opt_pipeline) e += 2;                         // calls of ONE sample per pixel: the pool is shared by consecutive calls (measured: 2.9 / 2.3 / 2.2 ms per 1024^2 frame at 0.5 / 1 / 2 M slots)
         if (e < 16) e = 16;
         if (e > e_max) e = e_max;
         n = 1 << e;
@@ -504,7 +505,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
         Y_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, 2 * sizeof(IterCounters), c->stream));
         Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
         c->it_global = 0;
-    }
+    } else if (spp_count > 0) Y_CUDA(c, launch_pool_revive(c->pool, c->stream));      // slots the previous call's drain retired
     Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
     RenderArgs a = make_args(c);
@@ -528,7 +529,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     int it = 0;
     bool done = spp_count == 0 && !cont;
-    const int sync_every = wait_all ? c->opt_sync_every : (c->opt_sync_every < 4 ? c->opt_sync_every : 4);
+    const int sync_every = wait_all ? c->opt_sync_every : 1;      // a pipelined call is a few iterations long: look after each one
     // Steady state = the windows between two host syncs in which the pool was full throughout: past the first iterations (the
     // path mix has settled) and with samples still left to hand out after the window (every finished slot was regenerated).
     // Their rays and timed launches are reported separately so that a roofline can divide like by like.

@@ -799,6 +799,13 @@ __global__ void k_pool_reset(PathPool P)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < P.n_slots) P.meta[s] = make_uint4(0, 0, 0, YS_FREE);
 }
+// A pipelined call (yune_ctx::carry) continues on a pool that the previous call left in its drain phase: slots that found no
+// sample to start are DONE.  They take part again.
+__global__ void k_pool_revive(PathPool P)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < P.n_slots && (P.meta[s].w & YS_STATE_MASK) == YS_DONE) P.meta[s].w = YS_FREE;
+}
 __global__ void k_fill_f4(float4* p, size_t n, float4 v)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -981,6 +988,11 @@ cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_ray
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st)
 {
     k_pool_reset<<<ceil_div(p.n_slots, 256), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_pool_revive(const PathPool& p, cudaStream_t st)
+{
+    k_pool_revive<<<ceil_div(p.n_slots, 256), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st)

@@ -39,6 +39,7 @@ cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per
 cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, int* occ_cache, cudaStream_t st);
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
+cudaError_t launch_pool_revive(const PathPool& p, cudaStream_t st);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);
 cudaError_t launch_fix_to_sum(const long long* fix, float4* sum, size_t n, cudaStream_t st);
 cudaError_t launch_sum_to_fix(const float4* sum, long long* fix, size_t n, cudaStream_t st);

@@ -154,6 +154,33 @@ def cpu_reference_run(cfg, scene, width, height, spp, threads):
     return width * height * spp / dt / 1e6, kind
 
 
+def reference_opencl_run(cfg, scene, width, height, frames, want_image=False):
+    """SURVEY.md 8c / 8d "opportunistic" second baseline: the reference's own udpt.cl run ON THE GPU by NVIDIA's OpenCL driver, with
+    the reference's launch protocol (oracle/_ref/yune_ref_ocl, built from the reference tree by oracle/gen_ref_ocl.py; test /
+    measurement infrastructure).  One frame = one sample per pixel.  Returns the binary's JSON line as a dict (or
+    {"unavailable": why}); with want_image also the final running-mean image."""
+    import tempfile
+    from tests.refbind import default_cam_array, frame_rands
+    exe = os.path.join(ROOT, "oracle", "_ref", "yune_ref_ocl")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/yune_ref_ocl not built (needs /root/reference at build time)"}
+    if cfg["ref_variant"] is None:
+        return {"unavailable": "the reference kernel cannot express this config (one built-in light, no Oren-Nayar, 1500-entry queue)"}
+    tris, mats, nodes, lights = scene
+    with tempfile.TemporaryDirectory() as d:
+        for name, a in (("tris", tris), ("mats", mats), ("nodes", nodes), ("cam", default_cam_array())):
+            np.ascontiguousarray(a).tofile(os.path.join(d, name + ".bin"))
+        np.array(frame_rands(SEED, frames + 1), np.uint32).tofile(os.path.join(d, "rands.bin"))
+        try:
+            p = subprocess.run([exe, d, str(width), str(height), str(frames), "1", cfg["opts"]], capture_output=True, text=True, timeout=300)
+            out = json.loads(p.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            return {"unavailable": "yune_ref_ocl failed: %s" % e}
+        if want_image and "unavailable" not in out:
+            out["image"] = np.fromfile(os.path.join(d, "image.bin"), np.float32).reshape(height, width, 4)
+    return out
+
+
 def cpu_sample_text(cfg, w, h, spp, kind):
     why = ""
     if kind == "port" and cfg["ref_variant"] is None:
@@ -207,6 +234,33 @@ def algorithmic_bytes_per_ray(r, tris, nodes, warm_spp):
         n = od.shape[0]
         out[name] = {"rays": n, "box": nb / n, "tri": nt / n, "bytes": 32.0 * nb / n + 48.0 * nt / n + 48.0}
     r.captureRays(0, 0)
+    return out
+
+
+def frame_times(m, lib, ctx, W, H):
+    """The reference's interactive call pattern: ONE sample per pixel per yune_render (src/RendererCore.cpp:483-486).  ms per call
+    when every call returns a complete image (default) and with option "pipeline" (a call returns when its samples are handed
+    out, paths in flight are carried into the next call; yune_finish completes the image)."""
+    import yune_b200 as yb
+    m.setOption("time_stages", 0)
+    st = yb._native.Stats()
+    exact = []
+    for f in range(6):
+        m.check(lib.yune_render(ctx, f, 1, 1, SEED, 1 if f == 0 else 0)); lib.yune_get_stats(ctx, C.byref(st)); exact.append(st.render_ms)
+    out = {"spp_per_call": 1, "image": "%dx%d" % (W, H), "complete_image_per_call_ms": float(np.median(exact[1:]))}
+    try:
+        m.setOption("pipeline", 1)
+        n = 64
+        m.check(lib.yune_render(ctx, 0, 1, 1, SEED, 1))
+        t0 = time.perf_counter()
+        for f in range(1, n + 1):
+            m.check(lib.yune_render(ctx, f, 1, 1, SEED, 0))
+        out["pipelined_ms"] = (time.perf_counter() - t0) * 1e3 / n
+        lib.yune_get_stats(ctx, C.byref(st)); out["pipelined_paths_in_flight"] = int(st.carried_paths)
+        m.check(lib.yune_finish(ctx)); lib.yune_get_stats(ctx, C.byref(st)); out["finish_ms"] = st.finish_ms
+        out["pipelined_pool_slots"] = int(m.getOption("pool_slots_in_use"))
+    finally:
+        m.setOption("pipeline", 0)
     return out
 
 
@@ -420,6 +474,12 @@ def run_ours(args, cfg):
     cw, ch, cspp = cfg["cpu_sample"]
     cpu_v, kind = cpu_reference_run(cfg, (tris, mats, nodes, lights), cw, ch, cspp, cores) if world == 1 else (None, "reference")
     rays = agg["extend_rays"] + agg["shadow_rays"]
+    # the reference's kernel on this very GPU (NVIDIA OpenCL), bounded: 16 frames of the config's image size
+    ref_ocl = None
+    if world == 1:
+        ref_ocl = reference_opencl_run(cfg, (tris, mats, nodes, lights), W, H, 16 if W * H <= (1 << 21) else 4)
+        ref_ocl["sample"] = "%dx%d, %d frames of 1 spp, reference RNG" % (W, H, ref_ocl.get("frames", 0)) if "unavailable" not in ref_ocl else None
+    frames = frame_times(m, lib, ctx, W, H) if world == 1 and not bdpt and W * H <= (1 << 21) else None
     line = {
         "metric": cfg["metric"], "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
@@ -438,6 +498,8 @@ def run_ours(args, cfg):
         "roofline": roofline,
         "roofline_onchip": onchip,
         "roofline_shade": roofline_shade,
+        "reference_opencl_same_gpu": ref_ocl,
+        "frame_ms": frames,
         "cpu_baseline": None if world > 1 else {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": cpu_sample_text(cfg, cw, ch, cspp, kind)},
     }
     sys.stdout.flush()

@@ -98,7 +98,11 @@ def build_oracle(force=False):
         kdeps = [os.path.join(odir, f) for f in ("gen_ref_kernels.py", "clc_shim.inc", "ref_kernel_driver.inc", "ref_tonemap_driver.inc")]
         if force or _newer(kern_so, kdeps):
             subprocess.check_call([sys.executable, os.path.join(odir, "gen_ref_kernels.py")])
-        outs += [host_so, kern_so]
+        ocl = os.path.join(refdir, "yune_ref_ocl")      # the reference's udpt.cl behind an OpenCL host (runs it on the box's GPU)
+        odeps = [os.path.join(odir, f) for f in ("gen_ref_ocl.py", "ref_ocl_driver.c")]
+        if force or _newer(ocl, odeps):
+            subprocess.check_call([sys.executable, os.path.join(odir, "gen_ref_ocl.py")])
+        outs += [host_so, kern_so, ocl]
     return outs
 
 

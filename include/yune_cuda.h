@@ -55,6 +55,16 @@ int yune_create_postproc_program(yune_ctx* ctx, const char* kernel, const char* 
 int yune_setup_vertex_buffer(yune_ctx* ctx, const yune_triangle* tris, int n_triangles);   /* args 3,4 */
 int yune_setup_mat_buffer(yune_ctx* ctx, const yune_material* mats, int n_materials);      /* arg 5    */
 int yune_setup_bvh_buffer(yune_ctx* ctx, const yune_bvh_node* nodes, int n_nodes);         /* args 6,7; n = 0 (nodes may be NULL): the reference's brute-force mode, udpt.cl:280-284 -- same hit records (every triangle, index order, no box test), answered by a walk over our own tree */
+/* BVH construction ON THE DEVICE, behind the same BVHNodeGPU contract (the reference builds on the host,
+ * src/BVH.cpp:56-173, and at 10 M triangles that is seconds before the first sample).  Needs the vertex and material buffers;
+ * replaces any uploaded BVH.  Builds a linear BVH (Morton order, Karras' parallel hierarchy) with leaves of <= leaf_max (1..10,
+ * 0 = 2) triangles and emits, without leaving the GPU, both the reference-format node array (breadth-first, siblings adjacent,
+ * nested boxes, the reference's +0.2 rule for flat boxes; yune_read_bvh_buffer hands it out) and the traversal layout of it.
+ * Hit records are those of the reference's walk (udpt.cl:288-431) over THAT array, bit for bit; it is not the reference
+ * builder's tree (yune_scene_load_bvh reproduces that one byte for byte) and, being an LBVH, costs more steps per ray. */
+int yune_build_bvh_on_device(yune_ctx* ctx, int leaf_max);
+int yune_bvh_info(yune_ctx* ctx, int* n_nodes, int* n_inner_nodes, int* depth, float* device_build_ms);
+int yune_read_bvh_buffer(yune_ctx* ctx, yune_bvh_node* nodes, int capacity);      /* the uploaded or device-built array */
 int yune_setup_camera_buffer(yune_ctx* ctx, const yune_cam* cam);                          /* arg 2    */
 int yune_setup_image_buffers(yune_ctx* ctx, int width, int height);                        /* args 0,1 */
 /* Replaces the kernels' __constant Quad light_sources[LIGHT_SIZE]; n in [1, 8].  n = 0 restores the

@@ -968,3 +968,70 @@ def test_pipelined_frames_add_up_to_one_big_call(gpu_manager):
         np.testing.assert_array_equal(r.readSumFixed(), whole)
     finally:
         m.setOption("pipeline", 0)
+
+
+@pytest.mark.parametrize("scene,leaf_max", [("teapot", 2), ("cornellbox", 1), ("uniform", 4), ("flats", 2), ("mixed", 10), ("tiny", 2)])
+def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene, leaf_max):
+    """the BVH built ON THE GPU (yune_build_bvh_on_device: Morton order + Karras hierarchy, bvh_build.cu) is handed
+    out in the reference's BVHNodeGPU format and walked by the device from the layout emitted next to it.  Pins: (a) the downloaded
+    array is a well-formed reference tree whose boxes nest (the host layout code accepts it for accel 1) and holds every triangle
+    exactly once; (b) device hits == the ORACLE's reference-style walk (udpt.cl:288-431) of that downloaded array, bit for bit,
+    closest and any-hit; (c) uploading the downloaded array like any host-built one gives the same hits again; (d) a render with it
+    agrees with the render over the reference builder's tree (same estimator; hits differ only where a ray grazes a box face)."""
+    import ctypes as C
+    from tests.helpers import ROOT, random_soup, soup_rays
+    from tests.refbind import ptr
+    hc = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libyune_hostcheck.so"))
+    m = gpu_manager
+    rng = np.random.default_rng(61)
+    mats = load_golden_scene("cornellbox")[1]
+    if scene in ("teapot", "cornellbox"):
+        sc = golden_scene_object(scene)
+        n = 200000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:1000, 0] = 0; d[1000:2000, 1] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od = np.concatenate([o, d], 1).astype(np.float32); tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
+    else:
+        T = random_soup(rng, 3 if scene == "tiny" else 3000, "uniform" if scene == "tiny" else scene)
+        sc = yb.Scene().setGeometry(T, mats)
+        od, tm = soup_rays(rng, T, 60000)
+    r = yb.RendererCore(m, 64, 64)
+    assert m.createRenderProgram("udpt.cl", compiler_opts=""), m.last_message
+    assert r.setup(sc), m.last_message
+    host_hits = r.traceRays(od)
+    assert m.buildBVHOnDevice(leaf_max), m.last_message
+    info = m.bvhInfo()
+    nodes = m.readBVHBuffer()
+    tris = sc.vert_data
+    # (a)
+    assert nodes.size == info["n_nodes"] and info["device_build_ms"] > 0
+    leaf = (nodes["child_idx"] == -1) & (nodes["vert_len"] > 0)
+    inner = nodes["child_idx"] > 0
+    assert (leaf | inner).all() and (nodes["vert_len"][leaf] <= leaf_max).all()
+    listed = np.concatenate([nodes["vert_list"][i, :nodes["vert_len"][i]] for i in np.nonzero(leaf)[0]])
+    assert np.array_equal(np.sort(listed), np.arange(tris.size))
+    assert hc.hc_layout_accel(ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), 0, 1) == 1
+    # (b)
+    cfg = Oracle.config("udpt")
+    tri, light, t = r.traceRays(od)
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all()
+    atri, alight, _ = r.traceRays(od, tm, any_hit=True)
+    stri, slight, _ = oracle.trace(cfg, od, tm, 1, tris, nodes)
+    assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
+    assert (tri != host_hits[0]).mean() < 1e-3                     # the two trees only disagree where a ray grazes a box face
+    # (d) before (c) replaces the device-built layout
+    if scene == "teapot":
+        r.seed = 3
+        m.check(r._lib.yune_render(r._ctx, 0, 16, 1, r.seed, 1)); img_dev = r.readSum()
+    # (c)
+    assert m.setupBVHBuffer(nodes), m.last_message
+    tri2, light2, t2 = r.traceRays(od)
+    assert (tri2 == tri).all() and (_bits(t2) == _bits(t)).all()
+    if scene == "teapot":
+        m.check(r._lib.yune_render(r._ctx, 0, 16, 1, r.seed, 1))
+        np.testing.assert_array_equal(r.readSum(), img_dev)       # same tree through both layout paths: the same image, bit for bit
+        assert r.setup(sc)
+        m.check(r._lib.yune_render(r._ctx, 0, 16, 1, r.seed, 1)); img_host = r.readSum()
+        assert abs(luminance(img_dev).mean() / luminance(img_host).mean() - 1) < 2e-3
+        assert (img_dev == img_host).all(-1).mean() > 0.99

@@ -38,6 +38,9 @@ CUDA_API = {
     "yune_setup_vertex_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yune_setup_mat_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yune_setup_bvh_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_build_bvh_on_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "yune_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "yune_read_bvh_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yune_setup_camera_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yune_setup_image_buffers": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "yune_set_light_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

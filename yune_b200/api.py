@@ -235,6 +235,21 @@ class CUDAManager:
         a = np.ascontiguousarray(vert_data)
         return self._ok(self._lib.yune_setup_vertex_buffer(self._ctx, _ptr(a), int(a.size)))
 
+    def buildBVHOnDevice(self, leaf_max=2):
+        """Build the BVH on the GPU from the uploaded vertex buffer (yune_build_bvh_on_device) instead of uploading one."""
+        return self._ok(self._lib.yune_build_bvh_on_device(self._ctx, int(leaf_max)))
+
+    def bvhInfo(self):
+        n, ni, d, ms = C.c_int(), C.c_int(), C.c_int(), C.c_float()
+        self.check(self._lib.yune_bvh_info(self._ctx, C.byref(n), C.byref(ni), C.byref(d), C.byref(ms)))
+        return dict(n_nodes=n.value, n_inner=ni.value, depth=d.value, device_build_ms=ms.value)
+
+    def readBVHBuffer(self):
+        """The BVHNodeGPU array in use (uploaded or device-built), reference record layout."""
+        a = np.zeros(self.bvhInfo()["n_nodes"], NODE_DTYPE)
+        self.check(self._lib.yune_read_bvh_buffer(self._ctx, _ptr(a), int(a.size)))
+        return a
+
     def setupMatBuffer(self, mat_data):
         a = np.ascontiguousarray(mat_data)
         return self._ok(self._lib.yune_setup_mat_buffer(self._ctx, _ptr(a), int(a.size)))

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "yune_b200", "csrc")
 LIB = os.path.join(ROOT, "yune_b200", "libyune_b200.so")
 
-CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu", "cuda/group.cu"]
+CUDA_SOURCES = ["cuda/kernels.cu", "cuda/bdpt.cu", "cuda/context.cu", "cuda/group.cu", "cuda/bvh_build.cu"]
 HOST_SOURCES = ["cuda/relayout.cpp", "host/BVH.cpp", "host/Scene.cpp", "host/Camera.cpp", "host/RendererCore.cpp", "host/ImageIO.cpp", "host/host_capi.cpp"]
 APP = os.path.join(ROOT, "yune_b200", "yune_headless")
 

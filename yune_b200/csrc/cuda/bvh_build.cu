@@ -1,0 +1,354 @@
+// bvh_build.cu -- BVH construction ON THE DEVICE behind the BVHNodeGPU contract.
+//
+// The reference builds its BVH on the host (BVH::createBVH, src/BVH.cpp:56-173: binned SAH, recursive) and uploads an array of
+// 80-byte BVHNodeGPU records (include/CL_headers.h:86-92) that its kernel walks through `child_idx` / `child_idx + 1`
+// (udpt.cl:288-324).  csrc/host/BVH.cpp reproduces that builder byte for byte and stays the parity source; at 10.5 M triangles
+// it costs 4 s on 16 cores plus 7 s of re-layout and upload before the first sample.  This file is the fast path to the same
+// CONTRACT: from the uploaded TriangleGPU records it produces, on the GPU,
+//   (1) a BVHNodeGPU array in the reference's format (breadth-first, siblings adjacent, leaves of <= `leaf_max` <= 10 triangle
+//       indices, boxes that contain their children's boxes exactly, the reference's +0.2 rule for flat triangle boxes,
+//       src/TriangleCPU.cpp:53-70) -- yune_read_bvh_buffer hands it out, the reference's kernel or the oracle can walk it;
+//   (2) the traversal layout of trav_layout.h for that very tree (pair records breadth-first, triangle records grouped by leaf,
+//       leaf boxes, shading records, specular flags), so no host re-layout runs.
+// The tree is a linear BVH: 63-bit Morton codes of the centroids, radix sort (cub), Karras' parallel hierarchy (one thread per
+// inner node, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees", HPG 2012), boxes bottom-up with one
+// atomic per node, subtrees of <= leaf_max triangles collapsed into leaves (an LBVH subtree is a contiguous range of the sorted
+// order), breadth-first numbering level by level with a prefix sum per level.  It is NOT the reference's tree -- hit records
+// are those of a reference-style walk of THIS array (tests: device hits == the oracle's walk of the downloaded array, bit for
+// bit) -- and an LBVH is a worse tree than the SAH one (more steps per ray): the option trades render speed for start-up time.
+#include "kernels.h"
+#include "bvh_build.h"
+#include "strict_math.h"
+#include "trav_layout.h"
+
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace yune {
+
+namespace {
+
+#define YB_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { char _b[256]; snprintf(_b, sizeof _b, "%s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); err = _b; return false; } } while (0)
+
+struct Box { float lo[3], hi[3]; };
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x)
+{   // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8)  & 0x100f00f00f00f00full;
+    x = (x | x << 4)  & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2)  & 0x1249249249249249ull;
+    return x;
+}
+
+// per triangle: exact box (reference rule), padded box (relayout.cpp: padded_bounds), centroid bounds of the scene
+__global__ void k_tri_boxes(const yune_triangle* tris, int n, Box* exact, Box* padded, float* scene_lo, float* scene_hi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
+    if (i < n) {
+        const yune_triangle& T = tris[i];
+        Box e, p; float ext = 0.0f, mag = 0.0f;
+        for (int k = 0; k < 3; k++) {
+            e.lo[k] = fminf(T.v1.s[k], fminf(T.v2.s[k], T.v3.s[k]));
+            e.hi[k] = fmaxf(T.v1.s[k], fmaxf(T.v2.s[k], T.v3.s[k]));
+            p.lo[k] = e.lo[k]; p.hi[k] = e.hi[k];
+            ext = fmaxf(ext, e.hi[k] - e.lo[k]); mag = fmaxf(mag, fmaxf(fabsf(e.lo[k]), fabsf(e.hi[k])));
+            const float c = 0.5f * (e.lo[k] + e.hi[k]);
+            clo[k] = c; chi[k] = c;
+            if (e.hi[k] - e.lo[k] == 0.0f) e.hi[k] += 0.2f;            // src/TriangleCPU.cpp:63-67: a flat box could never pass 't_max > t_min'
+        }
+        const float pad = 2.0e-3f * ext + 4.0e-6f * mag + 1.0e-30f;    // relayout.cpp: the conservative margin of the own tree
+        for (int k = 0; k < 3; k++) { p.lo[k] -= pad; p.hi[k] += pad; }
+        exact[i] = e; padded[i] = p;
+    }
+    // block reduction of the centroid bounds, then one atomic per block and axis (floats ordered through their int bits)
+    typedef cub::BlockReduce<float, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    for (int k = 0; k < 3; k++) {
+        const float lo = BR(tmp).Reduce(clo[k], cub::Min()); __syncthreads();
+        const float hi = BR(tmp).Reduce(chi[k], cub::Max()); __syncthreads();
+        if (threadIdx.x == 0) {
+            // atomicMin / atomicMax on floats via the ordered-int trick (sign handled by two cases)
+            if (lo >= 0.0f) atomicMin(reinterpret_cast<int*>(scene_lo + k), __float_as_int(lo)); else atomicMax(reinterpret_cast<unsigned*>(scene_lo + k), __float_as_uint(lo));
+            if (hi >= 0.0f) atomicMax(reinterpret_cast<int*>(scene_hi + k), __float_as_int(hi)); else atomicMin(reinterpret_cast<unsigned*>(scene_hi + k), __float_as_uint(hi));
+        }
+    }
+}
+
+__global__ void k_morton(const Box* exact_unpadded_src, const yune_triangle* tris, int n, const float* scene_lo, const float* scene_hi, unsigned long long* keys, int* idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const yune_triangle& T = tris[i];
+    unsigned long long code = 0;
+    for (int k = 0; k < 3; k++) {
+        const float lo = fminf(T.v1.s[k], fminf(T.v2.s[k], T.v3.s[k])), hi = fmaxf(T.v1.s[k], fmaxf(T.v2.s[k], T.v3.s[k]));
+        const float c = 0.5f * (lo + hi), ext = scene_hi[k] - scene_lo[k];
+        float u = ext > 0.0f ? (c - scene_lo[k]) / ext : 0.0f;
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        const unsigned long long q = (unsigned long long)fminf(u * 2097152.0f, 2097151.0f);
+        code |= spread21(q) << (2 - k);
+    }
+    keys[i] = code; idx[i] = i;
+}
+
+// Karras 2012.  Sorted keys may repeat: ties are broken by the position (the paper's augmented key).
+__device__ __forceinline__ int delta(const unsigned long long* keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    return a == b ? 64 + __clz(i ^ j) : __clzll((long long)(a ^ b));
+}
+// inner nodes 0 .. n-2; a child reference >= 0 is an inner node, < 0 is ~position of a sorted triangle
+__global__ void k_hierarchy(const unsigned long long* keys, int n, int2* child, int2* range, int* parent_inner, int* parent_leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do { t = (t + 1) / 2; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = lo == gamma ? ~gamma : gamma, right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    child[i] = make_int2(left, right); range[i] = make_int2(lo, hi);
+    if (left >= 0) parent_inner[left] = i; else parent_leaf[~left] = i;
+    if (right >= 0) parent_inner[right] = i; else parent_leaf[~right] = i;
+    if (i == 0) parent_inner[0] = -1;
+}
+
+// boxes bottom-up: node boxes live in arrays of 2n - 1 entries, inner node i at i, sorted triangle p at n - 1 + p
+__global__ void k_fit(const int* sorted_tri, const Box* tri_exact, const Box* tri_padded, int n, const int2* child, const int* parent_inner, const int* parent_leaf,
+                      Box* exact, Box* padded, int* arrived)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    exact[n - 1 + p] = tri_exact[sorted_tri[p]]; padded[n - 1 + p] = tri_padded[sorted_tri[p]];
+    if (n == 1) return;
+    int node = parent_leaf[p];
+    __threadfence();
+    while (node >= 0) {
+        if (atomicAdd(&arrived[node], 1) == 0) return;            // the sibling subtree is not done yet: its thread continues
+        __threadfence();
+        const int2 c = child[node];
+        const int a = c.x >= 0 ? c.x : n - 1 + ~c.x, b = c.y >= 0 ? c.y : n - 1 + ~c.y;
+        Box e, q;
+        const volatile Box* ea = exact + a; const volatile Box* eb = exact + b; const volatile Box* pa = padded + a; const volatile Box* pb = padded + b;
+        for (int k = 0; k < 3; k++) {
+            e.lo[k] = fminf(ea->lo[k], eb->lo[k]); e.hi[k] = fmaxf(ea->hi[k], eb->hi[k]);
+            q.lo[k] = fminf(pa->lo[k], pb->lo[k]); q.hi[k] = fmaxf(pa->hi[k], pb->hi[k]);
+        }
+        exact[node] = e; padded[node] = q;
+        __threadfence();
+        node = parent_inner[node];
+    }
+}
+
+// ---- breadth-first numbering of the collapsed tree, one level per launch ----
+// `order` is the concatenation of the levels' frontiers; a frontier entry is a child reference (>= 0 inner node, < 0 ~position).
+__device__ __forceinline__ bool is_inner(int ref, const int2* range, int leaf_max) { return ref >= 0 && range[ref].y - range[ref].x + 1 > leaf_max; }
+__global__ void k_level_flags(const int* frontier, int m, const int2* range, int leaf_max, int* flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) flags[k] = is_inner(frontier[k], range, leaf_max) ? 1 : 0;
+}
+__global__ void k_level_expand(const int* frontier, int m, const int* flags, const int* rank, const int2* child, int pair_base, int* pair_of, int* next_frontier)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m || !flags[k]) return;
+    const int node = frontier[k];
+    pair_of[node] = pair_base + rank[k];
+    const int2 c = child[node];
+    next_frontier[2 * rank[k]] = c.x; next_frontier[2 * rank[k] + 1] = c.y;
+}
+__global__ void k_leaf_flags(const int* order, int n_nodes, const int2* range, int leaf_max, int* flags)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_nodes) flags[b] = is_inner(order[b], range, leaf_max) ? 0 : 1;
+}
+
+// ---- emission: BVHNodeGPU records, pair records, leaf boxes, triangle records ----
+__device__ __forceinline__ float4 f4i(float x, float y, float z, int w) { return make_float4(x, y, z, __int_as_float(w)); }
+__global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes, int n, int leaf_max, const int2* child, const int2* range, const int* pair_of,
+                       const int* leaf_rank, const Box* exact, const Box* padded, const int* sorted_tri, const yune_triangle* tris,
+                       yune_bvh_node* nodes, float4* pairs, float4* leaf_boxes, float4* tri_rec)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_nodes) return;
+    const int ref = order[b];
+    const int bi = ref >= 0 ? ref : n - 1 + ~ref;
+    const Box e = exact[bi];
+    yune_bvh_node nd;
+    for (int k = 0; k < 3; k++) { nd.aabb.p_min.s[k] = e.lo[k]; nd.aabb.p_max.s[k] = e.hi[k]; }
+    nd.aabb.p_min.s[3] = 1.0f; nd.aabb.p_max.s[3] = 1.0f;
+    for (int j = 0; j < 10; j++) nd.vert_list[j] = 0;
+    if (is_inner(ref, range, leaf_max)) {
+        nd.child_idx = first_child_bfs[b]; nd.vert_len = -1;
+        const int2 c = child[ref];
+        int refs[2]; Box pb[2];
+        for (int s = 0; s < 2; s++) {
+            const int cr = s ? c.y : c.x;
+            pb[s] = padded[cr >= 0 ? cr : n - 1 + ~cr];
+            if (is_inner(cr, range, leaf_max)) refs[s] = pair_of[cr];
+            else { const int first = cr >= 0 ? range[cr].x : ~cr, cnt = cr >= 0 ? range[cr].y - range[cr].x + 1 : 1; refs[s] = ~((first << 4) | cnt); }
+        }
+        float4* q = pairs + 4 * (size_t)pair_of[ref];
+        q[0] = make_float4(pb[0].lo[0], pb[0].hi[0], pb[0].lo[1], pb[0].hi[1]);
+        q[1] = make_float4(pb[1].lo[0], pb[1].hi[0], pb[1].lo[1], pb[1].hi[1]);
+        q[2] = make_float4(pb[0].lo[2], pb[0].hi[2], pb[1].lo[2], pb[1].hi[2]);
+        q[3] = make_float4(__int_as_float(refs[0]), __int_as_float(refs[1]), 0.0f, 0.0f);
+    } else {
+        const int first = ref >= 0 ? range[ref].x : ~ref, cnt = ref >= 0 ? range[ref].y - range[ref].x + 1 : 1;
+        const int lr = leaf_rank[b];
+        nd.child_idx = -1; nd.vert_len = cnt;
+        leaf_boxes[2 * (size_t)lr] = make_float4(e.lo[0], e.lo[1], e.lo[2], 0.0f);
+        leaf_boxes[2 * (size_t)lr + 1] = make_float4(e.hi[0], e.hi[1], e.hi[2], 0.0f);
+        for (int j = 0; j < cnt; j++) {
+            const int t = sorted_tri[first + j];
+            nd.vert_list[j] = t;
+            const yune_triangle& T = tris[t];
+            const V3 v1 = v3(T.v1.s[0], T.v1.s[1], T.v1.s[2]);
+            const V3 e1 = vsub(v3(T.v2.s[0], T.v2.s[1], T.v2.s[2]), v1);     // udpt.cl:328-329, the reference's own expressions (relayout.cpp)
+            const V3 e2 = vsub(v3(T.v3.s[0], T.v3.s[1], T.v3.s[2]), v1);
+            float4* r = tri_rec + 3 * (size_t)(first + j);
+            r[0] = f4i(v1.x, v1.y, v1.z, t);
+            r[1] = f4i(e1.x, e1.y, e1.z, lr * 16 + j);                        // visiting rank: leaves in breadth-first order, then the slot
+            r[2] = f4i(e2.x, e2.y, e2.z, lr);
+        }
+    }
+    nodes[b] = nd;
+}
+// the breadth-first index of an inner node's first child = where its two frontier slots landed
+__global__ void k_first_child(const int* order, int level_begin, int m, const int* flags, const int* rank, int next_begin, int* first_child_bfs)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) first_child_bfs[level_begin + k] = flags[k] ? next_begin + 2 * rank[k] : -1;
+}
+
+// shading records and specular flags by ORIGINAL triangle index (relayout.cpp: shade_records; context.cu: tri_class)
+__global__ void k_shade_records(const yune_triangle* tris, int n, const yune_material* mats, int n_mats, float4* shade, unsigned char* tri_class)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const yune_triangle& T = tris[i];
+    const V3 n1 = vnormalize(v3(T.vn1.s[0], T.vn1.s[1], T.vn1.s[2]));       // udpt.cl:377-379
+    const V3 n2 = vnormalize(v3(T.vn2.s[0], T.vn2.s[1], T.vn2.s[2]));
+    const V3 n3 = vnormalize(v3(T.vn3.s[0], T.vn3.s[1], T.vn3.s[2]));
+    float4* s = shade + 4 * (size_t)i;
+    s[0] = f4i(n1.x, n1.y, n1.z, T.matID); s[1] = make_float4(n2.x, n2.y, n2.z, 0.0f); s[2] = make_float4(n3.x, n3.y, n3.z, 0.0f); s[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int mid = T.matID;
+    tri_class[i] = (mid >= 0 && mid < n_mats && mats[mid].is_specular != 0) ? 1 : 0;
+}
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+    T* release() { T* q = p; p = nullptr; return q; }
+};
+
+} // namespace
+
+void GpuBvh::free_all()
+{
+    cudaFree(pairs); cudaFree(tris); cudaFree(leaf_boxes); cudaFree(shade); cudaFree(tri_class); cudaFree(nodes);
+    pairs = tris = leaf_boxes = shade = nullptr; tri_class = nullptr; nodes = nullptr; n_nodes = n_inner = n_leaves = n_tris = 0;
+}
+
+bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err)
+{
+    out.free_all();
+    if (n < 1) { err = "no triangles"; return false; }
+    if (n >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
+    if (leaf_max < 1) leaf_max = 2;
+    if (leaf_max > 10) leaf_max = 10;                         // vert_list holds 10 indices (include/CL_headers.h:88)
+    const int B = 256;
+    auto grid = [&](long long m) { return (unsigned)((m + B - 1) / B); };
+    cudaEvent_t e0, e1; YB_CUDA(cudaEventCreate(&e0)); YB_CUDA(cudaEventCreate(&e1));
+
+    DevBuf<yune_triangle> d_tris; YB_CUDA(d_tris.alloc(n));
+    YB_CUDA(cudaMemcpyAsync(d_tris.p, h_tris, (size_t)n * sizeof(yune_triangle), cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaEventRecord(e0, st));
+    DevBuf<Box> tri_exact, tri_padded, exact, padded;
+    YB_CUDA(tri_exact.alloc(n)); YB_CUDA(tri_padded.alloc(n)); YB_CUDA(exact.alloc(2 * (size_t)n)); YB_CUDA(padded.alloc(2 * (size_t)n));
+    DevBuf<float> scene; YB_CUDA(scene.alloc(6));
+    const float init[6] = {3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+    YB_CUDA(cudaMemcpyAsync(scene.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    k_tri_boxes<<<grid(n), B, 0, st>>>(d_tris.p, n, tri_exact.p, tri_padded.p, scene.p, scene.p + 3);
+    DevBuf<unsigned long long> keys, keys_sorted; DevBuf<int> idx, sorted_tri;
+    YB_CUDA(keys.alloc(n)); YB_CUDA(keys_sorted.alloc(n)); YB_CUDA(idx.alloc(n)); YB_CUDA(sorted_tri.alloc(n));
+    k_morton<<<grid(n), B, 0, st>>>(tri_exact.p, d_tris.p, n, scene.p, scene.p + 3, keys.p, idx.p);
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    YB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, idx.p, sorted_tri.p, n, 0, 63, st));
+    YB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, 2 * n, st));
+    DevBuf<unsigned char> tmp; YB_CUDA(tmp.alloc(tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes));
+    size_t tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
+    YB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, idx.p, sorted_tri.p, n, 0, 63, st));
+
+    DevBuf<int2> child, range; DevBuf<int> parent_inner, parent_leaf, arrived;
+    YB_CUDA(child.alloc(n)); YB_CUDA(range.alloc(n)); YB_CUDA(parent_inner.alloc(n)); YB_CUDA(parent_leaf.alloc(n)); YB_CUDA(arrived.alloc(n));
+    YB_CUDA(cudaMemsetAsync(arrived.p, 0, (size_t)n * sizeof(int), st));
+    if (n > 1) k_hierarchy<<<grid(n - 1), B, 0, st>>>(keys_sorted.p, n, child.p, range.p, parent_inner.p, parent_leaf.p);
+    k_fit<<<grid(n), B, 0, st>>>(sorted_tri.p, tri_exact.p, tri_padded.p, n, child.p, parent_inner.p, parent_leaf.p, exact.p, padded.p, arrived.p);
+
+    // breadth-first numbering
+    DevBuf<int> order, flags, rank, pair_of, first_child_bfs;
+    YB_CUDA(order.alloc(2 * (size_t)n)); YB_CUDA(flags.alloc(2 * (size_t)n)); YB_CUDA(rank.alloc(2 * (size_t)n)); YB_CUDA(pair_of.alloc(n)); YB_CUDA(first_child_bfs.alloc(2 * (size_t)n));
+    const int root = n > 1 ? 0 : ~0;
+    YB_CUDA(cudaMemcpyAsync(order.p, &root, sizeof(int), cudaMemcpyHostToDevice, st));
+    int level_begin = 0, m = 1, n_pairs = 0, depth = 0;
+    while (m > 0) {
+        k_level_flags<<<grid(m), B, 0, st>>>(order.p + level_begin, m, range.p, leaf_max, flags.p);
+        tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
+        YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, rank.p, m, st));
+        int last[2];
+        YB_CUDA(cudaMemcpyAsync(&last[0], flags.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaMemcpyAsync(&last[1], rank.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        const int n_in = last[0] + last[1];
+        k_level_expand<<<grid(m), B, 0, st>>>(order.p + level_begin, m, flags.p, rank.p, child.p, n_pairs, pair_of.p, order.p + level_begin + m);
+        k_first_child<<<grid(m), B, 0, st>>>(order.p, level_begin, m, flags.p, rank.p, level_begin + m, first_child_bfs.p);
+        n_pairs += n_in; level_begin += m; m = 2 * n_in; depth++;
+        if (depth > YUNE_STACK_SIZE - 2) { err = "the linear BVH is deeper than the traversal stack (YUNE_STACK_SIZE): build the BVH on the host"; return false; }
+    }
+    const int n_nodes = level_begin;
+    DevBuf<int> leaf_rank; YB_CUDA(leaf_rank.alloc(n_nodes));
+    k_leaf_flags<<<grid(n_nodes), B, 0, st>>>(order.p, n_nodes, range.p, leaf_max, flags.p);
+    tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
+    YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, leaf_rank.p, n_nodes, st));
+    const int n_leaves = n_nodes - n_pairs;
+
+    DevBuf<yune_bvh_node> nodes; DevBuf<float4> pairs, leaf_boxes, tri_rec, shade; DevBuf<unsigned char> tri_class;
+    YB_CUDA(nodes.alloc(n_nodes)); YB_CUDA(pairs.alloc(4 * (size_t)(n_pairs > 0 ? n_pairs : 1))); YB_CUDA(leaf_boxes.alloc(2 * (size_t)n_leaves));
+    YB_CUDA(tri_rec.alloc(3 * (size_t)n)); YB_CUDA(shade.alloc(4 * (size_t)n)); YB_CUDA(tri_class.alloc(n));
+    k_emit<<<grid(n_nodes), B, 0, st>>>(order.p, first_child_bfs.p, n_nodes, n, leaf_max, child.p, range.p, pair_of.p, leaf_rank.p, exact.p, padded.p, sorted_tri.p, d_tris.p,
+                                        nodes.p, pairs.p, leaf_boxes.p, tri_rec.p);
+    k_shade_records<<<grid(n), B, 0, st>>>(d_tris.p, n, d_mats, n_mats, shade.p, tri_class.p);
+    Box root_box;
+    YB_CUDA(cudaMemcpyAsync(&root_box, padded.p + (n > 1 ? 0 : 0), sizeof(Box), cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaEventRecord(e1, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    YB_CUDA(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+
+    out.n_tris = n; out.n_nodes = n_nodes; out.n_inner = n_pairs; out.n_leaves = n_leaves; out.depth = depth; out.build_ms = ms; out.leaf_max = leaf_max;
+    for (int k = 0; k < 3; k++) { out.root_lo[k] = root_box.lo[k]; out.root_hi[k] = root_box.hi[k]; }
+    // the root: pair record 0, or -- a scene of <= leaf_max triangles -- one leaf
+    out.root_ref = n_pairs > 0 ? 0 : ~((0 << 4) | n);
+    out.nodes = nodes.release(); out.pairs = pairs.release(); out.leaf_boxes = leaf_boxes.release(); out.tris = tri_rec.release();
+    out.shade = shade.release(); out.tri_class = tri_class.release();
+    return true;
+}
+
+} // namespace yune

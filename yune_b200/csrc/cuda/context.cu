@@ -6,6 +6,7 @@
 #include "yune_cuda.h"
 #include "kernels.h"
 #include "trav_layout.h"
+#include "bvh_build.h"
 
 #include <algorithm>
 #include <cmath>
@@ -58,6 +59,7 @@ struct yune_ctx {
     unsigned char* d_tri_class = nullptr;      // per original triangle: 1 = its material is specular (shade-stage sorting key)
     bool class_dirty = true;
     DevScene sc{};
+    GpuBvh gpu_bvh; bool bvh_on_device = false;      // yune_build_bvh_on_device: the layout arrays below are the builder's (h_nodes is filled on demand)
     yune_cam cam{};
 
     int integrator = INTEGRATOR_NONE; int mis = 0; bool postproc = false;
@@ -173,8 +175,10 @@ static int ensure_scene(yune_ctx* c)
             if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
         std::vector<unsigned char> cls(std::max<size_t>(c->h_tris.size(), 1), 0);
         for (size_t i = 0; i < c->h_tris.size(); i++) cls[i] = c->h_mats[c->h_tris[i].matID].is_specular != 0 ? 1 : 0;
+        if (c->bvh_on_device) { if (c->gpu_bvh.tri_class) cudaFree(c->gpu_bvh.tri_class); c->gpu_bvh.tri_class = nullptr; c->d_tri_class = nullptr; }
         dfree(c->d_tri_class);
         Y_CUDA(c, cudaMalloc(&c->d_tri_class, cls.size()));
+        if (c->bvh_on_device) c->gpu_bvh.tri_class = c->d_tri_class;
         Y_CUDA(c, cudaMemcpyAsync(c->d_tri_class, cls.data(), cls.size(), cudaMemcpyHostToDevice, c->stream));
         Y_CUDA(c, cudaStreamSynchronize(c->stream));
         c->sc.tri_class = c->d_tri_class;
@@ -182,6 +186,15 @@ static int ensure_scene(yune_ctx* c)
     }
     if (!c->layout_dirty) return YUNE_OK;
     std::string err;
+    if (c->bvh_on_device) {
+        // an option that changes the layout (accel, leaf_split, isect) was set after the device build: the host re-layout takes
+        // over from the device-built tree, which is a valid reference-format array like any other
+        c->h_nodes.resize((size_t)c->gpu_bvh.n_nodes);
+        Y_CUDA(c, cudaMemcpy(c->h_nodes.data(), c->gpu_bvh.nodes, c->h_nodes.size() * sizeof(yune_bvh_node), cudaMemcpyDeviceToHost));
+        c->gpu_bvh.free_all(); c->bvh_on_device = false;
+        c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr; c->class_dirty = true;
+        return ensure_scene(c);
+    }
     if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
@@ -204,6 +217,17 @@ static int ensure_scene(yune_ctx* c)
     for (int k = 0; k < 3; k++) { s.root_lo[k] = L.root_lo[k]; s.root_hi[k] = L.root_hi[k]; }
     c->layout_dirty = false;
     return YUNE_OK;
+}
+
+// new geometry / a new uploaded tree: the device-built one (and the layout arrays it owns) goes
+static void drop_device_bvh(yune_ctx* c)
+{
+    if (!c->bvh_on_device) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->gpu_bvh.free_all(); c->bvh_on_device = false;
+    c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr;
+    c->class_dirty = true; c->have_nodes = false;
 }
 
 struct TraceLaunch { int grid, block; size_t smem; };
@@ -289,6 +313,7 @@ void yune_destroy(yune_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_pool(c);
+    if (c->bvh_on_device) { c->gpu_bvh.free_all(); c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr; }
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
     dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_fix); dfree(c->d_ctr); dfree(c->d_tot);
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
@@ -340,6 +365,7 @@ int yune_setup_vertex_buffer(yune_ctx* c, const yune_triangle* tris, int n)
     if (!c || n < 0 || (n > 0 && !tris)) { if (c) c->err = "yune_setup_vertex_buffer: bad arguments"; return YUNE_ERR_INVALID; }
     c->epoch++;
     c->h_tris.assign(tris, tris + n);
+    drop_device_bvh(c);
     c->have_tris = true; c->layout_dirty = true;
     return YUNE_OK;
 }
@@ -365,6 +391,7 @@ int yune_setup_bvh_buffer(yune_ctx* c, const yune_bvh_node* nodes, int n)
     c->epoch++;
     // n == 0: the reference's brute-force mode (kernel arg 6 bvh_size == 0, udpt.cl:280-284) -- same hits, see relayout.cpp
     if (n > 0) c->h_nodes.assign(nodes, nodes + n); else c->h_nodes.clear();
+    drop_device_bvh(c);
     c->have_nodes = true; c->layout_dirty = true;
     return YUNE_OK;
 }
@@ -460,6 +487,61 @@ int yune_get_option(yune_ctx* c, const char* key, double* value)
     int* p = option_slot(c, key);
     if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
     *value = *p;
+    return YUNE_OK;
+}
+
+// ---- BVH construction on the device (bvh_build.cu) ----
+int yune_build_bvh_on_device(yune_ctx* c, int leaf_max)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->have_tris || c->h_tris.empty()) Y_FAIL(c, YUNE_ERR_STATE, "yune_build_bvh_on_device: set up the vertex buffer first");
+    if (!c->have_mats) Y_FAIL(c, YUNE_ERR_STATE, "yune_build_bvh_on_device: set up the material buffer first");
+    if (c->opt_accel != 1 || c->opt_isect != 0) Y_FAIL(c, YUNE_ERR_STATE, "yune_build_bvh_on_device emits the layout of accel 1 / isect 0 (the defaults); set those options back first");
+    for (const yune_triangle& t : c->h_tris)
+        if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
+    Y_CUDA(c, cudaSetDevice(c->device));
+    Y_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->epoch++;
+    drop_device_bvh(c);
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
+    std::string err;
+    if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err)) {
+        c->gpu_bvh.free_all();
+        Y_FAIL(c, YUNE_ERR_LIMIT, "device BVH build failed: %s", err.c_str());
+    }
+    const GpuBvh& G = c->gpu_bvh;
+    c->bvh_on_device = true; c->h_nodes.clear();
+    c->d_pairs = G.pairs; c->d_tris = G.tris; c->d_shade = G.shade; c->d_leaf_boxes = G.leaf_boxes; c->d_tri_class = G.tri_class;
+    DevScene& s = c->sc;
+    s.pairs = G.pairs; s.tris = G.tris; s.shade = G.shade; s.mats = c->d_mats; s.leaf_boxes = G.leaf_boxes; s.tri_class = G.tri_class;
+    s.accel = 1; s.isect = 0; s.n_inner = G.n_inner; s.n_tris = G.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = G.root_ref;
+    for (int k = 0; k < 3; k++) { s.root_lo[k] = G.root_lo[k]; s.root_hi[k] = G.root_hi[k]; }
+    c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
+    c->have_nodes = true; c->layout_dirty = false; c->class_dirty = false;
+    return YUNE_OK;
+}
+
+int yune_bvh_info(yune_ctx* c, int* n_nodes, int* n_inner, int* depth, float* build_ms)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->have_nodes) Y_FAIL(c, YUNE_ERR_STATE, "no BVH has been set up or built");
+    if (n_nodes) *n_nodes = c->bvh_on_device ? c->gpu_bvh.n_nodes : (int)c->h_nodes.size();
+    if (n_inner) *n_inner = c->bvh_on_device ? c->gpu_bvh.n_inner : c->lay.n_inner;
+    if (depth) *depth = c->bvh_on_device ? c->gpu_bvh.depth : c->lay.max_depth;
+    if (build_ms) *build_ms = c->bvh_on_device ? c->gpu_bvh.build_ms : 0.0f;
+    return YUNE_OK;
+}
+
+int yune_read_bvh_buffer(yune_ctx* c, yune_bvh_node* nodes, int capacity)
+{
+    if (!c) return YUNE_ERR_INVALID;
+    if (!c->have_nodes) Y_FAIL(c, YUNE_ERR_STATE, "no BVH has been set up or built");
+    const int n = c->bvh_on_device ? c->gpu_bvh.n_nodes : (int)c->h_nodes.size();
+    if (!nodes || capacity < n) Y_FAIL(c, YUNE_ERR_INVALID, "yune_read_bvh_buffer: the array holds %d nodes, capacity %d", n, capacity);
+    if (c->bvh_on_device) {
+        Y_CUDA(c, cudaSetDevice(c->device));
+        Y_CUDA(c, cudaMemcpy(nodes, c->gpu_bvh.nodes, (size_t)n * sizeof(yune_bvh_node), cudaMemcpyDeviceToHost));
+    } else if (n > 0) std::memcpy(nodes, c->h_nodes.data(), (size_t)n * sizeof(yune_bvh_node));
     return YUNE_OK;
 }
 

@@ -427,12 +427,17 @@ def run_ours(args, cfg):
     bytes_per_launch = ext_per_launch * work["extend"]["bytes"] + sh_per_launch * work["shadow"]["bytes"]
     achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
     resident = cfg["scene"] != "c4"
-    traffic = prof.get("dram_bytes_per_launch") if prof.get("pool_slots", pool_in_use) == pool_in_use else None      # same pool size = same kind of launch
+    traffic, traffic_how = None, None
+    if prof.get("dram_bytes_per_launch") and prof.get("pool_slots", pool_in_use) == pool_in_use:      # same pool size = same kind of launch
+        traffic, traffic_how = prof["dram_bytes_per_launch"], "DRAM bytes of the captured steady-state launch (same pool size)"
+    elif prof.get("dram_bytes_per_ray"):      # captured at another pool size: the per-ray figure (node / triangle / queue sectors of one ray) times this launch's rays
+        traffic = prof["dram_bytes_per_ray"] * (ext_per_launch + sh_per_launch)
+        traffic_how = "captured launch's DRAM bytes per ray (%.0f B, pool of %d slots) x the live rays per launch" % (prof["dram_bytes_per_ray"], prof.get("pool_slots", 0))
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "hbm_frac_measured": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic and avg_launch_ms > 0 else None, "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "bytes_per_launch": bytes_per_launch,
                 "launches": which, "rays_per_launch": {"extend": ext_per_launch, "shadow": sh_per_launch}, "work_model": work,
-                "traffic_source": prof.get("source"),
+                "traffic_source": prof.get("source"), "traffic_how": traffic_how,
                 "trace_share_of_step": agg["trace_ms"] / max(agg["trace_ms"] + agg["shade_ms"], 1e-9),
                 "note": ("the scene (<= 0.9 MB) is resident in shared memory / L1 / L2: achieved is the EFFECTIVE bandwidth of the work model "
                          "(oracle's ordered walk of the reference BVH), it exceeds the HBM peak by construction and is not a physical fraction; "

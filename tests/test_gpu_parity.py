@@ -1035,3 +1035,42 @@ def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene,
         m.check(r._lib.yune_render(r._ctx, 0, 16, 1, r.seed, 1)); img_host = r.readSum()
         assert abs(luminance(img_dev).mean() / luminance(img_host).mean() - 1) < 2e-3
         assert (img_dev == img_host).all(-1).mean() > 0.99
+
+
+@pytest.mark.parametrize("scene", ["teapot", "cornellbox", "uniform", "flats", "mixed"])
+def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager, oracle, scene):
+    """Option "device_layout" = 1 (default from 2^20 triangles: C4): the walk's own tree for an UPLOADED BVH is built by the device
+    builder instead of the host's binned-SAH builder.  The uploaded tree still decides every hit -- triangle records carry ITS
+    leaves and visiting ranks, the filter tests ITS boxes: hit records bit-identical to the oracle's walk of the uploaded tree,
+    and a render is bit for bit the render with the host-built own tree."""
+    from tests.helpers import random_soup, soup_rays
+    m = gpu_manager
+    rng = np.random.default_rng(71)
+    if scene in ("teapot", "cornellbox"):
+        sc = golden_scene_object(scene, transmissive_teapot=(scene == "teapot"))
+        n = 200000
+        o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1)
+        d = rng.normal(size=(n, 3)); d[:1000, 0] = 0; d[1000:2000, 1] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        od = np.concatenate([o, d], 1).astype(np.float32); tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
+    else:
+        T = random_soup(rng, 2500, scene)
+        sc = yb.Scene().setGeometry(T, load_golden_scene("cornellbox")[1])
+        od, tm = soup_rays(rng, T, 60000)
+    r = yb.RendererCore(m, 64, 64)
+    assert m.createRenderProgram("udpt.cl", compiler_opts="-DMIS"), m.last_message
+    try:
+        assert r.setup(sc), m.last_message
+        r.seed = 17
+        m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); img_host = r.readSum()
+        m.setOption("device_layout", 1)
+        cfg = Oracle.config("udpt")
+        tri, light, t = r.traceRays(od)
+        otri, olight, ot = oracle.trace(cfg, od, None, 0, sc.vert_data, sc.bvh)
+        assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all()
+        atri, alight, _ = r.traceRays(od, tm, any_hit=True)
+        stri, slight, _ = oracle.trace(cfg, od, tm, 1, sc.vert_data, sc.bvh)
+        assert (((stri >= 0) | (slight >= 0)) == (atri >= 0)).all()
+        m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1))
+        np.testing.assert_array_equal(r.readSum(), img_host)
+    finally:
+        m.setOption("device_layout", -1)

@@ -47,10 +47,14 @@ if with_host:
     t0 = time.time()
     sc = yb.Scene().setGeometry(T, mats)
     t1 = time.time()
-    assert r.setup(sc), m.last_message
-    m.check(r._lib.yune_render(r._ctx, 0, 1, 1, 1, 1))
-    t2 = time.time()
-    render("host")
-    res["host"].update(m.bvhInfo()); res["host"]["bvh_build_s"] = t1 - t0; res["host"]["scene_to_first_sample_s"] = t2 - t0
+    for tag, dl in (("host_tree_device_layout", 1), ("host", 0)):      # the reference builder's tree uploaded; own tree built on the device / on the host
+        m.setOption("device_layout", dl)
+        t1b = time.time()
+        assert r.setup(sc), m.last_message
+        m.check(r._lib.yune_render(r._ctx, 0, 1, 1, 1, 1))
+        t2 = time.time()
+        render(tag)
+        res[tag].update(m.bvhInfo()); res[tag]["bvh_build_s"] = t1 - t0; res[tag]["upload_to_first_sample_s"] = t2 - t1b; res[tag]["scene_to_first_sample_s"] = (t1 - t0) + (t2 - t1b)
+        print(json.dumps(res), flush=True)
 print(json.dumps(res))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r2_c4_device_bvh.json"), "w"), indent=1)

@@ -182,7 +182,7 @@ __global__ void k_leaf_flags(const int* order, int n_nodes, const int2* range, i
 __device__ __forceinline__ float4 f4i(float x, float y, float z, int w) { return make_float4(x, y, z, __int_as_float(w)); }
 __global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes, int n, int leaf_max, const int2* child, const int2* range, const int* pair_of,
                        const int* leaf_rank, const Box* exact, const Box* padded, const int* sorted_tri, const yune_triangle* tris,
-                       yune_bvh_node* nodes, float4* pairs, float4* leaf_boxes, float4* tri_rec)
+                       yune_bvh_node* nodes, float4* pairs, float4* leaf_boxes, float4* tri_rec, const int* ref_leaf_of_tri, const int* ref_rank_of_tri)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_nodes) return;
@@ -212,8 +212,10 @@ __global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes
         const int first = ref >= 0 ? range[ref].x : ~ref, cnt = ref >= 0 ? range[ref].y - range[ref].x + 1 : 1;
         const int lr = leaf_rank[b];
         nd.child_idx = -1; nd.vert_len = cnt;
-        leaf_boxes[2 * (size_t)lr] = make_float4(e.lo[0], e.lo[1], e.lo[2], 0.0f);
-        leaf_boxes[2 * (size_t)lr + 1] = make_float4(e.hi[0], e.hi[1], e.hi[2], 0.0f);
+        if (!ref_leaf_of_tri) {
+            leaf_boxes[2 * (size_t)lr] = make_float4(e.lo[0], e.lo[1], e.lo[2], 0.0f);
+            leaf_boxes[2 * (size_t)lr + 1] = make_float4(e.hi[0], e.hi[1], e.hi[2], 0.0f);
+        }
         for (int j = 0; j < cnt; j++) {
             const int t = sorted_tri[first + j];
             nd.vert_list[j] = t;
@@ -223,11 +225,12 @@ __global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes
             const V3 e2 = vsub(v3(T.v3.s[0], T.v3.s[1], T.v3.s[2]), v1);
             float4* r = tri_rec + 3 * (size_t)(first + j);
             r[0] = f4i(v1.x, v1.y, v1.z, t);
-            r[1] = f4i(e1.x, e1.y, e1.z, lr * 16 + j);                        // visiting rank: leaves in breadth-first order, then the slot
-            r[2] = f4i(e2.x, e2.y, e2.z, lr);
+            // visiting rank: leaves in breadth-first order, then the slot -- of THIS tree, or of the uploaded reference tree
+            r[1] = f4i(e1.x, e1.y, e1.z, ref_leaf_of_tri ? ref_rank_of_tri[t] : lr * 16 + j);
+            r[2] = f4i(e2.x, e2.y, e2.z, ref_leaf_of_tri ? ref_leaf_of_tri[t] : lr);
         }
     }
-    nodes[b] = nd;
+    if (nodes) nodes[b] = nd;
 }
 // the breadth-first index of an inner node's first child = where its two frontier slots landed
 __global__ void k_first_child(const int* order, int level_begin, int m, const int* flags, const int* rank, int next_begin, int* first_child_bfs)
@@ -266,7 +269,7 @@ void GpuBvh::free_all()
     pairs = tris = leaf_boxes = shade = nullptr; tri_class = nullptr; nodes = nullptr; n_nodes = n_inner = n_leaves = n_tris = 0;
 }
 
-bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err)
+bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err, const RefLeaves* ref)
 {
     out.free_all();
     if (n < 1) { err = "no triangles"; return false; }
@@ -329,11 +332,18 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, leaf_rank.p, n_nodes, st));
     const int n_leaves = n_nodes - n_pairs;
 
-    DevBuf<yune_bvh_node> nodes; DevBuf<float4> pairs, leaf_boxes, tri_rec, shade; DevBuf<unsigned char> tri_class;
-    YB_CUDA(nodes.alloc(n_nodes)); YB_CUDA(pairs.alloc(4 * (size_t)(n_pairs > 0 ? n_pairs : 1))); YB_CUDA(leaf_boxes.alloc(2 * (size_t)n_leaves));
+    DevBuf<yune_bvh_node> nodes; DevBuf<float4> pairs, leaf_boxes, tri_rec, shade; DevBuf<unsigned char> tri_class; DevBuf<int> ref_leaf, ref_rank;
+    if (!ref) YB_CUDA(nodes.alloc(n_nodes));
+    YB_CUDA(pairs.alloc(4 * (size_t)(n_pairs > 0 ? n_pairs : 1))); YB_CUDA(leaf_boxes.alloc(2 * (size_t)(ref ? ref->n_leaves : n_leaves)));
     YB_CUDA(tri_rec.alloc(3 * (size_t)n)); YB_CUDA(shade.alloc(4 * (size_t)n)); YB_CUDA(tri_class.alloc(n));
+    if (ref) {
+        YB_CUDA(ref_leaf.alloc(n)); YB_CUDA(ref_rank.alloc(n));
+        YB_CUDA(cudaMemcpyAsync(ref_leaf.p, ref->leaf_of_tri, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        YB_CUDA(cudaMemcpyAsync(ref_rank.p, ref->rank_of_tri, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+        YB_CUDA(cudaMemcpyAsync(leaf_boxes.p, ref->leaf_boxes, 2 * (size_t)ref->n_leaves * sizeof(float4), cudaMemcpyHostToDevice, st));
+    }
     k_emit<<<grid(n_nodes), B, 0, st>>>(order.p, first_child_bfs.p, n_nodes, n, leaf_max, child.p, range.p, pair_of.p, leaf_rank.p, exact.p, padded.p, sorted_tri.p, d_tris.p,
-                                        nodes.p, pairs.p, leaf_boxes.p, tri_rec.p);
+                                        nodes.p, pairs.p, leaf_boxes.p, tri_rec.p, ref ? ref_leaf.p : nullptr, ref ? ref_rank.p : nullptr);
     k_shade_records<<<grid(n), B, 0, st>>>(d_tris.p, n, d_mats, n_mats, shade.p, tri_class.p);
     Box root_box;
     YB_CUDA(cudaMemcpyAsync(&root_box, padded.p + (n > 1 ? 0 : 0), sizeof(Box), cudaMemcpyDeviceToHost, st));
@@ -342,7 +352,7 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     YB_CUDA(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
 
-    out.n_tris = n; out.n_nodes = n_nodes; out.n_inner = n_pairs; out.n_leaves = n_leaves; out.depth = depth; out.build_ms = ms; out.leaf_max = leaf_max;
+    out.n_tris = n; out.n_nodes = ref ? 0 : n_nodes; out.n_inner = n_pairs; out.n_leaves = ref ? ref->n_leaves : n_leaves; out.depth = depth; out.build_ms = ms; out.leaf_max = leaf_max;
     for (int k = 0; k < 3; k++) { out.root_lo[k] = root_box.lo[k]; out.root_hi[k] = root_box.hi[k]; }
     // the root: pair record 0, or -- a scene of <= leaf_max triangles -- one leaf
     out.root_ref = n_pairs > 0 ? 0 : ~((0 << 4) | n);

@@ -21,9 +21,14 @@ struct GpuBvh {
     void free_all();
 };
 
+// The leaves of an UPLOADED reference tree (host arrays, relayout.cpp: referenceLeavesForDevice).  With them the device-built tree
+// is only the walk's own tree (accel 1): triangle records carry the reference leaf / visiting rank, the leaf-box filter tests the
+// uploaded boxes, hit records are those of the uploaded tree bit for bit; no BVHNodeGPU array is emitted.
+struct RefLeaves { const int* leaf_of_tri = nullptr; const int* rank_of_tri = nullptr; const float* leaf_boxes = nullptr; int n_leaves = 0; };
+
 // h_tris: the uploaded TriangleGPU records (host); d_mats: the uploaded Material records (device).
 bool buildBvhOnDevice(const yune_triangle* h_tris, int n_tris, const yune_material* d_mats, int n_mats, int leaf_max,
-                      cudaStream_t stream, GpuBvh& out, std::string& err);
+                      cudaStream_t stream, GpuBvh& out, std::string& err, const RefLeaves* ref = nullptr);
 
 } // namespace yune
 #endif

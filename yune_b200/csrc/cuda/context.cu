@@ -93,7 +93,7 @@ struct yune_ctx {
     // carried into the next call (or yune_finish), so the pool stays full across calls instead of draining ~130 nearly empty
     // iterations per frame.  `epoch` counts everything that invalidates paths in flight (scene, camera, program, lights, image size,
     // options): a carry from another epoch is discarded.
-    int opt_pipeline = 0;
+    int opt_pipeline = 0, opt_device_layout = -1;
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
@@ -165,6 +165,18 @@ static void set_builtin_lights(yune_ctx* c)
     c->lights.l[0] = unpack_light(c->integrator == INTEGRATOR_BDPT ? kBuiltinLightBdpt : kBuiltinLightUdpt);
 }
 
+// The layout arrays a device build produced become the context's (freed like the host-built ones); `G` keeps the node array.
+static void adopt_device_layout(yune_ctx* c, GpuBvh& G)
+{
+    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
+    c->d_pairs = G.pairs; c->d_tris = G.tris; c->d_shade = G.shade; c->d_leaf_boxes = G.leaf_boxes; c->d_tri_class = G.tri_class;
+    G.pairs = G.tris = G.shade = G.leaf_boxes = nullptr; G.tri_class = nullptr;
+    DevScene& s = c->sc;
+    s.pairs = c->d_pairs; s.tris = c->d_tris; s.shade = c->d_shade; s.mats = c->d_mats; s.leaf_boxes = c->d_leaf_boxes; s.tri_class = c->d_tri_class;
+    s.accel = 1; s.isect = 0; s.n_inner = G.n_inner; s.n_tris = G.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = G.root_ref;
+    for (int k = 0; k < 3; k++) { s.root_lo[k] = G.root_lo[k]; s.root_hi[k] = G.root_hi[k]; }
+}
+
 // (re)build the traversal layout and upload it
 static int ensure_scene(yune_ctx* c)
 {
@@ -175,10 +187,8 @@ static int ensure_scene(yune_ctx* c)
             if (t.matID < 0 || t.matID >= (int)c->h_mats.size()) Y_FAIL(c, YUNE_ERR_INVALID, "triangle references material %d of %d", t.matID, (int)c->h_mats.size());
         std::vector<unsigned char> cls(std::max<size_t>(c->h_tris.size(), 1), 0);
         for (size_t i = 0; i < c->h_tris.size(); i++) cls[i] = c->h_mats[c->h_tris[i].matID].is_specular != 0 ? 1 : 0;
-        if (c->bvh_on_device) { if (c->gpu_bvh.tri_class) cudaFree(c->gpu_bvh.tri_class); c->gpu_bvh.tri_class = nullptr; c->d_tri_class = nullptr; }
         dfree(c->d_tri_class);
         Y_CUDA(c, cudaMalloc(&c->d_tri_class, cls.size()));
-        if (c->bvh_on_device) c->gpu_bvh.tri_class = c->d_tri_class;
         Y_CUDA(c, cudaMemcpyAsync(c->d_tri_class, cls.data(), cls.size(), cudaMemcpyHostToDevice, c->stream));
         Y_CUDA(c, cudaStreamSynchronize(c->stream));
         c->sc.tri_class = c->d_tri_class;
@@ -192,8 +202,28 @@ static int ensure_scene(yune_ctx* c)
         c->h_nodes.resize((size_t)c->gpu_bvh.n_nodes);
         Y_CUDA(c, cudaMemcpy(c->h_nodes.data(), c->gpu_bvh.nodes, c->h_nodes.size() * sizeof(yune_bvh_node), cudaMemcpyDeviceToHost));
         c->gpu_bvh.free_all(); c->bvh_on_device = false;
-        c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr; c->class_dirty = true;
-        return ensure_scene(c);
+    }
+    // Big uploaded scenes: the walk's OWN tree (accel 1) is built on the device (bvh_build.cu) instead of by the host's binned-SAH
+    // builder -- at 10.5 M triangles the host re-layout is 5 s of every upload.  The uploaded tree still decides every hit: the
+    // triangle records carry its leaves / visiting ranks, the leaf-box filter tests its boxes (same soundness argument, it does
+    // not depend on the own tree's topology).  Option "device_layout": -1 (default) = from 2^20 triangles, 0 = never, 1 = always.
+    if (c->opt_accel == 1 && c->opt_isect == 0 && !c->h_nodes.empty() && !c->h_tris.empty()
+        && (c->opt_device_layout == 1 || (c->opt_device_layout < 0 && c->h_tris.size() >= ((size_t)1 << 20)))) {
+        std::vector<int> leaf_of_tri, rank_of_tri; std::vector<F4> leaf_boxes; bool usable = false;
+        if (!referenceLeavesForDevice(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), leaf_of_tri, rank_of_tri, leaf_boxes, usable, err))
+            Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
+        if (usable) {
+            RefLeaves R; R.leaf_of_tri = leaf_of_tri.data(); R.rank_of_tri = rank_of_tri.data(); R.leaf_boxes = &leaf_boxes[0].x; R.n_leaves = (int)(leaf_boxes.size() / 2);
+            GpuBvh G;
+            if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), c->opt_leaf_split > 0 ? c->opt_leaf_split : 2, c->stream, G, err, &R)) {
+                G.free_all();
+                Y_FAIL(c, YUNE_ERR_LIMIT, "device layout failed: %s", err.c_str());
+            }
+            adopt_device_layout(c, G);
+            c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
+            c->layout_dirty = false; c->class_dirty = false;
+            return YUNE_OK;
+        }
     }
     if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
@@ -226,7 +256,6 @@ static void drop_device_bvh(yune_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->gpu_bvh.free_all(); c->bvh_on_device = false;
-    c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr;
     c->class_dirty = true; c->have_nodes = false;
 }
 
@@ -313,7 +342,7 @@ void yune_destroy(yune_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_pool(c);
-    if (c->bvh_on_device) { c->gpu_bvh.free_all(); c->d_pairs = c->d_tris = c->d_shade = c->d_leaf_boxes = nullptr; c->d_tri_class = nullptr; }
+    c->gpu_bvh.free_all();
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_mats); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
     dfree(c->d_sum); dfree(c->d_hdr); dfree(c->d_ldr); dfree(c->d_fix); dfree(c->d_ctr); dfree(c->d_tot);
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
@@ -446,7 +475,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -465,6 +494,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_sync_every && v < 1) Y_FAIL(c, YUNE_ERR_INVALID, "sync_every must be >= 1");
     if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
+    if (p == &c->opt_device_layout && v != *p) c->layout_dirty = true;
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_deterministic && (v != 0) != (*p != 0) && c->d_sum) {
         // switching modes carries the image over: the fixed-point buffer is (re)built from the float sums, or dropped
@@ -503,19 +533,14 @@ int yune_build_bvh_on_device(yune_ctx* c, int leaf_max)
     Y_CUDA(c, cudaStreamSynchronize(c->stream));
     c->epoch++;
     drop_device_bvh(c);
-    dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes); dfree(c->d_tri_class);
     std::string err;
     if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err)) {
         c->gpu_bvh.free_all();
         Y_FAIL(c, YUNE_ERR_LIMIT, "device BVH build failed: %s", err.c_str());
     }
-    const GpuBvh& G = c->gpu_bvh;
+    GpuBvh& G = c->gpu_bvh;
     c->bvh_on_device = true; c->h_nodes.clear();
-    c->d_pairs = G.pairs; c->d_tris = G.tris; c->d_shade = G.shade; c->d_leaf_boxes = G.leaf_boxes; c->d_tri_class = G.tri_class;
-    DevScene& s = c->sc;
-    s.pairs = G.pairs; s.tris = G.tris; s.shade = G.shade; s.mats = c->d_mats; s.leaf_boxes = G.leaf_boxes; s.tri_class = G.tri_class;
-    s.accel = 1; s.isect = 0; s.n_inner = G.n_inner; s.n_tris = G.n_tris; s.n_mats = (int)c->h_mats.size(); s.root_ref = G.root_ref;
-    for (int k = 0; k < 3; k++) { s.root_lo[k] = G.root_lo[k]; s.root_hi[k] = G.root_hi[k]; }
+    adopt_device_layout(c, G);
     c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
     c->have_nodes = true; c->layout_dirty = false; c->class_dirty = false;
     return YUNE_OK;

@@ -373,6 +373,36 @@ static bool buildOwnLayout(const yune_triangle* tris, int n_tris, const yune_bvh
 
 } // namespace
 
+// What the DEVICE layout path (bvh_build.cu) needs from an uploaded reference tree: per triangle the id of its reference leaf and
+// its visiting rank, and the leaves' uploaded boxes.  `usable` = false when the own-tree argument does not hold for this array
+// (boxes that do not nest, a triangle listed by several leaves or by none): the caller then takes the host path.
+bool referenceLeavesForDevice(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
+                              std::vector<int>& leaf_of_tri, std::vector<int>& rank_of_tri, std::vector<F4>& leaf_boxes, bool& usable, std::string& err)
+{
+    usable = false;
+    if (n_nodes <= 0 || n_tris <= 0 || !nodes || !tris) return true;
+    std::vector<int> bfs_leaves; bool nested = true;
+    if (!validateReferenceTree(nodes, n_nodes, n_tris, err, &bfs_leaves, &nested)) return false;
+    if (!nested) return true;
+    leaf_of_tri.assign((size_t)n_tris, -1); rank_of_tri.assign((size_t)n_tris, 0);
+    leaf_boxes.clear(); leaf_boxes.reserve(bfs_leaves.size() * 2);
+    int rank = 0, leaf = 0;
+    for (const int i : bfs_leaves) {
+        const yune_bvh_node& nd = nodes[i];
+        leaf_boxes.push_back({nd.aabb.p_min.s[0], nd.aabb.p_min.s[1], nd.aabb.p_min.s[2], 0.0f});
+        leaf_boxes.push_back({nd.aabb.p_max.s[0], nd.aabb.p_max.s[1], nd.aabb.p_max.s[2], 0.0f});
+        for (int j = 0; j < nd.vert_len; j++) {
+            const int id = nd.vert_list[j];
+            if (leaf_of_tri[id] >= 0) return true;                  // listed twice: slots != triangles, host path
+            leaf_of_tri[id] = leaf; rank_of_tri[id] = rank++;
+        }
+        leaf++;
+    }
+    for (int i = 0; i < n_tris; i++) if (leaf_of_tri[i] < 0) return true;      // a triangle the reference never reaches: host path keeps it out of the tree
+    usable = true;
+    return true;
+}
+
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
                      TravLayoutHost& out, std::string& err, int leaf_split, int accel, int isect)
 {

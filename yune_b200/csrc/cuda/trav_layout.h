@@ -74,5 +74,9 @@ struct TravLayoutHost {
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
                      TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0, int isect = 0);
 
+// Reference leaves of an uploaded tree in the form the device layout path (bvh_build.cu) takes them; see relayout.cpp.
+bool referenceLeavesForDevice(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
+                              std::vector<int>& leaf_of_tri, std::vector<int>& rank_of_tri, std::vector<F4>& leaf_boxes, bool& usable, std::string& err);
+
 } // namespace yune
 #endif

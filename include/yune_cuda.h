@@ -57,11 +57,11 @@ int yune_setup_mat_buffer(yune_ctx* ctx, const yune_material* mats, int n_materi
 int yune_setup_bvh_buffer(yune_ctx* ctx, const yune_bvh_node* nodes, int n_nodes);         /* args 6,7; n = 0 (nodes may be NULL): the reference's brute-force mode, udpt.cl:280-284 -- same hit records (every triangle, index order, no box test), answered by a walk over our own tree */
 /* BVH construction ON THE DEVICE, behind the same BVHNodeGPU contract (the reference builds on the host,
  * src/BVH.cpp:56-173, and at 10 M triangles that is seconds before the first sample).  Needs the vertex and material buffers;
- * replaces any uploaded BVH.  Builds a linear BVH (Morton order, Karras' parallel hierarchy) with leaves of <= leaf_max (1..10,
- * 0 = 2) triangles and emits, without leaving the GPU, both the reference-format node array (breadth-first, siblings adjacent,
+ * replaces any uploaded BVH.  Builds a BVH over the Morton-sorted triangles (option "device_builder": PLOC -- bottom-up merging by surface area --
+ * or a linear BVH with Karras' parallel hierarchy) with leaves of <= leaf_max (1..10, 0 = 2) triangles and emits, without leaving the GPU, both the reference-format node array (breadth-first, siblings adjacent,
  * nested boxes, the reference's +0.2 rule for flat boxes; yune_read_bvh_buffer hands it out) and the traversal layout of it.
  * Hit records are those of the reference's walk (udpt.cl:288-431) over THAT array, bit for bit; it is not the reference
- * builder's tree (yune_scene_load_bvh reproduces that one byte for byte) and, being an LBVH, costs more steps per ray. */
+ * builder's tree (yune_scene_load_bvh reproduces that one byte for byte). */
 int yune_build_bvh_on_device(yune_ctx* ctx, int leaf_max);
 int yune_bvh_info(yune_ctx* ctx, int* n_nodes, int* n_inner_nodes, int* depth, float* device_build_ms);
 int yune_read_bvh_buffer(yune_ctx* ctx, yune_bvh_node* nodes, int capacity);      /* the uploaded or device-built array */
@@ -86,7 +86,7 @@ int yune_set_light_sources(yune_ctx* ctx, const yune_quad_light* lights, int n_l
  *   "isect" (0 = the reference's Moller-Trumbore behind the exact leaf-box filter: hit records bit-identical to udpt.cl:326-431, default;
  *   1 = PERF MODE: watertight edge-function test on the raw vertices, no filter -- needs accel 1; differs from 0 only for rays within rounding distance
  *   of an edge, a vertex or a reference box face), "deterministic" (0/1, below), "pipeline" (0/1, see yune_finish), "device_layout" (who builds the own tree of accel 1 for an UPLOADED BVH: 0 = the host's binned-SAH builder,
- *   1 = the device builder of yune_build_bvh_on_device -- the uploaded tree still decides every hit, bit for bit -- , -1 = the device from 2^20 triangles, default), "max_iterations", "sync_every", "time_stages", "count_work".
+ *   1 = the device builder of yune_build_bvh_on_device -- the uploaded tree still decides every hit, bit for bit -- , -1 = the device from 2^20 triangles, default), "device_builder" (the device builder's algorithm: 1 = PLOC, default; 0 = linear BVH), "max_iterations", "sync_every", "time_stages", "count_work".
  *   Unknown key -> YUNE_ERR_INVALID.  None of them changes a result: tests/test_gpu_parity.py pins that. */
 int yune_set_option(yune_ctx* ctx, const char* key, double value);
 int yune_get_option(yune_ctx* ctx, const char* key, double* value);

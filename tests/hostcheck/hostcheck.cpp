@@ -391,3 +391,15 @@ extern "C" int hc_layout_accel(const yune_triangle* tris, int ntri, const yune_b
     if (!buildTravLayout(tris, ntri, nodes, nnodes, lay, err, leaf_split, accel)) return -1;
     return lay.accel;
 }
+
+// what the device layout path takes from an uploaded tree (relayout.cpp: referenceLeavesForDevice); returns -1 malformed, 0 not usable, 1 usable
+extern "C" int hc_reference_leaves(const yune_triangle* tris, int ntri, const yune_bvh_node* nodes, int nnodes, int* leaf_of_tri, int* rank_of_tri, float* leaf_boxes8, int* n_leaves)
+{
+    std::vector<int> l, r; std::vector<F4> b; bool usable = false; std::string err;
+    if (!referenceLeavesForDevice(tris, ntri, nodes, nnodes, l, r, b, usable, err)) return -1;
+    if (!usable) return 0;
+    for (int i = 0; i < ntri; i++) { leaf_of_tri[i] = l[i]; rank_of_tri[i] = r[i]; }
+    *n_leaves = (int)(b.size() / 2);
+    if (leaf_boxes8) std::memcpy(leaf_boxes8, b.data(), b.size() * sizeof(F4));
+    return 1;
+}

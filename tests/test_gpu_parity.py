@@ -970,9 +970,10 @@ def test_pipelined_frames_add_up_to_one_big_call(gpu_manager):
         m.setOption("pipeline", 0)
 
 
+@pytest.mark.parametrize("builder", [1, 0])
 @pytest.mark.parametrize("scene,leaf_max", [("teapot", 2), ("cornellbox", 1), ("uniform", 4), ("flats", 2), ("mixed", 10), ("tiny", 2)])
-def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene, leaf_max):
-    """the BVH built ON THE GPU (yune_build_bvh_on_device: Morton order + Karras hierarchy, bvh_build.cu) is handed
+def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene, leaf_max, builder):
+    """the BVH built ON THE GPU (yune_build_bvh_on_device, bvh_build.cu; builder 1 = PLOC, 0 = linear BVH) is handed
     out in the reference's BVHNodeGPU format and walked by the device from the layout emitted next to it.  Pins: (a) the downloaded
     array is a well-formed reference tree whose boxes nest (the host layout code accepts it for accel 1) and holds every triangle
     exactly once; (b) device hits == the ORACLE's reference-style walk (udpt.cl:288-431) of that downloaded array, bit for bit,
@@ -999,7 +1000,9 @@ def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene,
     assert m.createRenderProgram("udpt.cl", compiler_opts=""), m.last_message
     assert r.setup(sc), m.last_message
     host_hits = r.traceRays(od)
+    m.setOption("device_builder", builder)
     assert m.buildBVHOnDevice(leaf_max), m.last_message
+    m.setOption("device_builder", 1)
     info = m.bvhInfo()
     nodes = m.readBVHBuffer()
     tris = sc.vert_data
@@ -1037,8 +1040,9 @@ def test_bvh_built_on_device_keeps_the_node_contract(gpu_manager, oracle, scene,
         assert (img_dev == img_host).all(-1).mean() > 0.99
 
 
+@pytest.mark.parametrize("builder", [1, 0])
 @pytest.mark.parametrize("scene", ["teapot", "cornellbox", "uniform", "flats", "mixed"])
-def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager, oracle, scene):
+def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager, oracle, scene, builder):
     """Option "device_layout" = 1 (default from 2^20 triangles: C4): the walk's own tree for an UPLOADED BVH is built by the device
     builder instead of the host's binned-SAH builder.  The uploaded tree still decides every hit -- triangle records carry ITS
     leaves and visiting ranks, the filter tests ITS boxes: hit records bit-identical to the oracle's walk of the uploaded tree,
@@ -1062,7 +1066,7 @@ def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager,
         assert r.setup(sc), m.last_message
         r.seed = 17
         m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1)); img_host = r.readSum()
-        m.setOption("device_layout", 1)
+        m.setOption("device_builder", builder); m.setOption("device_layout", 1)
         cfg = Oracle.config("udpt")
         tri, light, t = r.traceRays(od)
         otri, olight, ot = oracle.trace(cfg, od, None, 0, sc.vert_data, sc.bvh)
@@ -1073,4 +1077,4 @@ def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager,
         m.check(r._lib.yune_render(r._ctx, 0, 4, 1, r.seed, 1))
         np.testing.assert_array_equal(r.readSum(), img_host)
     finally:
-        m.setOption("device_layout", -1)
+        m.setOption("device_layout", -1); m.setOption("device_builder", 1)

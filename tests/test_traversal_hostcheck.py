@@ -418,3 +418,35 @@ def test_watertight_mode_needs_the_own_tree(hc):
     for accel in (0, 2):
         assert hc.hc_trace(1, ptr(od), None, 0, ptr(tris), int(tris.size), ptr(nodes), int(nodes.size), ptr(LIGHT_UDPT), 1,
                            ptr(tri), ptr(light), ptr(t), ptr(work), 0, accel | 256) == -1
+
+
+def test_reference_leaves_for_the_device_layout(hc):
+    """relayout.cpp: referenceLeavesForDevice -- what the device layout path (option device_layout, bvh_build.cu) takes from an
+    uploaded tree: every triangle's reference leaf and visiting rank (leaves in the order of the reference's breadth-first queue,
+    slots in vert_list order) and the leaves' uploaded boxes; trees whose boxes do not nest, or that list a triangle twice or
+    not at all, are left to the host path."""
+    tris, mats, nodes = load_golden_scene("teapot")
+    n = int(tris.size)
+    leaf = np.zeros(n, np.int32); rank = np.zeros(n, np.int32); nl = C.c_int(0)
+    boxes = np.zeros((int((nodes["vert_len"] > 0).sum()), 2, 4), np.float32)
+    assert hc.hc_reference_leaves(ptr(tris), n, ptr(nodes), int(nodes.size), ptr(leaf), ptr(rank), ptr(boxes), C.byref(nl)) == 1
+    is_leaf = (nodes["child_idx"] == -1) & (nodes["vert_len"] > 0)
+    ids = np.nonzero(is_leaf)[0]                                   # reference-built: node-index order == queue order
+    assert nl.value == ids.size
+    assert np.array_equal(np.sort(rank), np.arange(n))
+    k = 0
+    for li, i in enumerate(ids):
+        for j in range(int(nodes["vert_len"][i])):
+            t = int(nodes["vert_list"][i, j])
+            assert leaf[t] == li and rank[t] == k
+            k += 1
+        assert (boxes[li, 0, :3] == nodes["p_min"][i, :3]).all() and (boxes[li, 1, :3] == nodes["p_max"][i, :3]).all()
+    # a triangle listed by two leaves / boxes that do not nest: not usable (the host path handles them)
+    twice = nodes.copy(); a, b = ids[0], ids[1]
+    twice["vert_list"][b, 0] = twice["vert_list"][a, 0]
+    assert hc.hc_reference_leaves(ptr(tris), n, ptr(twice), int(twice.size), ptr(leaf), ptr(rank), None, C.byref(nl)) == 0
+    shrunk = nodes.copy(); inner = np.nonzero(nodes["child_idx"] > 0)[0][1]
+    shrunk["p_max"][inner, :3] = shrunk["p_min"][inner, :3] + 1e-3
+    assert hc.hc_reference_leaves(ptr(tris), n, ptr(shrunk), int(shrunk.size), ptr(leaf), ptr(rank), None, C.byref(nl)) == 0
+    bad = nodes.copy(); bad["child_idx"][0] = nodes.size + 5
+    assert hc.hc_reference_leaves(ptr(tris), n, ptr(bad), int(bad.size), ptr(leaf), ptr(rank), None, C.byref(nl)) == -1

@@ -31,18 +31,20 @@ def render(tag):
     img = r.readHDR()
     res[tag]["mean_luminance"] = float((0.212671 * img[..., 0] + 0.715160 * img[..., 1] + 0.072169 * img[..., 2]).mean())
 
-# device path: vertex + material upload, build on the GPU, first sample
-t0 = time.time()
-assert m.setupVertexBuffer(T) and m.setupMatBuffer(mats) and m.setupImageBuffers(W, H)
-m.setupCameraBuffer(yb.default_camera())
-assert m.buildBVHOnDevice(leaf_max), m.last_message
-t1 = time.time()
-m.check(r._lib.yune_render(r._ctx, 0, 1, 1, 1, 1))
-t2 = time.time()
-res["device"] = None
-render("device")
-res["device"].update(m.bvhInfo()); res["device"]["build_call_s"] = t1 - t0; res["device"]["scene_to_first_sample_s"] = t2 - t0
-print(json.dumps(res), flush=True)
+# device path: vertex + material upload, build on the GPU, first sample (builder 1 = PLOC, 0 = linear BVH)
+for builder, tag in ((1, "device_ploc"), (0, "device_lbvh")):
+    m.setOption("device_builder", builder)
+    t0 = time.time()
+    assert m.setupVertexBuffer(T) and m.setupMatBuffer(mats) and m.setupImageBuffers(W, H)
+    m.setupCameraBuffer(yb.default_camera())
+    assert m.buildBVHOnDevice(leaf_max), m.last_message
+    t1 = time.time()
+    m.check(r._lib.yune_render(r._ctx, 0, 1, 1, 1, 1))
+    t2 = time.time()
+    render(tag)
+    res[tag].update(m.bvhInfo()); res[tag]["build_call_s"] = t1 - t0; res[tag]["scene_to_first_sample_s"] = t2 - t0
+    print(json.dumps(res), flush=True)
+m.setOption("device_builder", 1)
 if with_host:
     t0 = time.time()
     sc = yb.Scene().setGeometry(T, mats)

@@ -10,12 +10,12 @@
 //       src/TriangleCPU.cpp:53-70) -- yune_read_bvh_buffer hands it out, the reference's kernel or the oracle can walk it;
 //   (2) the traversal layout of trav_layout.h for that very tree (pair records breadth-first, triangle records grouped by leaf,
 //       leaf boxes, shading records, specular flags), so no host re-layout runs.
-// The tree is a linear BVH: 63-bit Morton codes of the centroids, radix sort (cub), Karras' parallel hierarchy (one thread per
-// inner node, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees", HPG 2012), boxes bottom-up with one
-// atomic per node, subtrees of <= leaf_max triangles collapsed into leaves (an LBVH subtree is a contiguous range of the sorted
-// order), breadth-first numbering level by level with a prefix sum per level.  It is NOT the reference's tree -- hit records
-// are those of a reference-style walk of THIS array (tests: device hits == the oracle's walk of the downloaded array, bit for
-// bit) -- and an LBVH is a worse tree than the SAH one (more steps per ray): the option trades render speed for start-up time.
+// Two builders over the Morton-sorted triangles (63-bit codes of the centroids, cub radix sort): builder 1 (default) = PLOC,
+// bottom-up merging of mutual nearest neighbours by union surface area (Meister & Bittner 2018); builder 0 = a linear BVH, Karras'
+// parallel hierarchy (HPG 2012) with boxes fitted bottom-up.  Then, for either: subtrees of <= leaf_max triangles collapsed into
+// leaves, breadth-first numbering level by level with a prefix sum per level, triangle records in depth-first order, one emission
+// kernel.  It is NOT the reference's tree -- hit records are those of a reference-style walk of THIS array (tests: device hits ==
+// the oracle's walk of the downloaded array, bit for bit).
 #include "kernels.h"
 #include "bvh_build.h"
 #include "strict_math.h"
@@ -97,6 +97,8 @@ __global__ void k_morton(const Box* exact_unpadded_src, const yune_triangle* tri
     keys[i] = code; idx[i] = i;
 }
 
+// ---- node numbering shared by both builders: node p < n is the triangle at sorted position p; node n + k is inner node k ----
+
 // Karras 2012.  Sorted keys may repeat: ties are broken by the position (the paper's augmented key).
 __device__ __forceinline__ int delta(const unsigned long long* keys, int n, int i, int j)
 {
@@ -104,8 +106,7 @@ __device__ __forceinline__ int delta(const unsigned long long* keys, int n, int 
     const unsigned long long a = keys[i], b = keys[j];
     return a == b ? 64 + __clz(i ^ j) : __clzll((long long)(a ^ b));
 }
-// inner nodes 0 .. n-2; a child reference >= 0 is an inner node, < 0 is ~position of a sorted triangle
-__global__ void k_hierarchy(const unsigned long long* keys, int n, int2* child, int2* range, int* parent_inner, int* parent_leaf)
+__global__ void k_hierarchy(const unsigned long long* keys, int n, int2* child, int* parent)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -121,103 +122,174 @@ __global__ void k_hierarchy(const unsigned long long* keys, int n, int2* child, 
     do { t = (t + 1) / 2; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
     const int gamma = i + s * d + min(d, 0);
     const int lo = min(i, j), hi = max(i, j);
-    const int left = lo == gamma ? ~gamma : gamma, right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
-    child[i] = make_int2(left, right); range[i] = make_int2(lo, hi);
-    if (left >= 0) parent_inner[left] = i; else parent_leaf[~left] = i;
-    if (right >= 0) parent_inner[right] = i; else parent_leaf[~right] = i;
-    if (i == 0) parent_inner[0] = -1;
+    const int left = lo == gamma ? gamma : n + gamma, right = hi == gamma + 1 ? gamma + 1 : n + gamma + 1;
+    child[n + i] = make_int2(left, right);
+    parent[left] = n + i; parent[right] = n + i;
+    if (i == 0) parent[n] = -1;
 }
 
-// boxes bottom-up: node boxes live in arrays of 2n - 1 entries, inner node i at i, sorted triangle p at n - 1 + p
-__global__ void k_fit(const int* sorted_tri, const Box* tri_exact, const Box* tri_padded, int n, const int2* child, const int* parent_inner, const int* parent_leaf,
-                      Box* exact, Box* padded, int* arrived)
+__device__ __forceinline__ Box box_union(const Box& a, const Box& b)
+{
+    Box r;
+    for (int k = 0; k < 3; k++) { r.lo[k] = fminf(a.lo[k], b.lo[k]); r.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+    return r;
+}
+__global__ void k_leaf_boxes(const int* sorted_tri, const Box* tri_exact, const Box* tri_padded, int n, Box* exact, Box* padded, int* size)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    exact[n - 1 + p] = tri_exact[sorted_tri[p]]; padded[n - 1 + p] = tri_padded[sorted_tri[p]];
-    if (n == 1) return;
-    int node = parent_leaf[p];
+    exact[p] = tri_exact[sorted_tri[p]]; padded[p] = tri_padded[sorted_tri[p]]; size[p] = 1;
+}
+// LBVH: boxes and subtree sizes bottom-up, one atomic per inner node (the second thread to arrive goes on)
+__global__ void k_fit(int n, const int2* child, const int* parent, Box* exact, Box* padded, int* size, int* arrived)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || n == 1) return;
+    int node = parent[p];
     __threadfence();
     while (node >= 0) {
-        if (atomicAdd(&arrived[node], 1) == 0) return;            // the sibling subtree is not done yet: its thread continues
+        if (atomicAdd(&arrived[node - n], 1) == 0) return;
         __threadfence();
         const int2 c = child[node];
-        const int a = c.x >= 0 ? c.x : n - 1 + ~c.x, b = c.y >= 0 ? c.y : n - 1 + ~c.y;
-        Box e, q;
-        const volatile Box* ea = exact + a; const volatile Box* eb = exact + b; const volatile Box* pa = padded + a; const volatile Box* pb = padded + b;
-        for (int k = 0; k < 3; k++) {
-            e.lo[k] = fminf(ea->lo[k], eb->lo[k]); e.hi[k] = fmaxf(ea->hi[k], eb->hi[k]);
-            q.lo[k] = fminf(pa->lo[k], pb->lo[k]); q.hi[k] = fmaxf(pa->hi[k], pb->hi[k]);
-        }
-        exact[node] = e; padded[node] = q;
+        Box ea, eb, pa, pb;
+        const volatile Box* v;
+        v = exact + c.x;  for (int k = 0; k < 3; k++) { ea.lo[k] = v->lo[k]; ea.hi[k] = v->hi[k]; }
+        v = exact + c.y;  for (int k = 0; k < 3; k++) { eb.lo[k] = v->lo[k]; eb.hi[k] = v->hi[k]; }
+        v = padded + c.x; for (int k = 0; k < 3; k++) { pa.lo[k] = v->lo[k]; pa.hi[k] = v->hi[k]; }
+        v = padded + c.y; for (int k = 0; k < 3; k++) { pb.lo[k] = v->lo[k]; pb.hi[k] = v->hi[k]; }
+        exact[node] = box_union(ea, eb); padded[node] = box_union(pa, pb);
+        size[node] = ((volatile int*)size)[c.x] + ((volatile int*)size)[c.y];
         __threadfence();
-        node = parent_inner[node];
+        node = parent[node];
     }
 }
 
-// ---- breadth-first numbering of the collapsed tree, one level per launch ----
-// `order` is the concatenation of the levels' frontiers; a frontier entry is a child reference (>= 0 inner node, < 0 ~position).
-__device__ __forceinline__ bool is_inner(int ref, const int2* range, int leaf_max) { return ref >= 0 && range[ref].y - range[ref].x + 1 > leaf_max; }
-__global__ void k_level_flags(const int* frontier, int m, const int2* range, int leaf_max, int* flags)
+// ---- PLOC (Meister & Bittner, "Parallel locally-ordered clustering for bounding volume hierarchy construction", TVCG 2018) ----
+// Bottom-up: the clusters stay in Morton order; every round each cluster looks for the neighbour within YB_PLOC_R positions whose
+// union box has the smallest surface area, mutual nearest neighbours merge into a new inner node, the array is compacted.  The
+// merge criterion is the SAH's surface area, so large triangles find each other early instead of inflating a chain of boxes the
+// way they do in a Morton-split tree.
+#define YB_PLOC_R 16
+__device__ __forceinline__ float box_area(const Box& b) { const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2]; return dx * dy + dx * dz + dy * dz; }
+__global__ void k_ploc_nearest(const int* cl, int m, const Box* exact, int* nearest)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < m) flags[k] = is_inner(frontier[k], range, leaf_max) ? 1 : 0;
+    __shared__ Box sb[256 + 2 * YB_PLOC_R];
+    const int base = blockIdx.x * 256 - YB_PLOC_R;
+    for (int t = threadIdx.x; t < 256 + 2 * YB_PLOC_R; t += 256) {
+        const int i = base + t;
+        if (i >= 0 && i < m) sb[t] = exact[cl[i]];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    const Box me = sb[threadIdx.x + YB_PLOC_R];
+    float best = 3.0e38f; int best_j = -1;
+    for (int dj = -YB_PLOC_R; dj <= YB_PLOC_R; dj++) {
+        const int j = i + dj;
+        if (dj == 0 || j < 0 || j >= m) continue;
+        const float a = box_area(box_union(me, sb[threadIdx.x + YB_PLOC_R + dj]));
+        if (a < best) { best = a; best_j = j; }          // ties: the lower position (scan order)
+    }
+    nearest[i] = best_j;
 }
-__global__ void k_level_expand(const int* frontier, int m, const int* flags, const int* rank, const int2* child, int pair_base, int* pair_of, int* next_frontier)
+__global__ void k_ploc_flags(const int* nearest, int m, int* creates, int* keeps)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nearest[i];
+    const bool mutual = j >= 0 && nearest[j] == i;
+    creates[i] = (mutual && i < j) ? 1 : 0;              // the lower partner carries the new node
+    keeps[i] = (mutual && i > j) ? 0 : 1;                // the upper partner leaves the array
+}
+__global__ void k_ploc_merge(const int* cl, const int* nearest, int m, const int* creates, const int* create_rank, const int* keeps, const int* keep_rank,
+                             int next_node, int2* child, Box* exact, Box* padded, int* size, int* cl_next)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || !keeps[i]) return;
+    int id = cl[i];
+    if (creates[i]) {
+        const int a = cl[i], b = cl[nearest[i]];
+        id = next_node + create_rank[i];
+        child[id] = make_int2(a, b);
+        exact[id] = box_union(exact[a], exact[b]); padded[id] = box_union(padded[a], padded[b]);
+        size[id] = size[a] + size[b];
+    }
+    cl_next[keep_rank[i]] = id;
+}
+
+// ---- breadth-first numbering of the collapsed tree, one level per launch ----
+// `order` is the concatenation of the levels' frontiers (node ids).  A node is INNER when it holds more than leaf_max triangles;
+// everything else -- a single triangle or a small subtree -- is a leaf.  `tfirst` = where a node's triangles start in the
+// triangle-record array: depth-first order (left subtree first), so that a subtree's triangles are contiguous and neighbours in
+// space are neighbours in memory.
+__device__ __forceinline__ bool is_inner(int node, int n, const int* size, int leaf_max) { return node >= n && size[node] > leaf_max; }
+__global__ void k_level_flags(const int* frontier, int m, int n, const int* size, int leaf_max, int* flags)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m || !flags[k]) return;
+    if (k < m) flags[k] = is_inner(frontier[k], n, size, leaf_max) ? 1 : 0;
+}
+__global__ void k_level_expand(const int* frontier, int m, const int* flags, const int* rank, const int2* child, const int* size, int n, int pair_base, int* pair_of, int* tfirst,
+                               int* next_frontier, int level_begin, int next_begin, int* first_child_bfs)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    first_child_bfs[level_begin + k] = flags[k] ? next_begin + 2 * rank[k] : -1;
+    if (!flags[k]) return;
     const int node = frontier[k];
-    pair_of[node] = pair_base + rank[k];
+    pair_of[node - n] = pair_base + rank[k];
     const int2 c = child[node];
+    tfirst[c.x] = tfirst[node]; tfirst[c.y] = tfirst[node] + size[c.x];
     next_frontier[2 * rank[k]] = c.x; next_frontier[2 * rank[k] + 1] = c.y;
 }
-__global__ void k_leaf_flags(const int* order, int n_nodes, const int2* range, int leaf_max, int* flags)
+__global__ void k_leaf_flags(const int* order, int n_nodes, int n, const int* size, int leaf_max, int* flags)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_nodes) flags[b] = is_inner(order[b], range, leaf_max) ? 0 : 1;
+    if (b < n_nodes) flags[b] = is_inner(order[b], n, size, leaf_max) ? 0 : 1;
 }
 
 // ---- emission: BVHNodeGPU records, pair records, leaf boxes, triangle records ----
 __device__ __forceinline__ float4 f4i(float x, float y, float z, int w) { return make_float4(x, y, z, __int_as_float(w)); }
-__global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes, int n, int leaf_max, const int2* child, const int2* range, const int* pair_of,
+__global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes, int n, int leaf_max, const int2* child, const int* size, const int* tfirst, const int* pair_of,
                        const int* leaf_rank, const Box* exact, const Box* padded, const int* sorted_tri, const yune_triangle* tris,
                        yune_bvh_node* nodes, float4* pairs, float4* leaf_boxes, float4* tri_rec, const int* ref_leaf_of_tri, const int* ref_rank_of_tri)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_nodes) return;
-    const int ref = order[b];
-    const int bi = ref >= 0 ? ref : n - 1 + ~ref;
-    const Box e = exact[bi];
+    const int node = order[b];
+    const Box e = exact[node];
     yune_bvh_node nd;
     for (int k = 0; k < 3; k++) { nd.aabb.p_min.s[k] = e.lo[k]; nd.aabb.p_max.s[k] = e.hi[k]; }
     nd.aabb.p_min.s[3] = 1.0f; nd.aabb.p_max.s[3] = 1.0f;
     for (int j = 0; j < 10; j++) nd.vert_list[j] = 0;
-    if (is_inner(ref, range, leaf_max)) {
+    if (is_inner(node, n, size, leaf_max)) {
         nd.child_idx = first_child_bfs[b]; nd.vert_len = -1;
-        const int2 c = child[ref];
+        const int2 c = child[node];
         int refs[2]; Box pb[2];
         for (int s = 0; s < 2; s++) {
-            const int cr = s ? c.y : c.x;
-            pb[s] = padded[cr >= 0 ? cr : n - 1 + ~cr];
-            if (is_inner(cr, range, leaf_max)) refs[s] = pair_of[cr];
-            else { const int first = cr >= 0 ? range[cr].x : ~cr, cnt = cr >= 0 ? range[cr].y - range[cr].x + 1 : 1; refs[s] = ~((first << 4) | cnt); }
+            const int cn = s ? c.y : c.x;
+            pb[s] = padded[cn];
+            refs[s] = is_inner(cn, n, size, leaf_max) ? pair_of[cn - n] : ~((tfirst[cn] << 4) | size[cn]);
         }
-        float4* q = pairs + 4 * (size_t)pair_of[ref];
+        float4* q = pairs + 4 * (size_t)pair_of[node - n];
         q[0] = make_float4(pb[0].lo[0], pb[0].hi[0], pb[0].lo[1], pb[0].hi[1]);
         q[1] = make_float4(pb[1].lo[0], pb[1].hi[0], pb[1].lo[1], pb[1].hi[1]);
         q[2] = make_float4(pb[0].lo[2], pb[0].hi[2], pb[1].lo[2], pb[1].hi[2]);
         q[3] = make_float4(__int_as_float(refs[0]), __int_as_float(refs[1]), 0.0f, 0.0f);
     } else {
-        const int first = ref >= 0 ? range[ref].x : ~ref, cnt = ref >= 0 ? range[ref].y - range[ref].x + 1 : 1;
+        const int first = tfirst[node], cnt = size[node];
         const int lr = leaf_rank[b];
         nd.child_idx = -1; nd.vert_len = cnt;
         if (!ref_leaf_of_tri) {
             leaf_boxes[2 * (size_t)lr] = make_float4(e.lo[0], e.lo[1], e.lo[2], 0.0f);
             leaf_boxes[2 * (size_t)lr + 1] = make_float4(e.hi[0], e.hi[1], e.hi[2], 0.0f);
         }
-        for (int j = 0; j < cnt; j++) {
-            const int t = sorted_tri[first + j];
+        // the leaf's triangles: depth-first over its (<= leaf_max <= 10 triangles) subtree, left to right
+        int stack[12]; int sp = 0, j = 0;
+        stack[sp++] = node;
+        while (sp > 0) {
+            const int x = stack[--sp];
+            if (x >= n) { const int2 c = child[x]; stack[sp++] = c.y; stack[sp++] = c.x; continue; }
+            const int t = sorted_tri[x];
             nd.vert_list[j] = t;
             const yune_triangle& T = tris[t];
             const V3 v1 = v3(T.v1.s[0], T.v1.s[1], T.v1.s[2]);
@@ -228,16 +300,13 @@ __global__ void k_emit(const int* order, const int* first_child_bfs, int n_nodes
             // visiting rank: leaves in breadth-first order, then the slot -- of THIS tree, or of the uploaded reference tree
             r[1] = f4i(e1.x, e1.y, e1.z, ref_leaf_of_tri ? ref_rank_of_tri[t] : lr * 16 + j);
             r[2] = f4i(e2.x, e2.y, e2.z, ref_leaf_of_tri ? ref_leaf_of_tri[t] : lr);
+            j++;
         }
     }
     if (nodes) nodes[b] = nd;
 }
-// the breadth-first index of an inner node's first child = where its two frontier slots landed
-__global__ void k_first_child(const int* order, int level_begin, int m, const int* flags, const int* rank, int next_begin, int* first_child_bfs)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < m) first_child_bfs[level_begin + k] = flags[k] ? next_begin + 2 * rank[k] : -1;
-}
+
+__global__ void k_iota(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
 
 // shading records and specular flags by ORIGINAL triangle index (relayout.cpp: shade_records; context.cu: tri_class)
 __global__ void k_shade_records(const yune_triangle* tris, int n, const yune_material* mats, int n_mats, float4* shade, unsigned char* tri_class)
@@ -269,7 +338,7 @@ void GpuBvh::free_all()
     pairs = tris = leaf_boxes = shade = nullptr; tri_class = nullptr; nodes = nullptr; n_nodes = n_inner = n_leaves = n_tris = 0;
 }
 
-bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err, const RefLeaves* ref)
+bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err, const RefLeaves* ref, int builder)
 {
     out.free_all();
     if (n < 1) { err = "no triangles"; return false; }
@@ -295,41 +364,75 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     size_t tmp_bytes = 0, scan_bytes = 0;
     YB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, idx.p, sorted_tri.p, n, 0, 63, st));
     YB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, 2 * n, st));
-    DevBuf<unsigned char> tmp; YB_CUDA(tmp.alloc(tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes));
-    size_t tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
+    const size_t tmp_cap = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
+    DevBuf<unsigned char> tmp; YB_CUDA(tmp.alloc(tmp_cap));
+    size_t tb = tmp_cap;
     YB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, idx.p, sorted_tri.p, n, 0, 63, st));
 
-    DevBuf<int2> child, range; DevBuf<int> parent_inner, parent_leaf, arrived;
-    YB_CUDA(child.alloc(n)); YB_CUDA(range.alloc(n)); YB_CUDA(parent_inner.alloc(n)); YB_CUDA(parent_leaf.alloc(n)); YB_CUDA(arrived.alloc(n));
-    YB_CUDA(cudaMemsetAsync(arrived.p, 0, (size_t)n * sizeof(int), st));
-    if (n > 1) k_hierarchy<<<grid(n - 1), B, 0, st>>>(keys_sorted.p, n, child.p, range.p, parent_inner.p, parent_leaf.p);
-    k_fit<<<grid(n), B, 0, st>>>(sorted_tri.p, tri_exact.p, tri_padded.p, n, child.p, parent_inner.p, parent_leaf.p, exact.p, padded.p, arrived.p);
+    // ---- hierarchy over the sorted triangles: nodes [0, n) = triangles, [n, 2n - 1) = inner nodes ----
+    DevBuf<int2> child; DevBuf<int> size, parent, arrived;
+    YB_CUDA(child.alloc(2 * (size_t)n)); YB_CUDA(size.alloc(2 * (size_t)n));
+    k_leaf_boxes<<<grid(n), B, 0, st>>>(sorted_tri.p, tri_exact.p, tri_padded.p, n, exact.p, padded.p, size.p);
+    int root = 0, rounds = 0;
+    if (n > 1 && builder == 0) {
+        YB_CUDA(parent.alloc(2 * (size_t)n)); YB_CUDA(arrived.alloc(n));
+        YB_CUDA(cudaMemsetAsync(arrived.p, 0, (size_t)n * sizeof(int), st));
+        k_hierarchy<<<grid(n - 1), B, 0, st>>>(keys_sorted.p, n, child.p, parent.p);
+        k_fit<<<grid(n), B, 0, st>>>(n, child.p, parent.p, exact.p, padded.p, size.p, arrived.p);
+        root = n;
+    } else if (n > 1) {
+        DevBuf<int> cl_a, cl_b, nearest, creates, keeps, create_rank, keep_rank;
+        YB_CUDA(cl_a.alloc(n)); YB_CUDA(cl_b.alloc(n)); YB_CUDA(nearest.alloc(n)); YB_CUDA(creates.alloc(n)); YB_CUDA(keeps.alloc(n));
+        YB_CUDA(create_rank.alloc(n)); YB_CUDA(keep_rank.alloc(n));
+        k_iota<<<grid(n), B, 0, st>>>(cl_a.p, n);
+        int m = n, next_node = n;
+        int* cur = cl_a.p; int* nxt = cl_b.p;
+        while (m > 1) {
+            k_ploc_nearest<<<grid(m), 256, 0, st>>>(cur, m, exact.p, nearest.p);
+            k_ploc_flags<<<grid(m), B, 0, st>>>(nearest.p, m, creates.p, keeps.p);
+            tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, creates.p, create_rank.p, m, st));
+            tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, keeps.p, keep_rank.p, m, st));
+            int last[4];
+            YB_CUDA(cudaMemcpyAsync(&last[0], creates.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaMemcpyAsync(&last[1], create_rank.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaMemcpyAsync(&last[2], keeps.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaMemcpyAsync(&last[3], keep_rank.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaStreamSynchronize(st));
+            const int n_created = last[0] + last[1], m_next = last[2] + last[3];
+            if (n_created < 1 || m_next >= m) { err = "PLOC made no progress"; return false; }      // cannot happen: the globally best pair is mutual
+            k_ploc_merge<<<grid(m), B, 0, st>>>(cur, nearest.p, m, creates.p, create_rank.p, keeps.p, keep_rank.p, next_node, child.p, exact.p, padded.p, size.p, nxt);
+            next_node += n_created; m = m_next; rounds++;
+            int* t = cur; cur = nxt; nxt = t;
+        }
+        YB_CUDA(cudaMemcpyAsync(&root, cur, sizeof(int), cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        if (next_node != 2 * n - 1) { err = "PLOC node count mismatch"; return false; }
+    }
 
-    // breadth-first numbering
-    DevBuf<int> order, flags, rank, pair_of, first_child_bfs;
+    // ---- breadth-first numbering ----
+    DevBuf<int> order, flags, rank, pair_of, first_child_bfs, tfirst;
     YB_CUDA(order.alloc(2 * (size_t)n)); YB_CUDA(flags.alloc(2 * (size_t)n)); YB_CUDA(rank.alloc(2 * (size_t)n)); YB_CUDA(pair_of.alloc(n)); YB_CUDA(first_child_bfs.alloc(2 * (size_t)n));
-    const int root = n > 1 ? 0 : ~0;
+    YB_CUDA(tfirst.alloc(2 * (size_t)n));
     YB_CUDA(cudaMemcpyAsync(order.p, &root, sizeof(int), cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemsetAsync(tfirst.p + root, 0, sizeof(int), st));
     int level_begin = 0, m = 1, n_pairs = 0, depth = 0;
     while (m > 0) {
-        k_level_flags<<<grid(m), B, 0, st>>>(order.p + level_begin, m, range.p, leaf_max, flags.p);
-        tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
-        YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, rank.p, m, st));
+        k_level_flags<<<grid(m), B, 0, st>>>(order.p + level_begin, m, n, size.p, leaf_max, flags.p);
+        tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, rank.p, m, st));
         int last[2];
         YB_CUDA(cudaMemcpyAsync(&last[0], flags.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         YB_CUDA(cudaMemcpyAsync(&last[1], rank.p + m - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         YB_CUDA(cudaStreamSynchronize(st));
         const int n_in = last[0] + last[1];
-        k_level_expand<<<grid(m), B, 0, st>>>(order.p + level_begin, m, flags.p, rank.p, child.p, n_pairs, pair_of.p, order.p + level_begin + m);
-        k_first_child<<<grid(m), B, 0, st>>>(order.p, level_begin, m, flags.p, rank.p, level_begin + m, first_child_bfs.p);
+        k_level_expand<<<grid(m), B, 0, st>>>(order.p + level_begin, m, flags.p, rank.p, child.p, size.p, n, n_pairs, pair_of.p, tfirst.p,
+                                               order.p + level_begin + m, level_begin, level_begin + m, first_child_bfs.p);
         n_pairs += n_in; level_begin += m; m = 2 * n_in; depth++;
-        if (depth > YUNE_STACK_SIZE - 2) { err = "the linear BVH is deeper than the traversal stack (YUNE_STACK_SIZE): build the BVH on the host"; return false; }
+        if (depth > YUNE_STACK_SIZE - 2) { err = "the device-built BVH is deeper than the traversal stack (YUNE_STACK_SIZE): build the BVH on the host"; return false; }
     }
     const int n_nodes = level_begin;
     DevBuf<int> leaf_rank; YB_CUDA(leaf_rank.alloc(n_nodes));
-    k_leaf_flags<<<grid(n_nodes), B, 0, st>>>(order.p, n_nodes, range.p, leaf_max, flags.p);
-    tb = tmp_bytes > scan_bytes ? tmp_bytes : scan_bytes;
-    YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, leaf_rank.p, n_nodes, st));
+    k_leaf_flags<<<grid(n_nodes), B, 0, st>>>(order.p, n_nodes, n, size.p, leaf_max, flags.p);
+    tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, leaf_rank.p, n_nodes, st));
     const int n_leaves = n_nodes - n_pairs;
 
     DevBuf<yune_bvh_node> nodes; DevBuf<float4> pairs, leaf_boxes, tri_rec, shade; DevBuf<unsigned char> tri_class; DevBuf<int> ref_leaf, ref_rank;
@@ -342,20 +445,21 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
         YB_CUDA(cudaMemcpyAsync(ref_rank.p, ref->rank_of_tri, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
         YB_CUDA(cudaMemcpyAsync(leaf_boxes.p, ref->leaf_boxes, 2 * (size_t)ref->n_leaves * sizeof(float4), cudaMemcpyHostToDevice, st));
     }
-    k_emit<<<grid(n_nodes), B, 0, st>>>(order.p, first_child_bfs.p, n_nodes, n, leaf_max, child.p, range.p, pair_of.p, leaf_rank.p, exact.p, padded.p, sorted_tri.p, d_tris.p,
+    k_emit<<<grid(n_nodes), B, 0, st>>>(order.p, first_child_bfs.p, n_nodes, n, leaf_max, child.p, size.p, tfirst.p, pair_of.p, leaf_rank.p, exact.p, padded.p, sorted_tri.p, d_tris.p,
                                         nodes.p, pairs.p, leaf_boxes.p, tri_rec.p, ref ? ref_leaf.p : nullptr, ref ? ref_rank.p : nullptr);
     k_shade_records<<<grid(n), B, 0, st>>>(d_tris.p, n, d_mats, n_mats, shade.p, tri_class.p);
     Box root_box;
-    YB_CUDA(cudaMemcpyAsync(&root_box, padded.p + (n > 1 ? 0 : 0), sizeof(Box), cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaMemcpyAsync(&root_box, padded.p + root, sizeof(Box), cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaEventRecord(e1, st));
     YB_CUDA(cudaStreamSynchronize(st));
     YB_CUDA(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
 
     out.n_tris = n; out.n_nodes = ref ? 0 : n_nodes; out.n_inner = n_pairs; out.n_leaves = ref ? ref->n_leaves : n_leaves; out.depth = depth; out.build_ms = ms; out.leaf_max = leaf_max;
+    out.builder = builder; out.rounds = rounds;
     for (int k = 0; k < 3; k++) { out.root_lo[k] = root_box.lo[k]; out.root_hi[k] = root_box.hi[k]; }
     // the root: pair record 0, or -- a scene of <= leaf_max triangles -- one leaf
-    out.root_ref = n_pairs > 0 ? 0 : ~((0 << 4) | n);
+    out.root_ref = n_pairs > 0 ? 0 : ~((0 << 4) | n);      // (tfirst of the root is 0)
     out.nodes = nodes.release(); out.pairs = pairs.release(); out.leaf_boxes = leaf_boxes.release(); out.tris = tri_rec.release();
     out.shade = shade.release(); out.tri_class = tri_class.release();
     return true;

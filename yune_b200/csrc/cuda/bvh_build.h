@@ -16,6 +16,7 @@ struct GpuBvh {
     float4* leaf_boxes = nullptr; int n_leaves = 0;         // 2 x float4 per leaf: its box in `nodes`
     float4* shade = nullptr; unsigned char* tri_class = nullptr;   // by original triangle index
     int root_ref = 0, depth = 0, leaf_max = 2;
+    int builder = 1, rounds = 0;                            // 0 = LBVH (Karras), 1 = PLOC; PLOC merge rounds
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     float build_ms = 0;                                     // device time from the end of the triangle upload to the last kernel
     void free_all();
@@ -28,7 +29,7 @@ struct RefLeaves { const int* leaf_of_tri = nullptr; const int* rank_of_tri = nu
 
 // h_tris: the uploaded TriangleGPU records (host); d_mats: the uploaded Material records (device).
 bool buildBvhOnDevice(const yune_triangle* h_tris, int n_tris, const yune_material* d_mats, int n_mats, int leaf_max,
-                      cudaStream_t stream, GpuBvh& out, std::string& err, const RefLeaves* ref = nullptr);
+                      cudaStream_t stream, GpuBvh& out, std::string& err, const RefLeaves* ref = nullptr, int builder = 1);
 
 } // namespace yune
 #endif

@@ -93,7 +93,7 @@ struct yune_ctx {
     // carried into the next call (or yune_finish), so the pool stays full across calls instead of draining ~130 nearly empty
     // iterations per frame.  `epoch` counts everything that invalidates paths in flight (scene, camera, program, lights, image size,
     // options): a carry from another epoch is discarded.
-    int opt_pipeline = 0, opt_device_layout = -1;
+    int opt_pipeline = 0, opt_device_layout = -1, opt_device_builder = 1;
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
@@ -215,7 +215,7 @@ static int ensure_scene(yune_ctx* c)
         if (usable) {
             RefLeaves R; R.leaf_of_tri = leaf_of_tri.data(); R.rank_of_tri = rank_of_tri.data(); R.leaf_boxes = &leaf_boxes[0].x; R.n_leaves = (int)(leaf_boxes.size() / 2);
             GpuBvh G;
-            if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), c->opt_leaf_split > 0 ? c->opt_leaf_split : 2, c->stream, G, err, &R)) {
+            if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), c->opt_leaf_split > 0 ? c->opt_leaf_split : 2, c->stream, G, err, &R, c->opt_device_builder)) {
                 G.free_all();
                 Y_FAIL(c, YUNE_ERR_LIMIT, "device layout failed: %s", err.c_str());
             }
@@ -475,7 +475,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -495,6 +495,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_layout && v != *p) c->layout_dirty = true;
+    if (p == &c->opt_device_builder) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "device_builder must be 0 (linear BVH) or 1 (PLOC)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_deterministic && (v != 0) != (*p != 0) && c->d_sum) {
         // switching modes carries the image over: the fixed-point buffer is (re)built from the float sums, or dropped
@@ -534,7 +535,7 @@ int yune_build_bvh_on_device(yune_ctx* c, int leaf_max)
     c->epoch++;
     drop_device_bvh(c);
     std::string err;
-    if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err)) {
+    if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err, nullptr, c->opt_device_builder)) {
         c->gpu_bvh.free_all();
         Y_FAIL(c, YUNE_ERR_LIMIT, "device BVH build failed: %s", err.c_str());
     }

@@ -282,14 +282,14 @@ def test_sample_ranges_add_up_and_pool_size_is_invisible(gpu_manager):
     m.check(r._lib.yune_render(r._ctx, 0, 0, 1, r.seed, 0))
 
 
-@pytest.mark.parametrize("accel,leaf_split", [(0, 0), (0, 2), (1, 0), (2, 0), (2, 3)])
-def test_every_acceleration_mode_is_bit_exact(gpu_manager, oracle, accel, leaf_split):
-    """The walks (reference tree as is / with refined leaves / own tree + exact leaf-box filter / the same over 4-wide records)
-    against the oracle."""
+@pytest.mark.parametrize("accel,leaf_split,device_layout", [(0, 0, -1), (0, 2, -1), (1, 0, 0), (1, 0, 1), (2, 0, -1), (2, 3, -1)])
+def test_every_acceleration_mode_is_bit_exact(gpu_manager, oracle, accel, leaf_split, device_layout):
+    """The walks (reference tree as is / with refined leaves / own tree + exact leaf-box filter, the own tree built by the host's
+    binned-SAH builder or by the device's PLOC builder / the same over 4-wide records) against the oracle."""
     m = gpu_manager
     old = (m.getOption("accel"), m.getOption("leaf_split"))
     try:
-        m.setOption("accel", accel); m.setOption("leaf_split", leaf_split)
+        m.setOption("accel", accel); m.setOption("leaf_split", leaf_split); m.setOption("device_layout", device_layout)
         r, sc = _renderer(m, "teapot", 256, 256)
         tri, light, t = r.tracePrimary(1, 4711)
         otri, olight, ot, od, _ = oracle.primary(Oracle.config("udpt"), CAM, sc.vert_data, sc.bvh, 4711, 1, 256, 256)
@@ -303,8 +303,9 @@ def test_every_acceleration_mode_is_bit_exact(gpu_manager, oracle, accel, leaf_s
         tm = rng.uniform(0.001, 2.5, n).astype(np.float32)
         sa = r.traceRays(od6, tm, any_hit=True); sb = oracle.trace(Oracle.config("udpt"), od6, tm, 1, sc.vert_data, sc.bvh)
         assert (((sb[0] >= 0) | (sb[1] >= 0)) == (sa[0] >= 0)).all()
+        assert m.getOption("layout_built_on_device") == (1 if accel == 1 and device_layout != 0 else 0)
     finally:
-        m.setOption("accel", old[0]); m.setOption("leaf_split", old[1])
+        m.setOption("accel", old[0]); m.setOption("leaf_split", old[1]); m.setOption("device_layout", -1)
 
 
 def test_trace_result_independent_of_warp_scheduling(gpu_manager, oracle):

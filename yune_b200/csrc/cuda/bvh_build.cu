@@ -165,29 +165,29 @@ __global__ void k_fit(int n, const int2* child, const int* parent, Box* exact, B
 }
 
 // ---- PLOC (Meister & Bittner, "Parallel locally-ordered clustering for bounding volume hierarchy construction", TVCG 2018) ----
-// Bottom-up: the clusters stay in Morton order; every round each cluster looks for the neighbour within YB_PLOC_R positions whose
+// Bottom-up: the clusters stay in Morton order; every round each cluster looks for the neighbour within `radius` positions whose
 // union box has the smallest surface area, mutual nearest neighbours merge into a new inner node, the array is compacted.  The
 // merge criterion is the SAH's surface area, so large triangles find each other early instead of inflating a chain of boxes the
 // way they do in a Morton-split tree.
-#define YB_PLOC_R 16
+#define YB_PLOC_R_MAX 64      /* search radius: run-time (option "ploc_radius", default 16), at most this */
 __device__ __forceinline__ float box_area(const Box& b) { const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2]; return dx * dy + dx * dz + dy * dz; }
-__global__ void k_ploc_nearest(const int* cl, int m, const Box* exact, int* nearest)
+__global__ void k_ploc_nearest(const int* cl, int m, const Box* exact, int* nearest, const int R)
 {
-    __shared__ Box sb[256 + 2 * YB_PLOC_R];
-    const int base = blockIdx.x * 256 - YB_PLOC_R;
-    for (int t = threadIdx.x; t < 256 + 2 * YB_PLOC_R; t += 256) {
+    __shared__ Box sb[256 + 2 * YB_PLOC_R_MAX];
+    const int base = blockIdx.x * 256 - R;
+    for (int t = threadIdx.x; t < 256 + 2 * R; t += 256) {
         const int i = base + t;
         if (i >= 0 && i < m) sb[t] = exact[cl[i]];
     }
     __syncthreads();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
-    const Box me = sb[threadIdx.x + YB_PLOC_R];
+    const Box me = sb[threadIdx.x + R];
     float best = 3.0e38f; int best_j = -1;
-    for (int dj = -YB_PLOC_R; dj <= YB_PLOC_R; dj++) {
+    for (int dj = -R; dj <= R; dj++) {
         const int j = i + dj;
         if (dj == 0 || j < 0 || j >= m) continue;
-        const float a = box_area(box_union(me, sb[threadIdx.x + YB_PLOC_R + dj]));
+        const float a = box_area(box_union(me, sb[threadIdx.x + R + dj]));
         if (a < best) { best = a; best_j = j; }          // ties: the lower position (scan order)
     }
     nearest[i] = best_j;
@@ -338,8 +338,10 @@ void GpuBvh::free_all()
     pairs = tris = leaf_boxes = shade = nullptr; tri_class = nullptr; nodes = nullptr; n_nodes = n_inner = n_leaves = n_tris = 0;
 }
 
-bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err, const RefLeaves* ref, int builder)
+bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d_mats, int n_mats, int leaf_max, cudaStream_t st, GpuBvh& out, std::string& err, const RefLeaves* ref, int builder, int radius)
 {
+    if (radius < 1) radius = 32;
+    if (radius > YB_PLOC_R_MAX) radius = YB_PLOC_R_MAX;
     out.free_all();
     if (n < 1) { err = "no triangles"; return false; }
     if (n >= (1 << 27)) { err = "more than 2^27 triangles"; return false; }
@@ -388,7 +390,7 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
         int m = n, next_node = n;
         int* cur = cl_a.p; int* nxt = cl_b.p;
         while (m > 1) {
-            k_ploc_nearest<<<grid(m), 256, 0, st>>>(cur, m, exact.p, nearest.p);
+            k_ploc_nearest<<<grid(m), 256, 0, st>>>(cur, m, exact.p, nearest.p, radius);
             k_ploc_flags<<<grid(m), B, 0, st>>>(nearest.p, m, creates.p, keeps.p);
             tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, creates.p, create_rank.p, m, st));
             tb = tmp_cap; YB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, keeps.p, keep_rank.p, m, st));

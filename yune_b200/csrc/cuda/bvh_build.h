@@ -29,7 +29,7 @@ struct RefLeaves { const int* leaf_of_tri = nullptr; const int* rank_of_tri = nu
 
 // h_tris: the uploaded TriangleGPU records (host); d_mats: the uploaded Material records (device).
 bool buildBvhOnDevice(const yune_triangle* h_tris, int n_tris, const yune_material* d_mats, int n_mats, int leaf_max,
-                      cudaStream_t stream, GpuBvh& out, std::string& err, const RefLeaves* ref = nullptr, int builder = 1);
+                      cudaStream_t stream, GpuBvh& out, std::string& err, const RefLeaves* ref = nullptr, int builder = 1, int ploc_radius = 32);
 
 } // namespace yune
 #endif

@@ -59,6 +59,7 @@ struct yune_ctx {
     unsigned char* d_tri_class = nullptr;      // per original triangle: 1 = its material is specular (shade-stage sorting key)
     bool class_dirty = true;
     DevScene sc{};
+    int layout_built_on_device = 0;                  // the current layout's own tree came from bvh_build.cu (uploaded tree or device-built one)
     GpuBvh gpu_bvh; bool bvh_on_device = false;      // yune_build_bvh_on_device: the layout arrays below are the builder's (h_nodes is filled on demand)
     yune_cam cam{};
 
@@ -93,7 +94,7 @@ struct yune_ctx {
     // carried into the next call (or yune_finish), so the pool stays full across calls instead of draining ~130 nearly empty
     // iterations per frame.  `epoch` counts everything that invalidates paths in flight (scene, camera, program, lights, image size,
     // options): a carry from another epoch is discarded.
-    int opt_pipeline = 0, opt_device_layout = -1, opt_device_builder = 1;
+    int opt_pipeline = 0, opt_device_layout = -1, opt_device_builder = 1, opt_ploc_radius = 32;
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
@@ -203,28 +204,31 @@ static int ensure_scene(yune_ctx* c)
         Y_CUDA(c, cudaMemcpy(c->h_nodes.data(), c->gpu_bvh.nodes, c->h_nodes.size() * sizeof(yune_bvh_node), cudaMemcpyDeviceToHost));
         c->gpu_bvh.free_all(); c->bvh_on_device = false;
     }
-    // Big uploaded scenes: the walk's OWN tree (accel 1) is built on the device (bvh_build.cu) instead of by the host's binned-SAH
-    // builder -- at 10.5 M triangles the host re-layout is 5 s of every upload.  The uploaded tree still decides every hit: the
-    // triangle records carry its leaves / visiting ranks, the leaf-box filter tests its boxes (same soundness argument, it does
-    // not depend on the own tree's topology).  Option "device_layout": -1 (default) = from 2^20 triangles, 0 = never, 1 = always.
-    if (c->opt_accel == 1 && c->opt_isect == 0 && !c->h_nodes.empty() && !c->h_tris.empty()
-        && (c->opt_device_layout == 1 || (c->opt_device_layout < 0 && c->h_tris.size() >= ((size_t)1 << 20)))) {
+    // The walk's OWN tree (accel 1) is built on the device (bvh_build.cu, PLOC) rather than by the host's binned-SAH builder: at
+    // 10.5 M triangles the host re-layout is 5 s of every upload against 0.03 s, and the tree is as good (C4: trace 1.77 vs 1.76 ms
+    // per launch) or better (C2: 0.735 vs 0.749 ms).  The uploaded tree still decides every hit: the triangle records carry its
+    // leaves / visiting ranks, the leaf-box filter tests its boxes (the soundness argument does not depend on the own tree's
+    // topology).  Option "device_layout": -1 (default) / 1 = on the device when the uploaded tree allows it, 0 = on the host.
+    // A tree the device builder cannot take (deeper than the traversal stack) falls back to the host path.
+    if (c->opt_accel == 1 && c->opt_isect == 0 && !c->h_nodes.empty() && !c->h_tris.empty() && c->opt_device_layout != 0) {
         std::vector<int> leaf_of_tri, rank_of_tri; std::vector<F4> leaf_boxes; bool usable = false;
         if (!referenceLeavesForDevice(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), leaf_of_tri, rank_of_tri, leaf_boxes, usable, err))
             Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
         if (usable) {
             RefLeaves R; R.leaf_of_tri = leaf_of_tri.data(); R.rank_of_tri = rank_of_tri.data(); R.leaf_boxes = &leaf_boxes[0].x; R.n_leaves = (int)(leaf_boxes.size() / 2);
             GpuBvh G;
-            if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), c->opt_leaf_split > 0 ? c->opt_leaf_split : 2, c->stream, G, err, &R, c->opt_device_builder)) {
-                G.free_all();
-                Y_FAIL(c, YUNE_ERR_LIMIT, "device layout failed: %s", err.c_str());
+            if (buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), c->opt_leaf_split > 0 ? c->opt_leaf_split : 2, c->stream, G, err, &R, c->opt_device_builder, c->opt_ploc_radius)) {
+                adopt_device_layout(c, G);
+                c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
+                c->layout_dirty = false; c->class_dirty = false; c->layout_built_on_device = 1;
+                return YUNE_OK;
             }
-            adopt_device_layout(c, G);
-            c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
-            c->layout_dirty = false; c->class_dirty = false;
-            return YUNE_OK;
+            G.free_all();
+            cudaGetLastError();
+            err.clear();
         }
     }
+    c->layout_built_on_device = 0;
     if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
@@ -471,11 +475,11 @@ static int* option_slot(yune_ctx* c, const char* key)
 {
     if (!key) return nullptr;
     struct { const char* k; int* p; } tab[] = {
-        {"pool_slots", &c->opt_pool_slots}, {"pool_slots_in_use", &c->pool.n_slots}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
+        {"pool_slots", &c->opt_pool_slots}, {"pool_slots_in_use", &c->pool.n_slots}, {"layout_built_on_device", &c->layout_built_on_device}, {"smem_nodes", &c->opt_smem_nodes}, {"rr_threshold", &c->opt_rr_threshold},
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder}, {"ploc_radius", &c->opt_ploc_radius},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -487,7 +491,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (!p) Y_FAIL(c, YUNE_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
     const int v = (int)value;
     if (p == &c->opt_pool_slots && v != 0 && (v < 1024 || v > (1 << 26))) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots must be 0 (sized per job) or in [1024, 2^26]");
-    if (p == &c->pool.n_slots) Y_FAIL(c, YUNE_ERR_INVALID, "pool_slots_in_use is read-only");
+    if (p == &c->pool.n_slots || p == &c->layout_built_on_device) Y_FAIL(c, YUNE_ERR_INVALID, "%s is read-only", key);
     if (p == &c->opt_trace_block && (v < 32 || v > YUNE_TRACE_MAX_BLOCK || (v & 31))) Y_FAIL(c, YUNE_ERR_INVALID, "trace_block must be a multiple of 32 in [32, 1024]");
     if ((p == &c->opt_refill_idle || p == &c->opt_phase_min) && (v < 1 || v > 32) || (p == &c->opt_inner_min && (v < 1 || v > 33)) || (p == &c->opt_inner_chain && (v < 0 || v > 64))) Y_FAIL(c, YUNE_ERR_INVALID, "refill_idle / phase_min must be in [1, 32]");
     if (p == &c->opt_bdpt_bounces && (v < 2 || v > 32)) Y_FAIL(c, YUNE_ERR_INVALID, "bdpt_bounces must be in [2, 32]");
@@ -495,6 +499,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_layout && v != *p) c->layout_dirty = true;
+    if (p == &c->opt_ploc_radius) { if (v < 1 || v > 64) Y_FAIL(c, YUNE_ERR_INVALID, "ploc_radius must be in [1, 64]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_builder) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "device_builder must be 0 (linear BVH) or 1 (PLOC)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_deterministic && (v != 0) != (*p != 0) && c->d_sum) {
@@ -535,7 +540,7 @@ int yune_build_bvh_on_device(yune_ctx* c, int leaf_max)
     c->epoch++;
     drop_device_bvh(c);
     std::string err;
-    if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err, nullptr, c->opt_device_builder)) {
+    if (!buildBvhOnDevice(c->h_tris.data(), (int)c->h_tris.size(), reinterpret_cast<const yune_material*>(c->d_mats), (int)c->h_mats.size(), leaf_max, c->stream, c->gpu_bvh, err, nullptr, c->opt_device_builder, c->opt_ploc_radius)) {
         c->gpu_bvh.free_all();
         Y_FAIL(c, YUNE_ERR_LIMIT, "device BVH build failed: %s", err.c_str());
     }
@@ -543,7 +548,7 @@ int yune_build_bvh_on_device(yune_ctx* c, int leaf_max)
     c->bvh_on_device = true; c->h_nodes.clear();
     adopt_device_layout(c, G);
     c->lay = TravLayoutHost(); c->lay.accel = 1; c->lay.n_inner = G.n_inner; c->lay.n_tris = G.n_tris; c->lay.max_depth = G.depth;
-    c->have_nodes = true; c->layout_dirty = false; c->class_dirty = false;
+    c->have_nodes = true; c->layout_dirty = false; c->class_dirty = false; c->layout_built_on_device = 1;
     return YUNE_OK;
 }
 

@@ -94,7 +94,7 @@ struct yune_ctx {
     // carried into the next call (or yune_finish), so the pool stays full across calls instead of draining ~130 nearly empty
     // iterations per frame.  `epoch` counts everything that invalidates paths in flight (scene, camera, program, lights, image size,
     // options): a carry from another epoch is discarded.
-    int opt_pipeline = 0, opt_device_layout = -1, opt_device_builder = 1, opt_ploc_radius = 32;
+    int opt_pipeline = 0, opt_device_layout = -1, opt_device_builder = 1, opt_ploc_radius = 32, opt_own_tree_passes = -1;
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
@@ -208,9 +208,12 @@ static int ensure_scene(yune_ctx* c)
     // 10.5 M triangles the host re-layout is 5 s of every upload against 0.03 s, and the tree is as good (C4: trace 1.77 vs 1.76 ms
     // per launch) or better (C2: 0.735 vs 0.749 ms).  The uploaded tree still decides every hit: the triangle records carry its
     // leaves / visiting ranks, the leaf-box filter tests its boxes (the soundness argument does not depend on the own tree's
-    // topology).  Option "device_layout": -1 (default) / 1 = on the device when the uploaded tree allows it, 0 = on the host.
+    // topology).  Option "device_layout": 1 = on the device when the uploaded tree allows it, 0 = on the host, -1 (default) = on the
+    // device above 2^16 triangles; below, the host builder + reinsertion passes (relayout.cpp: OptTree) give the better tree for a
+    // few milliseconds (teapot: 25.2 -> 23.4 box tests per ray).
     // A tree the device builder cannot take (deeper than the traversal stack) falls back to the host path.
-    if (c->opt_accel == 1 && c->opt_isect == 0 && !c->h_nodes.empty() && !c->h_tris.empty() && c->opt_device_layout != 0) {
+    if (c->opt_accel == 1 && c->opt_isect == 0 && !c->h_nodes.empty() && !c->h_tris.empty()
+        && (c->opt_device_layout == 1 || (c->opt_device_layout < 0 && c->h_tris.size() > ((size_t)1 << 16)))) {
         std::vector<int> leaf_of_tri, rank_of_tri; std::vector<F4> leaf_boxes; bool usable = false;
         if (!referenceLeavesForDevice(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), leaf_of_tri, rank_of_tri, leaf_boxes, usable, err))
             Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
@@ -229,7 +232,7 @@ static int ensure_scene(yune_ctx* c)
         }
     }
     c->layout_built_on_device = 0;
-    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect))
+    if (!buildTravLayout(c->h_tris.data(), (int)c->h_tris.size(), c->h_nodes.data(), (int)c->h_nodes.size(), c->lay, err, c->opt_leaf_split, c->opt_accel, c->opt_isect, c->opt_own_tree_passes))
         Y_FAIL(c, YUNE_ERR_LIMIT, "BVH/triangle buffers rejected: %s", err.c_str());
     dfree(c->d_pairs); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_leaf_boxes);
     const TravLayoutHost& L = c->lay;
@@ -479,7 +482,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder}, {"ploc_radius", &c->opt_ploc_radius},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder}, {"ploc_radius", &c->opt_ploc_radius}, {"own_tree_passes", &c->opt_own_tree_passes},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -499,6 +502,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_layout && v != *p) c->layout_dirty = true;
+    if (p == &c->opt_own_tree_passes) { if (v < -1 || v > 16) Y_FAIL(c, YUNE_ERR_INVALID, "own_tree_passes must be in [-1, 16]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_ploc_radius) { if (v < 1 || v > 64) Y_FAIL(c, YUNE_ERR_INVALID, "ploc_radius must be in [1, 64]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_builder) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "device_builder must be 0 (linear BVH) or 1 (PLOC)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_leaf_split) { if (v < 0 || v > 10) Y_FAIL(c, YUNE_ERR_INVALID, "leaf_split must be in [0, 10]"); if (v != *p) c->layout_dirty = true; }

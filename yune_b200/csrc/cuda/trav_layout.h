@@ -68,11 +68,13 @@ struct TravLayoutHost {
 // n_nodes == 0: the reference's brute-force mode (udpt.cl:280-284).  Always built like accel 1, with ONE pseudo-leaf whose box
 //        every ray passes and visiting rank = triangle index: the hit records of the reference's loop over all triangles.
 //
+// own_opt_passes: reinsertion passes over the finished own tree (relayout.cpp: OptTree; accel 1 / 2); -1 = 2 up to 2^18 triangles, else 0.
+//
 // isect: 0 = the reference's Moller-Trumbore (parity mode: hit records bit-identical to the reference's);
 //        1 = watertight signed-volume test on the raw vertices, no leaf-box filter (perf mode, own tree only: accel 1).  Differs from
 //            mode 0 only for rays within rounding distance of an edge / vertex or of a reference box face (tests pin the rate).
 bool buildTravLayout(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,
-                     TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0, int isect = 0);
+                     TravLayoutHost& out, std::string& err, int leaf_split = 0, int accel = 0, int isect = 0, int own_opt_passes = -1);
 
 // Reference leaves of an uploaded tree in the form the device layout path (bvh_build.cu) takes them; see relayout.cpp.
 bool referenceLeavesForDevice(const yune_triangle* tris, int n_tris, const yune_bvh_node* nodes, int n_nodes,

@@ -1079,3 +1079,25 @@ def test_own_tree_built_on_the_device_keeps_the_uploaded_trees_hits(gpu_manager,
         np.testing.assert_array_equal(r.readSum(), img_host)
     finally:
         m.setOption("device_layout", -1); m.setOption("device_builder", 1)
+
+
+def test_rays_whose_origin_over_direction_overflows_on_device(gpu_manager, oracle):
+    """ADVICE r1 on the device: 1/d finite, o * (1/d) infinite (subnormal direction components): lane_init's guard sends the ray
+    through the guarded slab form; hit records are the oracle's, with the own tree built by either builder."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 64, 64)
+    rng = np.random.RandomState(3); n = 6000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1) * 8.0 + np.array([0, 0, 21.0])
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tiny = np.float32([1e-38, 3e-38, -2e-38, 1.2e-38])
+    for k in range(3):
+        d[k * 2000:(k + 1) * 2000, k] = tiny[rng.randint(0, 4, 2000)]
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    otri, olight, ot = oracle.trace(Oracle.config("udpt"), od, None, 0, sc.vert_data, sc.bvh)
+    try:
+        for dl in (0, 1):
+            m.setOption("device_layout", dl)
+            tri, light, t = r.traceRays(od)
+            assert (tri == otri).all() and (light == olight).all() and (_bits(t) == _bits(ot)).all(), dl
+    finally:
+        m.setOption("device_layout", -1)

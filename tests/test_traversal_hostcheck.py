@@ -450,3 +450,23 @@ def test_reference_leaves_for_the_device_layout(hc):
     assert hc.hc_reference_leaves(ptr(tris), n, ptr(shrunk), int(shrunk.size), ptr(leaf), ptr(rank), None, C.byref(nl)) == 0
     bad = nodes.copy(); bad["child_idx"][0] = nodes.size + 5
     assert hc.hc_reference_leaves(ptr(tris), n, ptr(bad), int(bad.size), ptr(leaf), ptr(rank), None, C.byref(nl)) == -1
+
+
+def test_rays_whose_origin_over_direction_overflows(hc, oracle):
+    """1/d finite but o * (1/d) = inf (|d_k| ~ 1e-38 next to |o_k| ~ 1e1): the fused slab test of the own tree would
+    see -inf on both planes of every box.  Such rays take the guarded form; hits must stay the oracle's."""
+    tris, mats, nodes = load_golden_scene("teapot")
+    rng = np.random.RandomState(3); n = 6000
+    o = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 0.98, n), rng.uniform(-4, -2, n)], 1) * 8.0 + np.array([0, 0, 21.0])
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tiny = np.float32([1e-38, 3e-38, -2e-38, 1.2e-38])
+    for k in range(3):
+        d[k * 2000:(k + 1) * 2000, k] = tiny[rng.randint(0, 4, 2000)]
+    od = np.concatenate([o, d], 1).astype(np.float32)
+    inv = 1.0 / od[:, 3:].astype(np.float64)
+    assert np.isfinite((1.0 / od[:, 3:]).astype(np.float32)).all() and (np.abs(od[:, :3] * inv.astype(np.float32)) == np.inf).any()
+    cfg = Oracle.config("udpt")
+    otri, olight, ot = oracle.trace(cfg, od, None, 0, tris, nodes)
+    for leaf_split, accel in ((0, 0), (0, 1), (0, 2)):
+        tri, light, t, _ = _trace(hc, od, None, 0, tris, nodes, leaf_split, accel)
+        assert (tri == otri).all() and (light == olight).all() and (t.view(np.uint32) == ot.view(np.uint32)).all(), (leaf_split, accel)

@@ -33,6 +33,9 @@ YUNE_HD RayPre make_ray(V3 o, V3 d)
     // finite <=> |x| < inf (false for NaN too)
     r.guard = !(fabsf(r.inv.x) < INFINITY && fabsf(r.inv.y) < INFINITY && fabsf(r.inv.z) < INFINITY);
     r.oi = v3(YF_MUL(o.x, r.inv.x), YF_MUL(o.y, r.inv.y), YF_MUL(o.z, r.inv.z));
+    // o * (1/d) can overflow although 1/d is finite (|d| ~ 1e-37 with |o| ~ 1e2): lo * inv - oi would then be -inf for both planes of
+    // a box and box_hit_own would lose it.  Such rays take the guarded subtract-then-multiply form too (kernels.cu: lane_init).
+    r.guard = r.guard || !(fabsf(r.oi.x) < INFINITY && fabsf(r.oi.y) < INFINITY && fabsf(r.oi.z) < INFINITY);
     return r;
 }
 

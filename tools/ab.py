@@ -32,7 +32,7 @@ if os.environ.get("YUNE_AB_CHILD"):
     for rep in range(2):
         st = r.enqueueKernels(spp, reset=True)
         n = max(st.timed_iterations, 1)
-        res = dict(msamples_s=round(st.samples / st.render_ms / 1e3, 1), ms=round(st.render_ms, 2), trace_ms=round(st.trace_ms / n, 4), shade_ms=round(st.shade_ms / n, 4),
+        res = dict(msamples_s=round(st.samples / st.render_ms / 1e3, 1), ms=round(st.render_ms, 2), trace_ms=round(st.trace_ms / n, 4), shade_ms=round(st.shade_ms / n, 4), sort_ms=round(st.sort_ms / n, 4),
                    iterations=int(st.iterations))
         if best is None or res["msamples_s"] > best["msamples_s"]:
             best = res

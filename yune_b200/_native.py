@@ -20,7 +20,7 @@ class Stats(C.Structure):
                 ("diffuse_visits", C.c_uint64), ("specular_visits", C.c_uint64), ("regenerations", C.c_uint64), ("slot_visits", C.c_uint64),
                 ("steady_iterations", C.c_uint32), ("steady_timed_iterations", C.c_uint32), ("steady_extend_rays", C.c_uint64),
                 ("steady_shadow_rays", C.c_uint64), ("steady_trace_ms", C.c_double), ("steady_shade_ms", C.c_double),
-                ("carried_paths", C.c_uint32), ("reserved0", C.c_uint32), ("finish_ms", C.c_double)]
+                ("carried_paths", C.c_uint32), ("reserved0", C.c_uint32), ("finish_ms", C.c_double), ("sort_ms", C.c_double)]
 
 
 class GroupStats(C.Structure):

@@ -332,6 +332,26 @@ template <class T> struct DevBuf {
 
 } // namespace
 
+// ---- option "sort_rays": the radix sort of a ray queue by origin cell lives here because this is the translation unit with cub ----
+size_t sort_pairs_tmp_bytes(int n_max)
+{
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, n_max, 0, 30);
+    return b;
+}
+cudaError_t sort_pairs_by_key(const unsigned* keys_in, unsigned* keys_out, const int* vals_in, int* vals_out, int n, int bits, void* tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    if (bits < 1) bits = 1;
+    if (bits > 30) bits = 30;
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, n, 30 - bits, 30, st);
+}
+cudaError_t launch_iota(int* p, int n, cudaStream_t st)
+{
+    if (n > 0) k_iota<<<(n + 255) / 256, 256, 0, st>>>(p, n);
+    return cudaGetLastError();
+}
+
 void GpuBvh::free_all()
 {
     cudaFree(pairs); cudaFree(tris); cudaFree(leaf_boxes); cudaFree(shade); cudaFree(tri_class); cudaFree(nodes);

@@ -98,6 +98,13 @@ struct yune_ctx {
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
+    // Option "sort_rays": both ray queues are sorted by the Morton cell of the ray origin between the shade and the trace kernel
+    // (cub radix sort on the top `sort_bits` bits of 30-bit keys).  For trees that do not fit the caches (C4: 0.9 GB of nodes and
+    // triangles) rays that start next to each other walk the same nodes; -1 = on when the tree is not fully staged in shared memory.
+    int opt_sort_rays = -1, opt_sort_bits = 18;
+    unsigned *d_eq_key = nullptr, *d_sq_key = nullptr, *d_key_tmp = nullptr; int *d_eq_sorted = nullptr, *d_sq_iota = nullptr, *d_sq_idx = nullptr;
+    void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; int sort_alloc = 0; int* h_cnt = nullptr;
+
     int occ_dense[2] = {0, 0}, occ_bdpt[2] = {0, 0};                           // shade-kernel occupancy caches
     int tc_variant = -1, tc_block = 0, tc_per_sm = 0; size_t tc_smem = 0;      // trace_config cache
 
@@ -112,9 +119,33 @@ struct yune_ctx {
 
 template <class T> static void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
+static void free_sort(yune_ctx* c)
+{
+    dfree(c->d_eq_key); dfree(c->d_sq_key); dfree(c->d_key_tmp); dfree(c->d_eq_sorted); dfree(c->d_sq_iota); dfree(c->d_sq_idx);
+    if (c->d_sort_tmp) { cudaFree(c->d_sort_tmp); c->d_sort_tmp = nullptr; }
+    c->sort_alloc = 0; c->sort_tmp_bytes = 0;
+}
+static int ensure_sort(yune_ctx* c)
+{
+    const int n = c->pool.n_slots;
+    if (c->sort_alloc >= n) return YUNE_OK;
+    free_sort(c);
+    const size_t N = (size_t)n;
+    Y_CUDA(c, cudaMalloc(&c->d_eq_key, N * 4)); Y_CUDA(c, cudaMalloc(&c->d_eq_sorted, N * 4));
+    Y_CUDA(c, cudaMalloc(&c->d_sq_key, 3 * N * 4)); Y_CUDA(c, cudaMalloc(&c->d_sq_iota, 3 * N * 4)); Y_CUDA(c, cudaMalloc(&c->d_sq_idx, 3 * N * 4));
+    Y_CUDA(c, cudaMalloc(&c->d_key_tmp, 3 * N * 4));
+    c->sort_tmp_bytes = sort_pairs_tmp_bytes(3 * n);
+    Y_CUDA(c, cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+    Y_CUDA(c, launch_iota(c->d_sq_iota, 3 * n, c->stream));
+    if (!c->h_cnt) Y_CUDA(c, cudaMallocHost(&c->h_cnt, 4 * sizeof(int)));
+    c->sort_alloc = n;
+    return YUNE_OK;
+}
+
 static void free_pool(yune_ctx* c)
 {
     PathPool& P = c->pool;
+    free_sort(c);
     dfree(P.ray_o.p); P.ray_d.p = nullptr; dfree(P.hit); dfree(P.thr.p); P.thr_next.p = nullptr; dfree(P.col.p); P.pend_l.p = nullptr;
     dfree(c->d_chunk_live);
     dfree(P.meta); dfree(P.evt_idx); dfree(P.vis_l); dfree(P.eq); dfree(P.sq_o); dfree(P.sq_d); dfree(P.evt); dfree(P.evt_vis);
@@ -355,6 +386,7 @@ void yune_destroy(yune_ctx* c)
     dfree(c->cap_eo); dfree(c->cap_ed); dfree(c->cap_so); dfree(c->cap_sd); dfree(c->cap_cnt);
     dfree(c->hk_o); dfree(c->hk_d); dfree(c->hk_hit); dfree(c->hk_tri); dfree(c->hk_light); dfree(c->hk_t); dfree(c->hk_od); dfree(c->hk_tmax); dfree(c->hk_vis); dfree(c->hk_cnt);
     if (c->h_tot) cudaFreeHost(c->h_tot);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -482,7 +514,7 @@ static int* option_slot(yune_ctx* c, const char* key)
         {"bdpt_bounces", &c->opt_bdpt_bounces}, {"oren_nayar", &c->opt_oren_nayar}, {"isect", &c->opt_isect},
         {"max_iterations", &c->opt_max_iterations}, {"count_work", &c->opt_count_work}, {"sync_every", &c->opt_sync_every},
         {"time_stages", &c->opt_time_stages}, {"trace_block", &c->opt_trace_block}, {"trace_blocks_per_sm", &c->opt_trace_blocks_per_sm},
-        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder}, {"ploc_radius", &c->opt_ploc_radius}, {"own_tree_passes", &c->opt_own_tree_passes},
+        {"refill_idle", &c->opt_refill_idle}, {"phase_min", &c->opt_phase_min}, {"inner_min", &c->opt_inner_min}, {"inner_chain", &c->opt_inner_chain}, {"leaf_split", &c->opt_leaf_split}, {"shade_blocks_per_sm", &c->opt_shade_blocks_per_sm}, {"accel", &c->opt_accel}, {"deterministic", &c->opt_deterministic}, {"pipeline", &c->opt_pipeline}, {"device_layout", &c->opt_device_layout}, {"device_builder", &c->opt_device_builder}, {"ploc_radius", &c->opt_ploc_radius}, {"own_tree_passes", &c->opt_own_tree_passes}, {"sort_rays", &c->opt_sort_rays}, {"sort_bits", &c->opt_sort_bits},
     };
     for (auto& t : tab) if (std::strcmp(t.k, key) == 0) return t.p;
     return nullptr;
@@ -502,6 +534,7 @@ int yune_set_option(yune_ctx* c, const char* key, double value)
     if (p == &c->opt_isect) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "isect must be 0 (the reference's Moller-Trumbore, bit-exact hit records) or 1 (watertight, perf mode; needs accel 1)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_accel) { if (v != 0 && v != 1 && v != 2) Y_FAIL(c, YUNE_ERR_INVALID, "accel must be 0 (walk the reference tree), 1 (own tree + exact leaf-box filter) or 2 (own tree, 4-wide records)"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_layout && v != *p) c->layout_dirty = true;
+    if (p == &c->opt_sort_bits && (v < 1 || v > 30)) Y_FAIL(c, YUNE_ERR_INVALID, "sort_bits must be in [1, 30]");
     if (p == &c->opt_own_tree_passes) { if (v < -1 || v > 16) Y_FAIL(c, YUNE_ERR_INVALID, "own_tree_passes must be in [-1, 16]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_ploc_radius) { if (v < 1 || v > 64) Y_FAIL(c, YUNE_ERR_INVALID, "ploc_radius must be in [1, 64]"); if (v != *p) c->layout_dirty = true; }
     if (p == &c->opt_device_builder) { if (v != 0 && v != 1) Y_FAIL(c, YUNE_ERR_INVALID, "device_builder must be 0 (linear BVH) or 1 (PLOC)"); if (v != *p) c->layout_dirty = true; }
@@ -625,6 +658,10 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     } else if (spp_count > 0) Y_CUDA(c, launch_pool_revive(c->pool, c->stream));      // slots the previous call's drain retired
     Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
+    // sorted ray queues (see yune_ctx::opt_sort_rays); the unidirectional integrator only
+    const bool sort_rays = c->integrator == INTEGRATOR_UDPT && (c->opt_sort_rays == 1 || (c->opt_sort_rays < 0 && c->sc.n_smem_pairs < c->sc.n_inner));
+    if (sort_rays) { if ((rc = ensure_sort(c)) != YUNE_OK) return rc; }
+    c->pool.eq_key = sort_rays ? c->d_eq_key : nullptr; c->pool.sq_key = sort_rays ? c->d_sq_key : nullptr;
     RenderArgs a = make_args(c);
     a.tail = 0; a.chunk_live = c->d_chunk_live; a.fix = det ? c->d_fix : nullptr;
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
@@ -640,7 +677,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     const int kMaxTimed = 128;
     int n_timed = 0;
     if (c->opt_time_stages > 0 && c->ev_pool.empty()) {
-        c->ev_pool.resize(3 * kMaxTimed);
+        c->ev_pool.resize(4 * kMaxTimed);
         for (auto& e : c->ev_pool) Y_CUDA(c, cudaEventCreate(&e));
     }
     Y_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -661,14 +698,32 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
             t.n_extend = &c->d_ctr[p].n_extend; t.fetch_extend = &c->d_ctr[p].fetch_extend;
             t.n_shadow = &c->d_ctr[p].n_shadow; t.fetch_shadow = &c->d_ctr[p].fetch_shadow;
             const bool timed = c->opt_time_stages > 0 && (it % c->opt_time_stages) == 0 && n_timed < kMaxTimed;
-            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed], c->stream));
+            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[4 * n_timed], c->stream));
             if (c->integrator == INTEGRATOR_BDPT) Y_CUDA(c, launch_shade_bdpt(a, c->bdpt, c->sm_count, c->occ_bdpt, c->stream));
             else Y_CUDA(c, launch_shade_dense(a, c->sm_count, c->opt_shade_blocks_per_sm, c->occ_dense, c->stream));
-            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 1], c->stream));
+            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[4 * n_timed + 1], c->stream));
             if (it == c->cap_iteration && c->cap_max > 0)
                 Y_CUDA(c, launch_capture(c->pool, c->d_ctr + p, c->cap_max, c->cap_eo, c->cap_ed, c->cap_so, c->cap_sd, c->cap_cnt, c->stream));
+            t.eq = c->pool.eq; t.sq_idx = nullptr;
+            if (sort_rays && !a.tail) {
+                // queue lengths to the host (an iteration of a scene this size is milliseconds long), then two radix sorts by origin cell
+                Y_CUDA(c, cudaMemcpyAsync(&c->h_cnt[0], &c->d_ctr[p].n_extend, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                Y_CUDA(c, cudaMemcpyAsync(&c->h_cnt[1], &c->d_ctr[p].n_shadow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                Y_CUDA(c, cudaStreamSynchronize(c->stream));
+                const int ne = c->h_cnt[0], ns = c->h_cnt[1];
+                if (ne > 0 && ne <= c->pool.n_slots) {
+                    Y_CUDA(c, sort_pairs_by_key(c->d_eq_key, c->d_key_tmp, c->pool.eq, c->d_eq_sorted, ne, c->opt_sort_bits, c->d_sort_tmp, c->sort_tmp_bytes, c->stream));
+                    t.eq = c->d_eq_sorted;
+                }
+                if (ns > 0 && (long long)ns <= 3ll * c->pool.n_slots) {
+                    Y_CUDA(c, sort_pairs_by_key(c->d_sq_key, c->d_key_tmp, c->d_sq_iota, c->d_sq_idx, ns, c->opt_sort_bits, c->d_sort_tmp, c->sort_tmp_bytes, c->stream));
+                    t.sq_idx = c->d_sq_idx;
+                }
+                st.kernel_launches += 2;
+            }
+            if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[4 * n_timed + 2], c->stream));
             Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, c->opt_count_work != 0, c->stream));
-            if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[3 * n_timed + 2], c->stream)); n_timed++; timed_it.push_back(it); }
+            if (timed) { Y_CUDA(c, cudaEventRecord(c->ev_pool[4 * n_timed + 3], c->stream)); n_timed++; timed_it.push_back(it); }
             Y_CUDA(c, launch_iter_end(c->d_ctr, c->d_tot, p, c->stream));
             st.kernel_launches += 3; st.trace_launches += 1;
         }
@@ -685,12 +740,13 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
         else if (!wait_all && a.tail) { done = true; c->carry = true; c->carry_epoch = c->epoch; c->carry_seed = seed; c->carry_gi = gi_check; }
         else if (it >= c->opt_max_iterations) Y_FAIL(c, YUNE_ERR_LIMIT, "yune_render: max_iterations (%d) reached with %d paths alive", c->opt_max_iterations, c->h_tot->live_last);
     }
-    float shade_ms = 0.f, trace_ms = 0.f;
+    float shade_ms = 0.f, trace_ms = 0.f, sort_ms = 0.f;
     for (int i = 0; i < n_timed; i++) {
-        float m1 = 0, m2 = 0;
-        cudaEventElapsedTime(&m1, c->ev_pool[3 * i], c->ev_pool[3 * i + 1]);
-        cudaEventElapsedTime(&m2, c->ev_pool[3 * i + 1], c->ev_pool[3 * i + 2]);
-        shade_ms += m1; trace_ms += m2;
+        float m1 = 0, m2 = 0, m3 = 0;
+        cudaEventElapsedTime(&m1, c->ev_pool[4 * i], c->ev_pool[4 * i + 1]);
+        cudaEventElapsedTime(&m3, c->ev_pool[4 * i + 1], c->ev_pool[4 * i + 2]);      // option "sort_rays": count read-back + the two radix sorts
+        cudaEventElapsedTime(&m2, c->ev_pool[4 * i + 2], c->ev_pool[4 * i + 3]);
+        shade_ms += m1; trace_ms += m2; sort_ms += m3;
         for (const auto& w : steady_windows)
             if (timed_it[i] >= w.first && timed_it[i] < w.second) { st.steady_shade_ms += m1; st.steady_trace_ms += m2; st.steady_timed_iterations++; break; }
     }
@@ -699,7 +755,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     Y_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     Y_CUDA(c, cudaEventSynchronize(c->ev1));
     float ms = 0; Y_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    st.render_ms = ms; st.shade_ms = shade_ms; st.trace_ms = trace_ms;
+    st.render_ms = ms; st.shade_ms = shade_ms; st.trace_ms = trace_ms; st.sort_ms = sort_ms;
     st.samples = c->h_tot->n_samples; st.extend_rays = c->h_tot->extend_rays; st.shadow_rays = c->h_tot->shadow_rays;
     st.diffuse_visits = c->h_tot->visits_d; st.specular_visits = c->h_tot->visits_s; st.regenerations = c->h_tot->visits_r;
     st.slot_visits = (uint64_t)c->pool.n_slots * (uint64_t)it;

@@ -133,6 +133,26 @@ __device__ __forceinline__ MatDev load_material(const float4* mats, int id)
     return m;
 }
 
+// 30-bit Morton code of a point inside the scene's (padded) root box: the sorting key of option "sort_rays" (rays that start
+// close to each other walk the same part of a tree that does not fit the caches).
+__device__ __forceinline__ unsigned spread10(unsigned x)
+{
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8))  & 0x0300f00fu;
+    x = (x | (x << 4))  & 0x030c30c3u;
+    x = (x | (x << 2))  & 0x09249249u;
+    return x;
+}
+__device__ __forceinline__ unsigned origin_key(const DevScene& sc, V3 o)
+{
+    const float ux = (o.x - sc.root_lo[0]) / (sc.root_hi[0] - sc.root_lo[0]), uy = (o.y - sc.root_lo[1]) / (sc.root_hi[1] - sc.root_lo[1]),
+                uz = (o.z - sc.root_lo[2]) / (sc.root_hi[2] - sc.root_lo[2]);
+    const unsigned qx = (unsigned)fminf(fmaxf(ux * 1024.0f, 0.0f), 1023.0f), qy = (unsigned)fminf(fmaxf(uy * 1024.0f, 0.0f), 1023.0f),
+                   qz = (unsigned)fminf(fmaxf(uz * 1024.0f, 0.0f), 1023.0f);
+    return (spread10(qx) << 2) | (spread10(qy) << 1) | spread10(qz);
+}
+
 struct ShadowOut { bool has; V3 o, d; float tmax; };
 
 // What evaluateDirectLighting (udpt.cl:535-609 == bdpt.cl:642-716) leaves to be resolved by rays:

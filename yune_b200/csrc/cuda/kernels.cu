@@ -384,7 +384,7 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
             const int q = chunk_next + __popc(idle & lane_lt);
             if (!have && q < chunk_end) {
                 float4 o, d;
-                if (ANY) { o = A.sq_o[q]; d = A.sq_d[q]; where = __float_as_int(d.w); }
+                if (ANY) { const int qq = A.sq_idx ? A.sq_idx[q] : q; o = A.sq_o[qq]; d = A.sq_d[qq]; where = __float_as_int(d.w); }
                 else { where = A.eq ? A.eq[q] : q; const size_t k = (size_t)where * A.ray_stride; o = A.ray_o[k]; d = A.ray_d[k]; }
                 lane_init<ANY, COUNT, ACCEL>(L, sc, o, d, wc, s_ray);
                 have = true;
@@ -651,14 +651,14 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
         const int cnt[1] = { has_ext ? 1 : 0 };
         int first[1];
         block_alloc<1, YUNE_NW>(counters, cnt, first, sh.cnt);
-        if (has_ext) P.eq[first[0]] = s;
+        if (has_ext) { P.eq[first[0]] = s; if (P.eq_key) P.eq_key[first[0]] = origin_key(A.sc, ext_o); }
     } else {
         const bool is_event = N.MV.has || N.MO.has;
         int* const counters[3] = { &C->n_extend, &C->n_shadow, &C->n_events };
         const int cnt[3] = { has_ext ? 1 : 0, (N.S.has ? 1 : 0) + (N.MV.has ? 1 : 0) + (N.MO.has ? 1 : 0), is_event ? 1 : 0 };
         int first[3];
         block_alloc<3, YUNE_NW>(counters, cnt, first, sh.cnt);
-        if (has_ext) P.eq[first[0]] = s;
+        if (has_ext) { P.eq[first[0]] = s; if (P.eq_key) P.eq_key[first[0]] = origin_key(A.sc, ext_o); }
         const int ev = A.parity * P.n_slots + first[2];
         if (is_event) {
             const int ef = (N.S.has ? YE_HAS_S : 0) | (N.MV.has ? YE_HAS_MV : 0) | (N.MO.has ? YE_HAS_MO : 0) | (N.mo_is_mv ? YE_MO_IS_MV : 0);
@@ -669,6 +669,10 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
             new_flags |= YF_PEND_EVT;
         } else if (N.S.has) new_flags |= YF_PEND_L;
         int qs = first[1];
+        if (P.sq_key) {                                     // the (up to three) shadow rays of a vertex share its origin cell
+            const unsigned key = origin_key(A.sc, N.S.has ? N.S.o : (N.MV.has ? N.MV.o : N.MO.o));
+            for (int k = 0; k < cnt[1]; k++) P.sq_key[qs + k] = key;
+        }
         if (N.S.has) {
             P.sq_o[qs] = f4(N.S.o, N.S.tmax);
             P.sq_d[qs] = f4(N.S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
@@ -721,6 +725,7 @@ __device__ __forceinline__ void regen_round(const RenderArgs& A, const int from,
             float rt = INFINITY;
             const int rl = light_loop(A.lights.l, A.lights.n, ro, rd, rt);
             P.eq[sh.ext_base + threadIdx.x] = s;
+            if (P.eq_key) P.eq_key[sh.ext_base + threadIdx.x] = origin_key(A.sc, ro);
             P.ray_o[s] = f4(ro, rt);
             P.ray_d[s] = f4(rd, __int_as_float(rl));
             P.meta[s] = make_uint4(pixel, sample, 0u, YS_TRACE | ((unsigned)(rl + 1) << YF_LID_SHIFT));

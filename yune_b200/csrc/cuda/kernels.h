@@ -23,6 +23,7 @@ struct TraceArgs {
     const int* n_extend; int* fetch_extend;
     // shadow rays (any hit): answer -> vis_a[target] (target >= 0) or vis_b[~target]; 1 = unoccluded
     const float4* sq_o; const float4* sq_d; unsigned char* vis_a; unsigned char* vis_b;
+    const int* sq_idx;    // option "sort_rays": shadow ray q is sq_o / sq_d[sq_idx[q]] (the queue sorted by origin cell), else NULL
     const int* n_shadow; int* fetch_shadow;
     Totals* tot;
     int refill_idle;      // refill a warp once this many of its lanes are idle
@@ -39,6 +40,10 @@ cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per
 cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, int* occ_cache, cudaStream_t st);
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st);
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
+// option "sort_rays" (bvh_build.cu, cub): values[0 .. n) reordered by the top `bits` bits of their 30-bit keys; tmp from sort_pairs_tmp_bytes
+size_t      sort_pairs_tmp_bytes(int n_max);
+cudaError_t sort_pairs_by_key(const unsigned* keys_in, unsigned* keys_out, const int* vals_in, int* vals_out, int n, int bits, void* tmp, size_t tmp_bytes, cudaStream_t st);
+cudaError_t launch_iota(int* p, int n, cudaStream_t st);
 cudaError_t launch_pool_revive(const PathPool& p, cudaStream_t st);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);
 cudaError_t launch_fix_to_sum(const long long* fix, float4* sum, size_t n, cudaStream_t st);

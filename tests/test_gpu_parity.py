@@ -1104,8 +1104,8 @@ def test_rays_whose_origin_over_direction_overflows_on_device(gpu_manager, oracl
 
 
 def test_sorted_ray_queues_do_not_change_the_image(gpu_manager):
-    """Option "sort_rays" (both ray queues radix-sorted by the Morton cell of the ray origin before the trace kernel; default for
-    scenes whose tree does not fit shared memory): the order in which rays are traced is invisible -- with fixed-point
+    """Option "sort_rays" (both ray queues radix-sorted by the Morton cell of the ray origin before the trace kernel; off by
+    default): the order in which rays are traced is invisible -- with fixed-point
     accumulation the image is bit for bit the unsorted one, for every number of key bits."""
     m = gpu_manager
     r, sc = _renderer(m, "teapot", 96, 96, opts="-DMIS", transmissive_teapot=True)
@@ -1118,4 +1118,4 @@ def test_sorted_ray_queues_do_not_change_the_image(gpu_manager):
             m.check(r._lib.yune_render(r._ctx, 0, 8, 1, r.seed, 1))
             np.testing.assert_array_equal(r.readSumFixed(), plain)
     finally:
-        m.setOption("sort_rays", -1); m.setOption("sort_bits", 18)
+        m.setOption("sort_rays", 0); m.setOption("sort_bits", 18)

@@ -98,10 +98,11 @@ struct yune_ctx {
     bool carry = false; unsigned epoch = 0, carry_epoch = 0; uint32_t carry_seed = 0; int carry_gi = 0;
     unsigned it_global = 0;                     // iterations since the pool was last reset: its parity selects the counter / event buffers
 
-    // Option "sort_rays": both ray queues are sorted by the Morton cell of the ray origin between the shade and the trace kernel
-    // (cub radix sort on the top `sort_bits` bits of 30-bit keys).  For trees that do not fit the caches (C4: 0.9 GB of nodes and
-    // triangles) rays that start next to each other walk the same nodes; -1 = on when the tree is not fully staged in shared memory.
-    int opt_sort_rays = -1, opt_sort_bits = 18;
+    // Option "sort_rays" = 1: both ray queues are sorted by the Morton cell of the ray origin between the shade and the trace kernel
+    // (cub radix sort on the top `sort_bits` bits of 30-bit keys), so that rays which start next to each other walk the same nodes
+    // of a tree that does not fit the caches.  MEASURED ON C4 (10.5 M triangles, profiles/r2_ab_c4_sort.log): the trace kernel gains
+    // 7 % (3.95 -> 3.67 ms per launch) and the sorts cost 0.53 ms + 0.08 ms of key writes: 754 vs 796 Msamples/s.  Off by default.
+    int opt_sort_rays = 0, opt_sort_bits = 18;
     unsigned *d_eq_key = nullptr, *d_sq_key = nullptr, *d_key_tmp = nullptr; int *d_eq_sorted = nullptr, *d_sq_iota = nullptr, *d_sq_idx = nullptr;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; int sort_alloc = 0; int* h_cnt = nullptr;
 
@@ -659,7 +660,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
 
     // sorted ray queues (see yune_ctx::opt_sort_rays); the unidirectional integrator only
-    const bool sort_rays = c->integrator == INTEGRATOR_UDPT && (c->opt_sort_rays == 1 || (c->opt_sort_rays < 0 && c->sc.n_smem_pairs < c->sc.n_inner));
+    const bool sort_rays = c->integrator == INTEGRATOR_UDPT && c->opt_sort_rays == 1;
     if (sort_rays) { if ((rc = ensure_sort(c)) != YUNE_OK) return rc; }
     c->pool.eq_key = sort_rays ? c->d_eq_key : nullptr; c->pool.sq_key = sort_rays ? c->d_sq_key : nullptr;
     RenderArgs a = make_args(c);

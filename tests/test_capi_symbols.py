@@ -64,6 +64,11 @@ def test_argument_errors_do_not_crash():
     assert lib.yune_setup(0, None) == -1
     assert lib.yune_render(None, 0, 1, 1, 0, 1) == -1
     assert lib.yune_get_stats(None, None) == -1
+    # round-2 entry points
+    assert lib.yune_finish(None) == -1
+    assert lib.yune_build_bvh_on_device(None, 2) == -1
+    assert lib.yune_bvh_info(None, None, None, None, None) == -1
+    assert lib.yune_read_bvh_buffer(None, None, 0) == -1
 
 
 def test_group_api_without_a_device_and_shard_rule():

@@ -424,6 +424,24 @@ def test_error_behaviour_on_device(gpu_manager):
         assert m.setupVertexBuffer(tris) and m.setupMatBuffer(mats) and m.setupBVHBuffer(bad) and m.setupImageBuffers(16, 16)
         m.setupCameraBuffer(yb.default_camera())
         assert r._lib.yune_render(m._ctx, 0, 1, 1, 0, 1) == -4            # malformed BVH rejected at upload, not traversed
+        # round-2 entry points: state errors, bad arguments
+        m2 = yb.CUDAManager().setup(0)
+        try:
+            assert m2.buildBVHOnDevice(2) is False and "vertex buffer" in m2.last_message        # nothing to build from
+            assert not m2._ok(m2._lib.yune_bvh_info(m2._ctx, None, None, None, None))
+            assert m2._ok(m2._lib.yune_finish(m2._ctx))                                           # nothing in flight: a no-op
+            assert m2.setupVertexBuffer(tris) and m2.setupMatBuffer(mats)
+            m2.setOption("accel", 0)
+            assert m2.buildBVHOnDevice(2) is False and "accel 1" in m2.last_message
+            m2.setOption("accel", 1)
+            assert m2.buildBVHOnDevice(2), m2.last_message
+            small = np.zeros(3, nodes.dtype)
+            assert not m2._ok(m2._lib.yune_read_bvh_buffer(m2._ctx, small.ctypes.data, 3)) and "capacity" in m2.last_message
+            for key, bad_value in (("isect", 2), ("device_builder", 5), ("ploc_radius", 0), ("sort_bits", 31), ("own_tree_passes", 99)):
+                assert not m2._ok(m2._lib.yune_set_option(m2._ctx, key.encode(), float(bad_value))), key
+            assert not m2._ok(m2._lib.yune_set_option(m2._ctx, b"layout_built_on_device", 1.0)) and "read-only" in m2.last_message
+        finally:
+            m2.close()
     finally:
         m.close()
 

@@ -213,6 +213,7 @@ int yune_group_create_postproc_program(yune_group* g, const char* kernel, const 
 int yune_group_setup_vertex_buffer(yune_group* g, const yune_triangle* tris, int n_triangles);
 int yune_group_setup_mat_buffer(yune_group* g, const yune_material* mats, int n_materials);
 int yune_group_setup_bvh_buffer(yune_group* g, const yune_bvh_node* nodes, int n_nodes);
+int yune_group_build_bvh_on_device(yune_group* g, int leaf_max);     /* instead of yune_group_setup_bvh_buffer */
 int yune_group_setup_camera_buffer(yune_group* g, const yune_cam* cam);
 int yune_group_setup_image_buffers(yune_group* g, int width, int height);
 int yune_group_set_light_sources(yune_group* g, const yune_quad_light* lights, int n_lights);

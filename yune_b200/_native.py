@@ -75,6 +75,7 @@ CUDA_API = {
     "yune_group_setup_vertex_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yune_group_setup_mat_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "yune_group_setup_bvh_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "yune_group_build_bvh_on_device": (C.c_int, [C.c_void_p, C.c_int]),
     "yune_group_setup_camera_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "yune_group_setup_image_buffers": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "yune_group_set_light_sources": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

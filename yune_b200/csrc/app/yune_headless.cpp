@@ -5,6 +5,8 @@
 //                 [--save-at N --save-at-out file [--save-at-ext .jpg|.png|.hdr]]     ("Save At Samples": image after N spp)
 //                 [--frame-by-frame [--pipeline]]   one yune_render per sample like the reference's viewer (src/RendererCore.cpp:483-486);
 //                                 --pipeline sets option "pipeline": a frame returns when its samples are handed out (yune_cuda.h)
+//                 [--device-bvh [--leaf-max N]]     build the BVH on the GPU (yune_build_bvh_on_device) instead of uploading the host-built one
+//                 [--option key=value ...]          any yune_set_option tunable (include/yune_cuda.h)
 //                 [--gpus N]     N > 1 (0 = every device): the sample range is sharded over N devices (yune_group_*), one ncclReduce
 #include "RendererCore.h"
 #include "ImageIO.h"
@@ -15,6 +17,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <utility>
 #include <vector>
 
 int main(int argc, char** argv)
@@ -22,7 +25,8 @@ int main(int argc, char** argv)
     std::string obj, kernel = "udpt.cl", opts, out, save_at_out, save_at_ext;
     int save_at = 0;
     int width = 1024, height = 1024, spp = 64, bins = 20, device = 0, gpus = 1;
-    unsigned seed = 12345; bool gi = true, frame_by_frame = false, pipeline = false; float fov = 60.0f;
+    unsigned seed = 12345; bool gi = true, frame_by_frame = false, pipeline = false, device_bvh = false; float fov = 60.0f; int leaf_max = 2;
+    std::vector<std::pair<std::string, double>> options;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { std::cerr << "missing value for " << a << "\n"; std::exit(2); } return argv[++i]; };
@@ -33,6 +37,8 @@ int main(int argc, char** argv)
         else if (a == "--fov") fov = (float)std::atof(next()); else if (a == "--out") out = next(); else if (a == "--no-gi") gi = false;
         else if (a == "--gpus") gpus = std::atoi(next());
         else if (a == "--frame-by-frame") frame_by_frame = true; else if (a == "--pipeline") pipeline = true;
+        else if (a == "--device-bvh") device_bvh = true; else if (a == "--leaf-max") leaf_max = std::atoi(next());
+        else if (a == "--option") { std::string kv = next(); const size_t eq = kv.find('='); if (eq == std::string::npos) { std::cerr << "--option needs key=value\n"; return 2; } options.push_back({kv.substr(0, eq), std::atof(kv.c_str() + eq + 1)}); }
         else if (a == "--save-at") save_at = std::atoi(next()); else if (a == "--save-at-out") save_at_out = next(); else if (a == "--save-at-ext") save_at_ext = next();
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
@@ -89,7 +95,15 @@ int main(int argc, char** argv)
         if (bins > 0 && bins != 20) core.render_scene.loadBVH(bins);
         core.render_scene.main_camera.y_FOV = fov; core.render_scene.main_camera.updateViewPlaneDist();
         std::cout << "Total Triangles Loaded: " << core.render_scene.vert_data.size() << "\nBVH Size: " << core.render_scene.bvh.gpu_node_list.size() << " Nodes\n";
+        for (const auto& kv : options)
+            if (yune_set_option(manager.ctx, kv.first.c_str(), kv.second) != YUNE_OK) { std::cerr << yune_last_error(manager.ctx) << "\n"; return 1; }
         if (!core.setup(gi)) { std::cerr << manager.last_message << "\n"; return 1; }
+        if (device_bvh) {
+            if (yune_build_bvh_on_device(manager.ctx, leaf_max) != YUNE_OK) { std::cerr << yune_last_error(manager.ctx) << "\n"; return 1; }
+            int n_nodes = 0, n_inner = 0, depth = 0; float ms = 0;
+            yune_bvh_info(manager.ctx, &n_nodes, &n_inner, &depth, &ms);
+            std::printf("BVH built on the device: %d nodes (%d inner), depth %d, %.2f ms\n", n_nodes, n_inner, depth, ms);
+        }
         if (frame_by_frame) {
             if (pipeline && yune_set_option(manager.ctx, "pipeline", 1) != YUNE_OK) { std::cerr << yune_last_error(manager.ctx) << "\n"; return 1; }
             if (!core.enqueueKernels(1, gi)) { std::cerr << manager.last_message << "\n"; return 1; }      // first frame: pool allocation

@@ -130,6 +130,7 @@ int yune_group_create_postproc_program(yune_group* g, const char* kernel, const 
 int yune_group_setup_vertex_buffer(yune_group* g, const yune_triangle* t, int n) { G_EACH(g, yune_setup_vertex_buffer(ctx, t, n)); }
 int yune_group_setup_mat_buffer(yune_group* g, const yune_material* m, int n) { G_EACH(g, yune_setup_mat_buffer(ctx, m, n)); }
 int yune_group_setup_bvh_buffer(yune_group* g, const yune_bvh_node* b, int n) { G_EACH(g, yune_setup_bvh_buffer(ctx, b, n)); }
+int yune_group_build_bvh_on_device(yune_group* g, int leaf_max) { G_EACH(g, yune_build_bvh_on_device(ctx, leaf_max)); }      // every rank builds the same (deterministic) tree
 int yune_group_setup_camera_buffer(yune_group* g, const yune_cam* cam) { G_EACH(g, yune_setup_camera_buffer(ctx, cam)); }
 int yune_group_setup_image_buffers(yune_group* g, int w, int h) { G_EACH(g, yune_setup_image_buffers(ctx, w, h)); }
 int yune_group_set_light_sources(yune_group* g, const yune_quad_light* l, int n) { G_EACH(g, yune_set_light_sources(ctx, l, n)); }

@@ -101,7 +101,7 @@ struct yune_ctx {
     // Option "sort_rays" = 1: both ray queues are sorted by the Morton cell of the ray origin between the shade and the trace kernel
     // (cub radix sort on the top `sort_bits` bits of 30-bit keys), so that rays which start next to each other walk the same nodes
     // of a tree that does not fit the caches.  MEASURED ON C4 (10.5 M triangles, profiles/r2_ab_c4_sort.log): the trace kernel gains
-    // 7 % (3.95 -> 3.67 ms per launch) and the sorts cost 0.53 ms + 0.08 ms of key writes: 754 vs 796 Msamples/s.  Off by default.
+    // 7 % (3.95 -> 3.67 ms per launch) and keys + sorts cost 0.6 ms: 754 vs 796 Msamples/s.  Off by default.
     int opt_sort_rays = 0, opt_sort_bits = 18;
     unsigned *d_eq_key = nullptr, *d_sq_key = nullptr, *d_key_tmp = nullptr; int *d_eq_sorted = nullptr, *d_sq_iota = nullptr, *d_sq_idx = nullptr;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; int sort_alloc = 0; int* h_cnt = nullptr;
@@ -662,7 +662,6 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
     // sorted ray queues (see yune_ctx::opt_sort_rays); the unidirectional integrator only
     const bool sort_rays = c->integrator == INTEGRATOR_UDPT && c->opt_sort_rays == 1;
     if (sort_rays) { if ((rc = ensure_sort(c)) != YUNE_OK) return rc; }
-    c->pool.eq_key = sort_rays ? c->d_eq_key : nullptr; c->pool.sq_key = sort_rays ? c->d_sq_key : nullptr;
     RenderArgs a = make_args(c);
     a.tail = 0; a.chunk_live = c->d_chunk_live; a.fix = det ? c->d_fix : nullptr;
     a.spp_begin = spp_begin; a.seed = seed; a.gi_check = gi_check;
@@ -712,6 +711,8 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
                 Y_CUDA(c, cudaMemcpyAsync(&c->h_cnt[1], &c->d_ctr[p].n_shadow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 Y_CUDA(c, cudaStreamSynchronize(c->stream));
                 const int ne = c->h_cnt[0], ns = c->h_cnt[1];
+                if (ne <= c->pool.n_slots && (long long)ns <= 3ll * c->pool.n_slots)
+                    Y_CUDA(c, launch_ray_keys(c->sc, c->pool, ne, ns, c->d_eq_key, c->d_sq_key, c->stream));
                 if (ne > 0 && ne <= c->pool.n_slots) {
                     Y_CUDA(c, sort_pairs_by_key(c->d_eq_key, c->d_key_tmp, c->pool.eq, c->d_eq_sorted, ne, c->opt_sort_bits, c->d_sort_tmp, c->sort_tmp_bytes, c->stream));
                     t.eq = c->d_eq_sorted;
@@ -720,7 +721,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
                     Y_CUDA(c, sort_pairs_by_key(c->d_sq_key, c->d_key_tmp, c->d_sq_iota, c->d_sq_idx, ns, c->opt_sort_bits, c->d_sort_tmp, c->sort_tmp_bytes, c->stream));
                     t.sq_idx = c->d_sq_idx;
                 }
-                st.kernel_launches += 2;
+                st.kernel_launches += 3;
             }
             if (timed) Y_CUDA(c, cudaEventRecord(c->ev_pool[4 * n_timed + 2], c->stream));
             Y_CUDA(c, launch_trace(t, tl.grid, tl.block, tl.smem, c->opt_count_work != 0, c->stream));

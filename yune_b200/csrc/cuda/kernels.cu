@@ -651,14 +651,14 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
         const int cnt[1] = { has_ext ? 1 : 0 };
         int first[1];
         block_alloc<1, YUNE_NW>(counters, cnt, first, sh.cnt);
-        if (has_ext) { P.eq[first[0]] = s; if (P.eq_key) P.eq_key[first[0]] = origin_key(A.sc, ext_o); }
+        if (has_ext) P.eq[first[0]] = s;
     } else {
         const bool is_event = N.MV.has || N.MO.has;
         int* const counters[3] = { &C->n_extend, &C->n_shadow, &C->n_events };
         const int cnt[3] = { has_ext ? 1 : 0, (N.S.has ? 1 : 0) + (N.MV.has ? 1 : 0) + (N.MO.has ? 1 : 0), is_event ? 1 : 0 };
         int first[3];
         block_alloc<3, YUNE_NW>(counters, cnt, first, sh.cnt);
-        if (has_ext) { P.eq[first[0]] = s; if (P.eq_key) P.eq_key[first[0]] = origin_key(A.sc, ext_o); }
+        if (has_ext) P.eq[first[0]] = s;
         const int ev = A.parity * P.n_slots + first[2];
         if (is_event) {
             const int ef = (N.S.has ? YE_HAS_S : 0) | (N.MV.has ? YE_HAS_MV : 0) | (N.MO.has ? YE_HAS_MO : 0) | (N.mo_is_mv ? YE_MO_IS_MV : 0);
@@ -669,10 +669,6 @@ __device__ __forceinline__ void surface_round(const RenderArgs& A, const int s, 
             new_flags |= YF_PEND_EVT;
         } else if (N.S.has) new_flags |= YF_PEND_L;
         int qs = first[1];
-        if (P.sq_key) {                                     // the (up to three) shadow rays of a vertex share its origin cell
-            const unsigned key = origin_key(A.sc, N.S.has ? N.S.o : (N.MV.has ? N.MV.o : N.MO.o));
-            for (int k = 0; k < cnt[1]; k++) P.sq_key[qs + k] = key;
-        }
         if (N.S.has) {
             P.sq_o[qs] = f4(N.S.o, N.S.tmax);
             P.sq_d[qs] = f4(N.S.d, __int_as_float(is_event ? ~(4 * ev + 0) : s));
@@ -725,7 +721,6 @@ __device__ __forceinline__ void regen_round(const RenderArgs& A, const int from,
             float rt = INFINITY;
             const int rl = light_loop(A.lights.l, A.lights.n, ro, rd, rt);
             P.eq[sh.ext_base + threadIdx.x] = s;
-            if (P.eq_key) P.eq_key[sh.ext_base + threadIdx.x] = origin_key(A.sc, ro);
             P.ray_o[s] = f4(ro, rt);
             P.ray_d[s] = f4(rd, __int_as_float(rl));
             P.meta[s] = make_uint4(pixel, sample, 0u, YS_TRACE | ((unsigned)(rl + 1) << YF_LID_SHIFT));
@@ -917,6 +912,15 @@ __global__ void k_hook_finish(int n, int any_hit, const float4* ray_o, const flo
     }
 }
 
+// option "sort_rays": the sorting keys of both queues (Morton cell of the ray origin), computed just before the sorts so that the
+// shade kernel carries no code for an option that is off by default
+__global__ void k_ray_keys(DevScene sc, PathPool P, int n_ext, int n_sh, unsigned* eq_key, unsigned* sq_key)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ext) eq_key[i] = origin_key(sc, xyz(P.ray_o[P.eq[i]]));
+    if (i < n_sh) sq_key[i] = origin_key(sc, xyz(P.sq_o[i]));
+}
+
 // Copies the first `max_rays` rays of this iteration's two queues into side buffers (measurement aid: the bench hands
 // them to the oracle, which counts the box/triangle tests of ITS ordered walk -- the roofline's work model).
 __global__ void k_capture(PathPool P, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts)
@@ -988,6 +992,12 @@ cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per
 cudaError_t launch_capture(const PathPool& p, const IterCounters* c, int max_rays, float4* ext_o, float4* ext_d, float4* sh_o, float4* sh_d, int* counts, cudaStream_t st)
 {
     k_capture<<<ceil_div(max_rays, 256), 256, 0, st>>>(p, c, max_rays, ext_o, ext_d, sh_o, sh_d, counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_ray_keys(const DevScene& sc, const PathPool& p, int n_ext, int n_sh, unsigned* eq_key, unsigned* sq_key, cudaStream_t st)
+{
+    const int n = n_ext > n_sh ? n_ext : n_sh;
+    if (n > 0) k_ray_keys<<<ceil_div(n, 256), 256, 0, st>>>(sc, p, n_ext, n_sh, eq_key, sq_key);
     return cudaGetLastError();
 }
 cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st)

@@ -44,6 +44,7 @@ cudaError_t launch_pool_reset(const PathPool& p, cudaStream_t st);
 size_t      sort_pairs_tmp_bytes(int n_max);
 cudaError_t sort_pairs_by_key(const unsigned* keys_in, unsigned* keys_out, const int* vals_in, int* vals_out, int n, int bits, void* tmp, size_t tmp_bytes, cudaStream_t st);
 cudaError_t launch_iota(int* p, int n, cudaStream_t st);
+cudaError_t launch_ray_keys(const DevScene& sc, const PathPool& p, int n_ext, int n_sh, unsigned* eq_key, unsigned* sq_key, cudaStream_t st);
 cudaError_t launch_pool_revive(const PathPool& p, cudaStream_t st);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t st);
 cudaError_t launch_fix_to_sum(const long long* fix, float4* sum, size_t n, cudaStream_t st);

@@ -83,8 +83,6 @@ struct PathPool {
     unsigned char* vis_l;   // 1 = NEE shadow ray reached the light (written by the trace kernel)
     // queues
     int*     eq;         // extension queue: slot indices
-    unsigned* eq_key;    // option "sort_rays": Morton code of each queued ray's origin (same index as eq), else NULL
-    unsigned* sq_key;    // likewise for the shadow queue
     float4*  sq_o;       // shadow queue: xyz origin, w = tmax
     float4*  sq_d;       // xyz direction, w = int bits: target (>= 0 slot -> vis_l ; < 0 -> ~target = event*4 + which)
     // MIS events (rare): 3 x float4 each: (Lv.xyz, flags), (BV.xyz, -), (BO.xyz, -); answers in evt_vis[4*e + which]

@@ -1154,3 +1154,23 @@ def test_sorted_ray_queues_do_not_change_the_image(gpu_manager):
             np.testing.assert_array_equal(r.readSumFixed(), plain)
     finally:
         m.setOption("sort_rays", 0); m.setOption("sort_bits", 18)
+
+
+def test_pipelined_frames_with_the_bidirectional_integrator(gpu_manager):
+    """Option "pipeline" with bdpt.cl: a BDPT slot carries its light path and pending connections across calls like a udpt slot
+    carries its ray; frames + yune_finish == one call, bit for bit."""
+    m = gpu_manager
+    r, sc = _renderer(m, "teapot", 64, 64, kernel="bdpt.cl")
+    r.seed = 13
+    lib, ctx = r._lib, r._ctx
+    N = 6
+    m.check(lib.yune_render(ctx, 0, N, 1, r.seed, 1)); whole = r.readSumFixed()
+    try:
+        m.setOption("pipeline", 1)
+        for f in range(N):
+            m.check(lib.yune_render(ctx, f, 1, 1, r.seed, 1 if f == 0 else 0))
+        r.finish()
+        np.testing.assert_array_equal(r.readSumFixed(), whole)
+    finally:
+        m.setOption("pipeline", 0)
+        m.createRenderProgram("udpt.cl")

@@ -369,7 +369,9 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     if (leaf_max > 10) leaf_max = 10;                         // vert_list holds 10 indices (include/CL_headers.h:88)
     const int B = 256;
     auto grid = [&](long long m) { return (unsigned)((m + B - 1) / B); };
-    cudaEvent_t e0, e1; YB_CUDA(cudaEventCreate(&e0)); YB_CUDA(cudaEventCreate(&e1));
+    struct Events { cudaEvent_t a = nullptr, b = nullptr; ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev;      // (freed on every return path)
+    YB_CUDA(cudaEventCreate(&ev.a)); YB_CUDA(cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
 
     DevBuf<yune_triangle> d_tris; YB_CUDA(d_tris.alloc(n));
     YB_CUDA(cudaMemcpyAsync(d_tris.p, h_tris, (size_t)n * sizeof(yune_triangle), cudaMemcpyHostToDevice, st));
@@ -475,7 +477,7 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     YB_CUDA(cudaEventRecord(e1, st));
     YB_CUDA(cudaStreamSynchronize(st));
     YB_CUDA(cudaGetLastError());
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
 
     out.n_tris = n; out.n_nodes = ref ? 0 : n_nodes; out.n_inner = n_pairs; out.n_leaves = ref ? ref->n_leaves : n_leaves; out.depth = depth; out.build_ms = ms; out.leaf_max = leaf_max;
     out.builder = builder; out.rounds = rounds;

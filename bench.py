@@ -480,11 +480,17 @@ def run_ours(args, cfg):
     cpu_v, kind = cpu_reference_run(cfg, (tris, mats, nodes, lights), cw, ch, cspp, cores) if world == 1 else (None, "reference")
     rays = agg["extend_rays"] + agg["shadow_rays"]
     # the reference's kernel on this very GPU (NVIDIA OpenCL), bounded: 16 frames of the config's image size
-    ref_ocl = None
-    if world == 1:
-        ref_ocl = reference_opencl_run(cfg, (tris, mats, nodes, lights), W, H, 16 if W * H <= (1 << 21) else 4)
-        ref_ocl["sample"] = "%dx%d, %d frames of 1 spp, reference RNG" % (W, H, ref_ocl.get("frames", 0)) if "unavailable" not in ref_ocl else None
-    frames = frame_times(m, lib, ctx, W, H) if world == 1 and not bdpt and W * H <= (1 << 21) else None
+    ref_ocl, frames = None, None
+    if world == 1:                       # side measurements: never allowed to cost the bench line
+        try:
+            ref_ocl = reference_opencl_run(cfg, (tris, mats, nodes, lights), W, H, 16 if W * H <= (1 << 21) else 4)
+            ref_ocl["sample"] = "%dx%d, %d frames of 1 spp, reference RNG" % (W, H, ref_ocl.get("frames", 0)) if "unavailable" not in ref_ocl else None
+        except Exception as e:
+            ref_ocl = {"unavailable": "reference_opencl_run raised %r" % (e,)}
+        try:
+            frames = frame_times(m, lib, ctx, W, H) if not bdpt and W * H <= (1 << 21) else None
+        except Exception as e:
+            frames = {"unavailable": "frame_times raised %r" % (e,)}
     line = {
         "metric": cfg["metric"], "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",

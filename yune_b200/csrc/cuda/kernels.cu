@@ -13,6 +13,7 @@
 //   k_hook_*       parity hooks: primary rays / arbitrary rays through the same k_trace.
 //
 // Tensor cores are not used: no stage is a dense contraction (every ray gathers its own nodes/triangles).
+#include <cstdlib>
 #include "kernel_common.cuh"
 #include "trace_core.h"
 
@@ -976,6 +977,14 @@ cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per
 {      // occ[2]: resident blocks per SM of the two instantiations, cached by the caller per context (0 = not asked yet)
     const int v = a.mis ? 1 : 0;
     if (occ[v] == 0) {
+        // The kernel needs 3 x 9.4 KB of shared memory per SM; left alone the driver configures 64 KB (ncu: launch__shared_mem_config_size),
+        // 32 KB of it taken from an L1 whose hit rate is 42 %.  Ask for the smallest carve-out that fits.
+        int carve = 13;                                  // per cent of 228 KB -> the 32 KB configuration
+        if (const char* e = getenv("YUNE_SHADE_CARVEOUT")) carve = atoi(e);
+        if (carve >= 0) {
+            if (v) cudaFuncSetAttribute(k_shade_dense<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            else   cudaFuncSetAttribute(k_shade_dense<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
         cudaError_t e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_dense<true>, YUNE_SHADE_BLOCK, 0)
                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], k_shade_dense<false>, YUNE_SHADE_BLOCK, 0);
         if (e != cudaSuccess) return e;

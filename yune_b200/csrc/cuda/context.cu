@@ -85,7 +85,7 @@ struct yune_ctx {
 
     // options
     int opt_pool_slots = 0, opt_smem_nodes = -1, opt_rr_threshold = -1, opt_bdpt_bounces = 20;
-    int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = 12, opt_phase_min = 24, opt_inner_min = 16, opt_inner_chain = 8;
+    int opt_trace_block = 1024, opt_trace_blocks_per_sm = 0, opt_refill_idle = YUNE_DEF_REFILL_IDLE, opt_phase_min = YUNE_DEF_PHASE_MIN, opt_inner_min = YUNE_DEF_INNER_MIN, opt_inner_chain = YUNE_DEF_INNER_CHAIN;
     int opt_leaf_split = 2, opt_accel = 1, opt_shade_blocks_per_sm = 0;
     int opt_oren_nayar = 0, opt_isect = 0, opt_max_iterations = 1 << 30, opt_count_work = 0, opt_sync_every = 8, opt_time_stages = 0, opt_deterministic = 1;
 
@@ -316,10 +316,11 @@ static int trace_config(yune_ctx* c, TraceLaunch& tl, bool count)
     if (tl.smem < 16) tl.smem = 16;
     // the attribute and the occupancy belong to ONE instantiation, block size and staging size: asked once per combination and
     // kept in the context (not in function statics: contexts live on different devices)
-    const int variant = trace_variant_id(c->sc, count);
+    const bool def_knobs = c->opt_refill_idle == YUNE_DEF_REFILL_IDLE && c->opt_phase_min == YUNE_DEF_PHASE_MIN && c->opt_inner_min == YUNE_DEF_INNER_MIN && c->opt_inner_chain == YUNE_DEF_INNER_CHAIN;
+    const int variant = trace_variant_id(c->sc, count, def_knobs);
     if (c->tc_variant != variant || c->tc_block != tl.block || c->tc_smem != tl.smem) {
         int per_sm = 0;
-        Y_CUDA(c, trace_prepare(c->sc, count, tl.block, tl.smem, &per_sm));
+        Y_CUDA(c, trace_prepare(c->sc, count, def_knobs, tl.block, tl.smem, &per_sm));
         if (per_sm < 1) Y_FAIL(c, YUNE_ERR_CUDA, "trace kernel does not fit on an SM with %zu bytes of shared memory", tl.smem);
         c->tc_variant = variant; c->tc_block = tl.block; c->tc_smem = tl.smem; c->tc_per_sm = per_sm;
     }

@@ -359,7 +359,10 @@ __device__ __forceinline__ void trace_queue(const TraceArgs& A, const uint32_t s
     const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
     const int fetch_chunk = min(YUNE_FETCH_CHUNK, max(8, ((n / n_warps) + 7) & ~7));
     int chunk_next = 0, chunk_end = 0;            // warp-uniform: the private range of queue entries still to hand out
-    const int refill_idle = A.refill_idle, tri_min = A.phase_min, inner_min = A.inner_min, inner_chain = A.inner_chain;
+    // ACCEL bit 4: the four scheduling knobs are at their defaults and compiled in as immediates (as kernel parameters they are
+    // re-read from the constant bank inside the step loop -- no register is free to hold them: trace -1.7 %)
+    const int refill_idle = (ACCEL & 16) ? YUNE_DEF_REFILL_IDLE : A.refill_idle, tri_min = (ACCEL & 16) ? YUNE_DEF_PHASE_MIN : A.phase_min,
+              inner_min = (ACCEL & 16) ? YUNE_DEF_INNER_MIN : A.inner_min, inner_chain = (ACCEL & 16) ? YUNE_DEF_INNER_CHAIN : A.inner_chain;
 
     for (;;) {
         // ---- retire finished rays ----
@@ -432,7 +435,10 @@ __global__ void __launch_bounds__(YUNE_TRACE_MAX_BLOCK, 1) k_trace(TraceArgs A)
     __syncthreads();
 
     WorkCount wc; wc.box = 0; wc.tri = 0;
-    const uint32_t a_box = (uint32_t)__cvta_generic_to_shared(s_box), a_ref = (uint32_t)__cvta_generic_to_shared(s_ref);
+    uint32_t a_box = (uint32_t)__cvta_generic_to_shared(s_box), a_ref = (uint32_t)__cvta_generic_to_shared(s_ref);
+    // Opaque to the compiler: otherwise ptxas re-derives this address from SR_CgaCtaId in every node step (S2R + MOV + LEA) instead
+    // of keeping it in a (uniform) register: trace -1.1 %.
+    asm volatile("mov.u32 %0, %0;" : "+r"(a_box));
     const uint32_t a_ray = a_box + 112u * (uint32_t)sc.n_smem_pairs + 16u * threadIdx.x;      // ACCEL bit 2: this thread's (o, u) record
     trace_queue<true, COUNT, ACCEL>(A, a_box, a_ref, a_ray, wc);      // shadow rays: any hit
     trace_queue<false, COUNT, ACCEL>(A, a_box, a_ref, a_ray, wc);     // extension rays: closest hit
@@ -942,28 +948,33 @@ static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); 
 // memory (no global node path compiled in), bit 2 = 4-wide records, bit 3 = watertight intersection instead of the filter + the
 // reference's Moller-Trumbore (isect 1, own binary tree only).
 typedef void (*TraceKernel)(TraceArgs);
-static TraceKernel trace_kernel(const DevScene& sc, bool count)
+static TraceKernel trace_kernel(const DevScene& sc, bool count, bool default_knobs)
 {
     const bool all_staged = sc.n_smem_pairs >= sc.n_inner;
+    if (default_knobs && !count && sc.isect == 0 && sc.accel == 1) return all_staged ? k_trace<false, 19> : k_trace<false, 17>;      // the two production variants
     if (sc.isect == 1) return count ? k_trace<true, 9> : (all_staged ? k_trace<false, 11> : k_trace<false, 9>);
     if (sc.accel == 2) return count ? k_trace<true, 5> : (all_staged ? k_trace<false, 7> : k_trace<false, 5>);
     if (sc.accel == 1) return count ? k_trace<true, 1> : (all_staged ? k_trace<false, 3> : k_trace<false, 1>);
     return count ? k_trace<true, 0> : k_trace<false, 0>;
 }
-int trace_variant_id(const DevScene& sc, bool count)
+static bool knobs_are_default(int refill_idle, int phase_min, int inner_min, int inner_chain)
 {
-    return sc.accel | (sc.n_smem_pairs >= sc.n_inner ? 4 : 0) | (count ? 8 : 0) | (sc.isect ? 16 : 0);
+    return refill_idle == YUNE_DEF_REFILL_IDLE && phase_min == YUNE_DEF_PHASE_MIN && inner_min == YUNE_DEF_INNER_MIN && inner_chain == YUNE_DEF_INNER_CHAIN;
+}
+int trace_variant_id(const DevScene& sc, bool count, bool default_knobs)
+{
+    return sc.accel | (sc.n_smem_pairs >= sc.n_inner ? 4 : 0) | (count ? 8 : 0) | (sc.isect ? 16 : 0) | (default_knobs ? 32 : 0);
 }
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st)
 {
-    trace_kernel(a.sc, count)<<<grid, block, smem_bytes, st>>>(a);
+    trace_kernel(a.sc, count, knobs_are_default(a.refill_idle, a.phase_min, a.inner_min, a.inner_chain))<<<grid, block, smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 // Shared-memory opt-in and resident blocks per SM of the instantiation that will be launched (the caller caches the answer per
 // (variant, block, smem) and per context).
-cudaError_t trace_prepare(const DevScene& sc, bool count, int block, size_t smem_bytes, int* blocks_per_sm)
+cudaError_t trace_prepare(const DevScene& sc, bool count, bool default_knobs, int block, size_t smem_bytes, int* blocks_per_sm)
 {
-    TraceKernel k = trace_kernel(sc, count);
+    TraceKernel k = trace_kernel(sc, count, default_knobs);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, block, smem_bytes);

@@ -4,6 +4,12 @@
 
 #include "wavefront_types.h"
 
+/* defaults of the trace kernel's scheduling knobs (options "refill_idle", "phase_min", "inner_min", "inner_chain"); with all four
+   at these values the kernel variants that have them compiled in are launched */
+#define YUNE_DEF_REFILL_IDLE 12
+#define YUNE_DEF_PHASE_MIN   24
+#define YUNE_DEF_INNER_MIN   16
+#define YUNE_DEF_INNER_CHAIN 8
 #define YUNE_TRACE_MAX_BLOCK  1024     /* k_trace is compiled for <= 64 registers so any block size up to this fits */
 #ifndef YUNE_SHADE_BLOCK
 #define YUNE_SHADE_BLOCK      256
@@ -33,8 +39,8 @@ struct TraceArgs {
 };
 
 cudaError_t launch_trace(const TraceArgs& a, int grid, int block, size_t smem_bytes, bool count, cudaStream_t st);
-cudaError_t trace_prepare(const DevScene& sc, bool count, int block, size_t smem_bytes, int* blocks_per_sm);
-int         trace_variant_id(const DevScene& sc, bool count);
+cudaError_t trace_prepare(const DevScene& sc, bool count, bool default_knobs, int block, size_t smem_bytes, int* blocks_per_sm);
+int         trace_variant_id(const DevScene& sc, bool count, bool default_knobs);
 cudaError_t launch_iter_end(IterCounters* ctr, Totals* tot, int parity, cudaStream_t st);
 cudaError_t launch_shade_dense(const RenderArgs& a, int sm_count, int blocks_per_sm, int* occ_cache, cudaStream_t st);   // persistent, in-block sorted (default)
 cudaError_t launch_shade_bdpt(const RenderArgs& a, const BdptPool& b, int sm_count, int* occ_cache, cudaStream_t st);

@@ -186,7 +186,7 @@ static int ensure_pool(yune_ctx* c, unsigned long long n_samples, bool keep)
         Y_CUDA(c, cudaMalloc(&c->bdpt.lp, N * V * 4 * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.pend_c, N * V * 16)); Y_CUDA(c, cudaMalloc(&c->bdpt.bmeta, N * 16));
     }
     Y_CUDA(c, cudaMalloc(&P.evt, 2 * 3 * N * 16)); Y_CUDA(c, cudaMalloc(&P.evt_vis, 2 * 4 * N));
-    Y_CUDA(c, cudaMalloc(&c->d_chunk_live, N / 256 + 1));
+    Y_CUDA(c, cudaMalloc(&c->d_chunk_live, N / YUNE_SHADE_BLOCK + 2));
     P.n_slots = n; c->pool_alloc = n; c->pool_integrator = c->integrator;
     return YUNE_OK;
 }
@@ -658,7 +658,7 @@ static int render_impl(yune_ctx* c, int spp_begin, int spp_count, int gi_check, 
         Y_CUDA(c, launch_pool_reset(c->pool, c->stream));
         c->it_global = 0;
     } else if (spp_count > 0) Y_CUDA(c, launch_pool_revive(c->pool, c->stream));      // slots the previous call's drain retired
-    Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / 256 + 1, c->stream));
+    Y_CUDA(c, cudaMemsetAsync(c->d_chunk_live, 1, (size_t)c->pool.n_slots / YUNE_SHADE_BLOCK + 2, c->stream));
 
     // sorted ray queues (see yune_ctx::opt_sort_rays); the unidirectional integrator only
     const bool sort_rays = c->integrator == INTEGRATOR_UDPT && c->opt_sort_rays == 1;

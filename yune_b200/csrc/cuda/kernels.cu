@@ -481,8 +481,10 @@ enum { YL_DIFFUSE = 0, YL_SPECULAR = 1 };
 
 
 struct DenseShared {
-    int surf[2][2 * YUNE_SHADE_BLOCK];      // diffuse / specular surface hits waiting for a full round
-    int regen[4 * YUNE_SHADE_BLOCK];        // slots waiting for a fresh sample (fed by A, D and S)
+    // A classify phase adds up to YUNE_CLASSIFY_N blocks of entries to < 1 block of leftovers; the regeneration list is emptied to
+    // < 1 block before every surface round (which adds at most one block to it).
+    int surf[2][(YUNE_CLASSIFY_N + 1) * YUNE_SHADE_BLOCK];      // diffuse / specular surface hits waiting for a full round
+    int regen[(YUNE_CLASSIFY_N + 1) * YUNE_SHADE_BLOCK];        // slots waiting for a fresh sample (fed by A, D and S)
     int n_surf[2], n_regen;
     int cnt[3 * (YUNE_NW + 1)];             // block_alloc scratch
     unsigned long long sample_base; int ext_base;
@@ -491,19 +493,36 @@ struct DenseShared {
 
 // phase A for one slot
 // Returns whether the slot goes on to a surface round (it may stay in flight).
-__device__ __forceinline__ bool classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
+struct ClassifyIn { uint4 meta; float hit_w; unsigned char vis_l; bool valid, spec; float4 col, thr, pend; };
+// the loads of phase A, all independent of each other: issued together (and, with YUNE_CLASSIFY2, for two slots at once)
+__device__ __forceinline__ ClassifyIn classify_load(const RenderArgs& A, const int s)
 {
     const PathPool& P = A.pool;
-    const bool valid = s < P.n_slots;
-    const uint4 meta = valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
-    const float hit_w = valid ? P.hit[s].w : 0.0f;                             // unconditional: in flight together with meta
-    const unsigned char vis_l = valid ? P.vis_l[s] : 0;                        // likewise: saves the pending-NEE path one dependent round trip
+    ClassifyIn in;
+    in.valid = s < P.n_slots;
+    in.meta = in.valid ? P.meta[s] : make_uint4(0, 0, 0, YS_DONE);
+    in.hit_w = in.valid ? P.hit[s].w : 0.0f;                                   // unconditional: in flight together with meta
+    in.vis_l = in.valid ? P.vis_l[s] : 0;                                      // likewise: saves the pending-NEE path one dependent round trip
     // Speculative: the state a pending NEE answer needs is requested before the flags are known (one dependent round trip less
     // for the ~half of the slots that have one).  Not while the pool drains (A.tail): most slots are DONE then and the scan
     // itself is what an iteration costs.
-    const bool spec = valid && !A.tail;
-    float4 spec_col = make_float4(0, 0, 0, 0), spec_thr = spec_col, spec_pend = spec_col;
-    if (spec) { spec_col = P.col[s]; spec_thr = P.thr[s]; spec_pend = P.pend_l[s]; }
+    in.spec = in.valid && !A.tail;
+    in.col = make_float4(0, 0, 0, 0); in.thr = in.col; in.pend = in.col;
+    if (in.spec) { in.col = P.col[s]; in.thr = P.thr[s]; in.pend = P.pend_l[s]; }
+    return in;
+}
+__device__ __forceinline__ bool classify_finish(const RenderArgs& A, const int s, const ClassifyIn& in, DenseShared& sh);
+__device__ __forceinline__ bool classify_slot(const RenderArgs& A, const int s, DenseShared& sh)
+{
+    const ClassifyIn in = classify_load(A, s);
+    return classify_finish(A, s, in, sh);
+}
+__device__ __forceinline__ bool classify_finish(const RenderArgs& A, const int s, const ClassifyIn& in, DenseShared& sh)
+{
+    const PathPool& P = A.pool;
+    const bool valid = in.valid, spec = in.spec;
+    const uint4 meta = in.meta; const float hit_w = in.hit_w; const unsigned char vis_l = in.vis_l;
+    float4 spec_col = in.col, spec_thr = in.thr, spec_pend = in.pend;
     const unsigned state = meta.w & YS_STATE_MASK;
     bool to_regen = valid && state == YS_FREE, to_d = false, to_s = false;
     if (state == YS_TRACE || state == YS_DRAIN) {
@@ -746,39 +765,56 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
     const int tid = threadIdx.x;
     if (tid == 0) { sh.n_surf[0] = sh.n_surf[1] = 0; sh.n_regen = 0; sh.visits[0] = sh.visits[1] = sh.visits[2] = 0; }
     __syncthreads();
-    const int n_chunks = (A.pool.n_slots + YUNE_SHADE_BLOCK - 1) / YUNE_SHADE_BLOCK;
+    // A chunk is YUNE_CLASSIFY_N blocks of slots: every thread classifies N slots with all their (independent) loads in flight
+    // together.  Phase A is where the kernel waits for DRAM (per-line stall view: the first use of meta / hit and the barrier after
+    // it); two slots per thread: 1.162 -> 1.129 ms per launch (profiles/r2_ab_shade_classify2.log).
+    const int CH = YUNE_CLASSIFY_N * YUNE_SHADE_BLOCK;
+    const int n_chunks = (A.pool.n_slots + CH - 1) / CH;
     int live = 0;                                   // slots this thread left in flight (TRACE or DRAIN)
     for (int chunk = blockIdx.x; ; chunk += gridDim.x) {
         const bool flush = chunk >= n_chunks;       // block-uniform: the pass after the last chunk empties the lists
-        // While the pool drains (A.tail: every sample has been handed out) a chunk whose 256 slots had nothing in flight after the
+        // While the pool drains (A.tail: every sample has been handed out) a chunk whose slots had nothing in flight after the
         // previous iteration is skipped by reading one byte.
         if (!flush && A.tail && A.chunk_live[chunk] == 0) continue;
         bool cont = false;
-        if (!flush) cont = classify_slot(A, chunk * YUNE_SHADE_BLOCK + tid, sh);
+        if (!flush) {
+            ClassifyIn in[YUNE_CLASSIFY_N];
+            #pragma unroll
+            for (int j = 0; j < YUNE_CLASSIFY_N; j++) in[j] = classify_load(A, chunk * CH + j * YUNE_SHADE_BLOCK + tid);
+            #pragma unroll
+            for (int j = 0; j < YUNE_CLASSIFY_N; j++) cont = classify_finish(A, chunk * CH + j * YUNE_SHADE_BLOCK + tid, in[j], sh) || cont;
+        }
         if (A.tail && !flush) {
             const int any = __syncthreads_or(cont ? 1 : 0);
             if (tid == 0) A.chunk_live[chunk] = any ? 1 : 0;
         } else __syncthreads();
-        YUNE_NO_UNROLL
-        for (int k = 0; k < 2; k++) {
-            const int n = sh.n_surf[k];
-            if (n >= YUNE_SHADE_BLOCK || (flush && n > 0)) {
-                const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
-                const int s = tid < take ? sh.surf[k][n - take + tid] : -1;
-                __syncthreads();
-                if (tid == 0) { sh.n_surf[k] = n - take; sh.visits[k] += take; }
-                if (k == YL_DIFFUSE) surface_round<MIS, false>(A, s, sh, live);
-                else                 surface_round<MIS, true>(A, s, sh, live);
-                __syncthreads();
-            }
-        }
         for (;;) {
-            const int n = sh.n_regen;
-            if (!(n >= YUNE_SHADE_BLOCK || (flush && n > 0))) break;
-            const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
-            __syncthreads();
-            if (tid == 0) { sh.n_regen = n - take; sh.visits[2] += take; }
-            regen_round(A, n - take, take, sh, live);
+            // regeneration rounds first: keeps that list below one block before a surface round adds to it
+            for (;;) {
+                const int n = sh.n_regen;
+                if (!(n >= YUNE_SHADE_BLOCK || (flush && n > 0))) break;
+                const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
+                __syncthreads();
+                if (tid == 0) { sh.n_regen = n - take; sh.visits[2] += take; }
+                regen_round(A, n - take, take, sh, live);
+            }
+            bool did = false;
+            YUNE_NO_UNROLL
+            for (int k = 0; k < 2; k++) {
+                const int n = sh.n_surf[k];
+                if (n >= YUNE_SHADE_BLOCK || (flush && n > 0)) {
+                    const int take = n < YUNE_SHADE_BLOCK ? n : YUNE_SHADE_BLOCK;
+                    const int s = tid < take ? sh.surf[k][n - take + tid] : -1;
+                    __syncthreads();
+                    if (tid == 0) { sh.n_surf[k] = n - take; sh.visits[k] += take; }
+                    if (k == YL_DIFFUSE) surface_round<MIS, false>(A, s, sh, live);
+                    else                 surface_round<MIS, true>(A, s, sh, live);
+                    __syncthreads();
+                    did = true;
+                    break;                          // back to the regeneration list before the next surface round
+                }
+            }
+            if (!did) break;
         }
         if (flush) break;
         __syncthreads();                            // every warp has read the list counts before the next chunk's classify bumps them

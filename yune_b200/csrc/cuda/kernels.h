@@ -14,6 +14,9 @@
 #ifndef YUNE_SHADE_BLOCK
 #define YUNE_SHADE_BLOCK      256
 #endif
+#ifndef YUNE_CLASSIFY_N
+#define YUNE_CLASSIFY_N       2        /* slots a thread of k_shade_dense classifies per chunk (see the kernel) */
+#endif
 #ifndef YUNE_SHADE_MIN_BLOCKS
 #define YUNE_SHADE_MIN_BLOCKS 3
 #endif

@@ -781,8 +781,19 @@ __global__ void __launch_bounds__(YUNE_SHADE_BLOCK, YUNE_SHADE_MIN_BLOCKS) k_sha
             ClassifyIn in[YUNE_CLASSIFY_N];
             #pragma unroll
             for (int j = 0; j < YUNE_CLASSIFY_N; j++) in[j] = classify_load(A, chunk * CH + j * YUNE_SHADE_BLOCK + tid);
+#if YUNE_CLASSIFY_N == 2
+            // ONE copy of the finish code, the slot's loaded state picked by selects: the kernel's hot path is instruction-cache
+            // bound (no_instruction is its second-largest stall) and the unrolled form costs 300 SASS lines: 1.112 -> 1.081 ms
+            #pragma unroll 1
+            for (int j = 0; j < 2; j++) {
+                ClassifyIn x = in[0];
+                if (j) x = in[1];
+                cont = classify_finish(A, chunk * CH + j * YUNE_SHADE_BLOCK + tid, x, sh) || cont;
+            }
+#else
             #pragma unroll
             for (int j = 0; j < YUNE_CLASSIFY_N; j++) cont = classify_finish(A, chunk * CH + j * YUNE_SHADE_BLOCK + tid, in[j], sh) || cont;
+#endif
         }
         if (A.tail && !flush) {
             const int any = __syncthreads_or(cont ? 1 : 0);

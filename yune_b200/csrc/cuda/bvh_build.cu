@@ -80,7 +80,7 @@ __global__ void k_tri_boxes(const yune_triangle* tris, int n, Box* exact, Box* p
     }
 }
 
-__global__ void k_morton(const Box* exact_unpadded_src, const yune_triangle* tris, int n, const float* scene_lo, const float* scene_hi, unsigned long long* keys, int* idx)
+__global__ void k_morton(const yune_triangle* tris, int n, const float* scene_lo, const float* scene_hi, unsigned long long* keys, int* idx)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -384,7 +384,7 @@ bool buildBvhOnDevice(const yune_triangle* h_tris, int n, const yune_material* d
     k_tri_boxes<<<grid(n), B, 0, st>>>(d_tris.p, n, tri_exact.p, tri_padded.p, scene.p, scene.p + 3);
     DevBuf<unsigned long long> keys, keys_sorted; DevBuf<int> idx, sorted_tri;
     YB_CUDA(keys.alloc(n)); YB_CUDA(keys_sorted.alloc(n)); YB_CUDA(idx.alloc(n)); YB_CUDA(sorted_tri.alloc(n));
-    k_morton<<<grid(n), B, 0, st>>>(tri_exact.p, d_tris.p, n, scene.p, scene.p + 3, keys.p, idx.p);
+    k_morton<<<grid(n), B, 0, st>>>(d_tris.p, n, scene.p, scene.p + 3, keys.p, idx.p);
     size_t tmp_bytes = 0, scan_bytes = 0;
     YB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, idx.p, sorted_tri.p, n, 0, 63, st));
     YB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, 2 * n, st));
